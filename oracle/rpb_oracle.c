@@ -1,0 +1,1040 @@
+/*
+ * rpb_oracle.c -- CPU restatement of the RAJAPerf hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY: the parity checker for the Base_B200 variant.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * leg may load it; the product (rajaperf_b200/) never does.
+ *
+ * Parity pin: every orc_kat_* driver below reproduces the Base_Seq checksum the
+ * reference's own build prints (tests/golden/ref_checksums.json, BASELINE.md
+ * section 2) -- see tests/test_oracle_kat.py.
+ *
+ * All file:line citations are relative to /root/reference/src.  Build with
+ * -O2 -ffp-contract=off (no FMA contraction, no value-changing FP optimisation)
+ * to match the reference's x86-64 Base_Seq arithmetic.
+ */
+#include "rpb_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* ======================================================================== */
+/* Synthetic inputs (common/DataUtils.cpp)                                   */
+/* ======================================================================== */
+
+/* DataUtils.cpp:131-147: one global counter, reset by KernelBase::execute
+ * (KernelBase.cpp:366), bumped by every init call of any type.              */
+static int g_init_count = 0;
+
+void orc_reset_init_count(void) { g_init_count = 0; }
+int  orc_get_init_count(void)   { return g_init_count; }
+
+static double parity_factor(void) { return (g_init_count % 2) ? 0.1 : 0.2; }
+
+/* DataUtils.cpp:504-513 */
+void orc_init_real(double* p, int64_t n)
+{
+  const double f = parity_factor();
+  for (int64_t i = 0; i < n; ++i) p[i] = f * (i + 1.1) / (i + 1.12345);
+  g_init_count++;
+}
+
+/* DataUtils.cpp:518-525 */
+void orc_init_const(double* p, int64_t n, double v)
+{
+  for (int64_t i = 0; i < n; ++i) p[i] = v;
+  g_init_count++;
+}
+
+/* DataUtils.cpp:560-569 : glibc rand(), re-seeded on every call */
+void orc_init_rand_value(double* p, int64_t n)
+{
+  srand(4793);
+  for (int64_t i = 0; i < n; ++i) p[i] = (double)rand() / RAND_MAX;
+  g_init_count++;
+}
+
+/* DataUtils.cpp:542-555 */
+void orc_init_rand_sign(double* p, int64_t n)
+{
+  const double f = parity_factor();
+  srand(4793);
+  for (int64_t i = 0; i < n; ++i) {
+    double s = (double)rand() / RAND_MAX;
+    s = (s < 0.5) ? -1.0 : 1.0;
+    p[i] = s * f * (i + 1.1) / (i + 1.12345);
+  }
+  g_init_count++;
+}
+
+/* DataUtils.cpp:477-497 */
+void orc_init_int(int* p, int64_t n)
+{
+  srand(4793);
+  double s = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    s = (double)rand() / RAND_MAX;
+    p[i] = (s < 0.5) ? -1 : 1;
+  }
+  s = (double)rand() / RAND_MAX;
+  p[(int64_t)(n * s)] = -58;
+  s = (double)rand() / RAND_MAX;
+  p[(int64_t)(n * s)] = 19;
+  g_init_count++;
+}
+
+/* DataUtils.cpp:589-595 */
+double orc_init_scalar(void)
+{
+  const double f = parity_factor();
+  g_init_count++;
+  return f * 1.1 / 1.12345;
+}
+
+/* DataUtils.cpp:600-621 : long-double Kahan sum of (|sin(j+1)|+0.5)*data[j];
+ * the weight is formed in double, the product and the sum in long double.   */
+long double orc_checksum(const double* p, int64_t n, double scale)
+{
+  long double sum = 0.0L, comp = 0.0L;
+  for (int64_t j = 0; j < n; ++j) {
+    const double w = fabs(sin(j + 1.0)) + 0.5;
+    const long double x = (long double)w * (long double)p[j];
+    const long double y = x - comp;
+    volatile long double t = sum + y;
+    volatile long double z = t - sum;
+    comp = z - y;
+    sum = t;
+  }
+  sum *= scale;
+  return sum;
+}
+
+/* ======================================================================== */
+/* Stream group                                                              */
+/* ======================================================================== */
+
+/* stream/COPY.hpp:24-25, COPY-Seq.cpp rep body */
+void orc_stream_copy(double* c, const double* a, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) c[i] = a[i]; }
+
+/* stream/MUL.hpp:25-26 */
+void orc_stream_mul(double* b, const double* c, double alpha, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) b[i] = alpha * c[i]; }
+
+/* stream/ADD.hpp:25-26 */
+void orc_stream_add(double* c, const double* a, const double* b, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) c[i] = a[i] + b[i]; }
+
+/* stream/TRIAD.hpp:20-27, TRIAD-Seq.cpp:40-46 : separate multiply and add */
+void orc_stream_triad(double* a, const double* b, const double* c, double alpha, int64_t n)
+{ for (int64_t i = 0; i < n; ++i) a[i] = b[i] + alpha * c[i]; }
+
+/* stream/DOT.hpp:20-25, DOT-Seq.cpp:37-47 : left-to-right double sum */
+double orc_stream_dot(const double* a, const double* b, int64_t n, double init)
+{
+  double dot = init;
+  for (int64_t i = 0; i < n; ++i) dot += a[i] * b[i];
+  return dot;
+}
+
+/* ======================================================================== */
+/* Algorithm group                                                           */
+/* ======================================================================== */
+
+/* algorithm/REDUCE_SUM-Seq.cpp:37-47 */
+double orc_reduce_sum(const double* x, int64_t n, double init)
+{
+  double s = init;
+  for (int64_t i = 0; i < n; ++i) s += x[i];
+  return s;
+}
+
+/* algorithm/SCAN.hpp (SCAN_PROLOGUE / SCAN_BODY), SCAN-Seq.cpp:33-41 */
+void orc_scan_exclusive(const double* x, double* y, int64_t n)
+{
+  double run = 0.0;
+  for (int64_t i = 0; i < n; ++i) { y[i] = run; run += x[i]; }
+}
+
+static int cmp_f64(const void* pa, const void* pb)
+{
+  const double a = *(const double*)pa, b = *(const double*)pb;
+  return (a > b) - (a < b);
+}
+
+/* algorithm/SORT-Seq.cpp:34-38 : std::sort ascending.  Keys only, so any
+ * correct comparison sort yields the identical array.                       */
+void orc_sort(double* x, int64_t n) { qsort(x, (size_t)n, sizeof(double), cmp_f64); }
+
+/* algorithm/SORTPAIRS-Seq.cpp:34-59 : sort (key,value) by key.  The reference
+ * uses an unstable std::sort on .first; its output is only defined up to the
+ * order of equal keys.  This restatement is a stable merge sort, so for inputs
+ * whose equal keys carry equal values (the suite's own: x == i,
+ * SORTPAIRS.cpp:56-57) or whose keys are distinct it is THE answer.          */
+typedef struct { double k, v; } kv_t;
+
+static void merge_sort_kv(kv_t* a, kv_t* tmp, int64_t n)
+{
+  if (n < 2) return;
+  const int64_t h = n / 2;
+  merge_sort_kv(a, tmp, h);
+  merge_sort_kv(a + h, tmp, n - h);
+  int64_t i = 0, j = h, o = 0;
+  while (i < h && j < n) tmp[o++] = (a[j].k < a[i].k) ? a[j++] : a[i++];
+  while (i < h) tmp[o++] = a[i++];
+  while (j < n) tmp[o++] = a[j++];
+  memcpy(a, tmp, (size_t)n * sizeof(kv_t));
+}
+
+void orc_sort_pairs(double* keys, double* vals, int64_t n)
+{
+  kv_t* a = (kv_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(kv_t));
+  kv_t* t = (kv_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(kv_t));
+  for (int64_t i = 0; i < n; ++i) { a[i].k = keys[i]; a[i].v = vals[i]; }
+  merge_sort_kv(a, t, n);
+  for (int64_t i = 0; i < n; ++i) { keys[i] = a[i].k; vals[i] = a[i].v; }
+  free(a); free(t);
+}
+
+/* ======================================================================== */
+/* Apps group: partial-assembly FEM operators                                */
+/* ======================================================================== */
+
+/* apps/MASS3DPA.hpp:158-339 + MASS3DPA-Seq.cpp:31-90.
+ * D1D=4, Q1D=5.  Two scratch cubes are ping-ponged exactly as the reference's
+ * sm0/sm1; the 20-entry basis scratch is first filled as [q][d] from B, later
+ * refilled as [d][q] from Bt with the reference's own (q + 4*d) indexing.    */
+#define M_D 4
+#define M_Q 5
+void orc_mass3dpa(const double* B, const double* Bt, const double* D,
+                  const double* X, double* Y, int64_t NE)
+{
+  for (int64_t e = 0; e < NE; ++e) {
+    double bas[M_Q * M_D];
+    double s0[M_Q * M_Q * M_Q], s1[M_Q * M_Q * M_Q];
+    const double* Xe = X + (int64_t)M_D * M_D * M_D * e;
+    const double* De = D + (int64_t)M_Q * M_Q * M_Q * e;
+    double* Ye = Y + (int64_t)M_D * M_D * M_D * e;
+
+    /* steps 1,2 (hpp:229-237): X -> s0[dz][dy][dx]; bas[q][d] = B[q + 5 d] */
+    for (int dy = 0; dy < M_D; ++dy) {
+      for (int dx = 0; dx < M_D; ++dx)
+        for (int dz = 0; dz < M_D; ++dz)
+          s0[(dz * M_D + dy) * M_D + dx] = Xe[dx + M_D * dy + M_D * M_D * dz];
+      for (int q = 0; q < M_Q; ++q) bas[q * M_D + dy] = B[q + M_Q * dy];
+    }
+    /* step 3 (hpp:240-256): contract dx -> s1 viewed [dz][dy][qx] */
+    for (int dy = 0; dy < M_D; ++dy)
+      for (int qx = 0; qx < M_Q; ++qx) {
+        double u[M_D] = {0, 0, 0, 0};
+        for (int dx = 0; dx < M_D; ++dx)
+          for (int dz = 0; dz < M_D; ++dz)
+            u[dz] += s0[(dz * M_D + dy) * M_D + dx] * bas[qx * M_D + dx];
+        for (int dz = 0; dz < M_D; ++dz) s1[(dz * M_D + dy) * M_Q + qx] = u[dz];
+      }
+    /* step 4 (hpp:259-275): contract dy -> s0 viewed [dz][qy][qx] */
+    for (int qy = 0; qy < M_Q; ++qy)
+      for (int qx = 0; qx < M_Q; ++qx) {
+        double u[M_D] = {0, 0, 0, 0};
+        for (int dy = 0; dy < M_D; ++dy)
+          for (int dz = 0; dz < M_D; ++dz)
+            u[dz] += s1[(dz * M_D + dy) * M_Q + qx] * bas[qy * M_D + dy];
+        for (int dz = 0; dz < M_D; ++dz) s0[(dz * M_Q + qy) * M_Q + qx] = u[dz];
+      }
+    /* step 5 (hpp:278-294): contract dz, scale by D -> s1 viewed [qz][qy][qx] */
+    for (int qy = 0; qy < M_Q; ++qy)
+      for (int qx = 0; qx < M_Q; ++qx) {
+        double u[M_Q] = {0, 0, 0, 0, 0};
+        for (int dz = 0; dz < M_D; ++dz)
+          for (int qz = 0; qz < M_Q; ++qz)
+            u[qz] += s0[(dz * M_Q + qy) * M_Q + qx] * bas[qz * M_D + dz];
+        for (int qz = 0; qz < M_Q; ++qz)
+          s1[(qz * M_Q + qy) * M_Q + qx] = u[qz] * De[qx + M_Q * qy + M_Q * M_Q * qz];
+      }
+    /* step 6 (hpp:296-297): bas[d][q] = Bt[q + 4 d] */
+    for (int d = 0; d < M_D; ++d)
+      for (int q = 0; q < M_Q; ++q) bas[d * M_Q + q] = Bt[q + M_D * d];
+    /* step 7 (hpp:300-316): contract qx -> s0 viewed [qz][qy][dx] */
+    for (int qy = 0; qy < M_Q; ++qy)
+      for (int dx = 0; dx < M_D; ++dx) {
+        double u[M_Q] = {0, 0, 0, 0, 0};
+        for (int qx = 0; qx < M_Q; ++qx)
+          for (int qz = 0; qz < M_Q; ++qz)
+            u[qz] += s1[(qz * M_Q + qy) * M_Q + qx] * bas[dx * M_Q + qx];
+        for (int qz = 0; qz < M_Q; ++qz) s0[(qz * M_Q + qy) * M_D + dx] = u[qz];
+      }
+    /* step 8 (hpp:319-335): contract qy -> s1 viewed [qz][dy][dx] */
+    for (int dy = 0; dy < M_D; ++dy)
+      for (int dx = 0; dx < M_D; ++dx) {
+        double u[M_Q] = {0, 0, 0, 0, 0};
+        for (int qy = 0; qy < M_Q; ++qy)
+          for (int qz = 0; qz < M_Q; ++qz)
+            u[qz] += s0[(qz * M_Q + qy) * M_D + dx] * bas[dy * M_Q + qy];
+        for (int qz = 0; qz < M_Q; ++qz) s1[(qz * M_D + dy) * M_D + dx] = u[qz];
+      }
+    /* step 9 (hpp:338-354): contract qz, accumulate into Y */
+    for (int dy = 0; dy < M_D; ++dy)
+      for (int dx = 0; dx < M_D; ++dx) {
+        double u[M_D] = {0, 0, 0, 0};
+        for (int qz = 0; qz < M_Q; ++qz)
+          for (int dz = 0; dz < M_D; ++dz)
+            u[dz] += s1[(qz * M_D + dy) * M_D + dx] * bas[dz * M_Q + qz];
+        for (int dz = 0; dz < M_D; ++dz) Ye[dx + M_D * dy + M_D * M_D * dz] += u[dz];
+      }
+  }
+}
+
+/* apps/DIFFUSION3DPA.hpp:245-268 index helpers for the half-stored basis */
+#define F_D 3
+#define F_Q 4
+static int h_qi(int q, int d) { return (q <= d) ? q : F_Q - 1 - q; }
+static int h_dj(int q, int d) { return (q <= d) ? d : F_D - 1 - d; }
+static int h_qk(int q, int d) { return (q <= d) ? F_Q - 1 - q : q; }
+static int h_dl(int q, int d) { return (q <= d) ? F_D - 1 - d : d; }
+static double h_sg(int q, int d) { return (q <= d) ? -1.0 : 1.0; }
+
+/* The reference keeps B, G, Bt and Gt in ONE 12-double array
+ * (DIFFUSION3DPA.hpp:301-305), so the two fills overwrite each other and the
+ * content depends on loop order.  Base_Seq order: fill #1 dy-outer/qx-inner,
+ * B then G per iteration (DIFFUSION3DPA-Seq.cpp:45-49, hpp:333-340); fill #2
+ * d-outer/q-inner on top of fill #1's leftovers (Seq.cpp:75-79, hpp:405-411). */
+static void diffusion_fill1(const double* Basis, const double* dBasis, double* t)
+{
+  for (int dy = 0; dy < F_D; ++dy)
+    for (int qx = 0; qx < F_Q; ++qx) {
+      t[h_qi(qx, dy) * F_D + h_dj(qx, dy)] = Basis[qx + F_Q * dy];
+      t[h_qk(qx, dy) * F_D + h_dl(qx, dy)] = dBasis[qx + F_Q * dy] * h_sg(qx, dy);
+    }
+}
+static void diffusion_fill2(const double* Basis, const double* dBasis, double* t)
+{
+  for (int d = 0; d < F_D; ++d)
+    for (int q = 0; q < F_Q; ++q) {
+      t[h_dj(q, d) * F_Q + h_qi(q, d)] = Basis[q + F_Q * d];
+      t[h_dl(q, d) * F_Q + h_qk(q, d)] = dBasis[q + F_Q * d] * h_sg(q, d);
+    }
+}
+
+void orc_diffusion3dpa_tables(const double* Basis, const double* dBasis,
+                              double* fill1, double* fill2)
+{
+  for (int i = 0; i < F_Q * F_D; ++i) fill1[i] = NAN;  /* reference: uninitialised */
+  diffusion_fill1(Basis, dBasis, fill1);
+  memcpy(fill2, fill1, sizeof(double) * F_Q * F_D);
+  diffusion_fill2(Basis, dBasis, fill2);
+}
+
+/* apps/DIFFUSION3DPA.hpp:216-458 + DIFFUSION3DPA-Seq.cpp:31-106 */
+void orc_diffusion3dpa(const double* Basis, const double* dBasis, const double* D,
+                       const double* X, double* Y, int64_t NE, int symmetric)
+{
+  enum { C = F_Q * F_Q * F_Q };
+  for (int64_t e = 0; e < NE; ++e) {
+    double t[F_Q * F_D];
+    double a[3][C], b[3][C];          /* reference sm0, sm1 */
+    const double* Xe = X + (int64_t)27 * e;
+    double* Ye = Y + (int64_t)27 * e;
+    const int nsym = symmetric ? 6 : 9;
+    const double* De = D + (int64_t)C * 6 * e;  /* stride is SYM=6 (hpp:240-241) */
+    (void)nsym;
+    for (int i = 0; i < F_Q * F_D; ++i) t[i] = NAN;
+
+    /* step 1: X -> a[2] viewed [dz][dy][dx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int dx = 0; dx < F_D; ++dx)
+          a[2][(dz * F_D + dy) * F_D + dx] = Xe[dx + F_D * dy + F_D * F_D * dz];
+    /* step 2 */
+    diffusion_fill1(Basis, dBasis, t);
+    /* step 3 (hpp:342-357): a[0],a[1] viewed [dz][dy][qx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int qx = 0; qx < F_Q; ++qx) {
+          double u = 0.0, v = 0.0;
+          for (int dx = 0; dx < F_D; ++dx) {
+            const double bb = t[h_qi(qx, dx) * F_D + h_dj(qx, dx)];
+            const double gg = t[h_qk(qx, dx) * F_D + h_dl(qx, dx)];
+            const double s = h_sg(qx, dx);
+            const double c = a[2][(dz * F_D + dy) * F_D + dx];
+            u += c * bb;
+            v += c * gg * s;
+          }
+          a[0][(dz * F_D + dy) * F_Q + qx] = u;
+          a[1][(dz * F_D + dy) * F_Q + qx] = v;
+        }
+    /* step 4 (hpp:359-375): b[0..2] viewed [dz][qy][qx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int qx = 0; qx < F_Q; ++qx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+          for (int dy = 0; dy < F_D; ++dy) {
+            const double bb = t[h_qi(qy, dy) * F_D + h_dj(qy, dy)];
+            const double gg = t[h_qk(qy, dy) * F_D + h_dl(qy, dy)];
+            const double s = h_sg(qy, dy);
+            const double d0 = a[0][(dz * F_D + dy) * F_Q + qx];
+            const double d1 = a[1][(dz * F_D + dy) * F_Q + qx];
+            u += d1 * bb;
+            v += d0 * gg * s;
+            w += d0 * bb;
+          }
+          b[0][(dz * F_Q + qy) * F_Q + qx] = u;
+          b[1][(dz * F_Q + qy) * F_Q + qx] = v;
+          b[2][(dz * F_Q + qy) * F_Q + qx] = w;
+        }
+    /* step 5 (hpp:377-403): a[0..2] viewed [qz][qy][qx] */
+    for (int qz = 0; qz < F_Q; ++qz)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int qx = 0; qx < F_Q; ++qx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+          for (int dz = 0; dz < F_D; ++dz) {
+            const double bb = t[h_qi(qz, dz) * F_D + h_dj(qz, dz)];
+            const double gg = t[h_qk(qz, dz) * F_D + h_dl(qz, dz)];
+            const double s = h_sg(qz, dz);
+            u += b[0][(dz * F_Q + qy) * F_Q + qx] * bb;
+            v += b[1][(dz * F_Q + qy) * F_Q + qx] * bb;
+            w += b[2][(dz * F_Q + qy) * F_Q + qx] * gg * s;
+          }
+          const int q = qx + F_Q * qy + F_Q * F_Q * qz;
+#define DD(s_) De[q + C * (s_)]
+          const double O11 = DD(0), O12 = DD(1), O13 = DD(2);
+          const double O21 = symmetric ? O12 : DD(3);
+          const double O22 = symmetric ? DD(3) : DD(4);
+          const double O23 = symmetric ? DD(4) : DD(5);
+          const double O31 = symmetric ? O13 : DD(6);
+          const double O32 = symmetric ? O23 : DD(7);
+          const double O33 = symmetric ? DD(5) : DD(8);
+#undef DD
+          a[0][(qz * F_Q + qy) * F_Q + qx] = (O11 * u) + (O12 * v) + (O13 * w);
+          a[1][(qz * F_Q + qy) * F_Q + qx] = (O21 * u) + (O22 * v) + (O23 * w);
+          a[2][(qz * F_Q + qy) * F_Q + qx] = (O31 * u) + (O32 * v) + (O33 * w);
+        }
+    /* step 6 */
+    diffusion_fill2(Basis, dBasis, t);
+    /* step 7 (hpp:413-429): b[0..2] viewed [qz][qy][dx] */
+    for (int qz = 0; qz < F_Q; ++qz)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int dx = 0; dx < F_D; ++dx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+          for (int qx = 0; qx < F_Q; ++qx) {
+            const double bt = t[h_dj(qx, dx) * F_Q + h_qi(qx, dx)];
+            const double gt = t[h_dl(qx, dx) * F_Q + h_qk(qx, dx)];
+            const double s = h_sg(qx, dx);
+            u += a[0][(qz * F_Q + qy) * F_Q + qx] * gt * s;
+            v += a[1][(qz * F_Q + qy) * F_Q + qx] * bt;
+            w += a[2][(qz * F_Q + qy) * F_Q + qx] * bt;
+          }
+          b[0][(qz * F_Q + qy) * F_D + dx] = u;
+          b[1][(qz * F_Q + qy) * F_D + dx] = v;
+          b[2][(qz * F_Q + qy) * F_D + dx] = w;
+        }
+    /* step 8 (hpp:431-447): a[0..2] viewed [qz][dy][dx] */
+    for (int qz = 0; qz < F_Q; ++qz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int dx = 0; dx < F_D; ++dx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+          for (int qy = 0; qy < F_Q; ++qy) {
+            const double bt = t[h_dj(qy, dy) * F_Q + h_qi(qy, dy)];
+            const double gt = t[h_dl(qy, dy) * F_Q + h_qk(qy, dy)];
+            const double s = h_sg(qy, dy);
+            u += b[0][(qz * F_Q + qy) * F_D + dx] * bt;
+            v += b[1][(qz * F_Q + qy) * F_D + dx] * gt * s;
+            w += b[2][(qz * F_Q + qy) * F_D + dx] * bt;
+          }
+          a[0][(qz * F_D + dy) * F_D + dx] = u;
+          a[1][(qz * F_D + dy) * F_D + dx] = v;
+          a[2][(qz * F_D + dy) * F_D + dx] = w;
+        }
+    /* step 9 (hpp:449-463) */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int dx = 0; dx < F_D; ++dx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+          for (int qz = 0; qz < F_Q; ++qz) {
+            const double bt = t[h_dj(qz, dz) * F_Q + h_qi(qz, dz)];
+            const double gt = t[h_dl(qz, dz) * F_Q + h_qk(qz, dz)];
+            const double s = h_sg(qz, dz);
+            u += a[0][(qz * F_D + dy) * F_D + dx] * bt;
+            v += a[1][(qz * F_D + dy) * F_D + dx] * bt;
+            w += a[2][(qz * F_D + dy) * F_D + dx] * gt * s;
+          }
+          Ye[dx + F_D * dy + F_D * F_D * dz] += (u + v + w);
+        }
+  }
+}
+
+/* apps/CONVECTION3DPA.hpp:197-355 + CONVECTION3DPA-Seq.cpp:31-120.
+ * D1D=3, Q1D=4, VDIM=3; B, Bt, G read straight from the 12-entry tables.     */
+void orc_convection3dpa(const double* Basis, const double* tBasis, const double* dBasis,
+                        const double* D, const double* X, double* Y, int64_t NE)
+{
+  enum { C = F_Q * F_Q * F_Q };
+  for (int64_t e = 0; e < NE; ++e) {
+    double s0[C], s1[C], s2[C], s3[C], s4[C], s5[C];
+    const double* Xe = X + (int64_t)27 * e;
+    const double* De = D + (int64_t)3 * C * e;
+    double* Ye = Y + (int64_t)27 * e;
+
+    /* 1: u[dz][dy][dx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int dx = 0; dx < F_D; ++dx)
+          s0[(dz * F_D + dy) * F_D + dx] = Xe[dx + F_D * dy + F_D * F_D * dz];
+    /* 2 (hpp:263-275): Bu, Gu [dz][dy][qx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int qx = 0; qx < F_Q; ++qx) {
+          double bu = 0.0, gu = 0.0;
+          for (int dx = 0; dx < F_D; ++dx) {
+            const double x = s0[(dz * F_D + dy) * F_D + dx];
+            bu += Basis[qx + F_Q * dx] * x;
+            gu += dBasis[qx + F_Q * dx] * x;
+          }
+          s1[(dz * F_D + dy) * F_Q + qx] = bu;
+          s2[(dz * F_D + dy) * F_Q + qx] = gu;
+        }
+    /* 3 (hpp:277-292): BBu, GBu, BGu [dz][qy][qx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int qx = 0; qx < F_Q; ++qx)
+        for (int qy = 0; qy < F_Q; ++qy) {
+          double bbu = 0.0, gbu = 0.0, bgu = 0.0;
+          for (int dy = 0; dy < F_D; ++dy) {
+            const double bx = Basis[qy + F_Q * dy], gx = dBasis[qy + F_Q * dy];
+            bbu += bx * s1[(dz * F_D + dy) * F_Q + qx];
+            gbu += gx * s1[(dz * F_D + dy) * F_Q + qx];
+            bgu += bx * s2[(dz * F_D + dy) * F_Q + qx];
+          }
+          s3[(dz * F_Q + qy) * F_Q + qx] = bbu;
+          s4[(dz * F_Q + qy) * F_Q + qx] = gbu;
+          s5[(dz * F_Q + qy) * F_Q + qx] = bgu;
+        }
+    /* 4 (hpp:294-309): GBBu->s0, BGBu->s1, BBGu->s2 [qz][qy][qx] */
+    for (int qx = 0; qx < F_Q; ++qx)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int qz = 0; qz < F_Q; ++qz) {
+          double gbbu = 0.0, bgbu = 0.0, bbgu = 0.0;
+          for (int dz = 0; dz < F_D; ++dz) {
+            const double bx = Basis[qz + F_Q * dz], gx = dBasis[qz + F_Q * dz];
+            gbbu += gx * s3[(dz * F_Q + qy) * F_Q + qx];
+            bgbu += bx * s4[(dz * F_Q + qy) * F_Q + qx];
+            bbgu += bx * s5[(dz * F_Q + qy) * F_Q + qx];
+          }
+          s0[(qz * F_Q + qy) * F_Q + qx] = gbbu;
+          s1[(qz * F_Q + qy) * F_Q + qx] = bgbu;
+          s2[(qz * F_Q + qy) * F_Q + qx] = bbgu;
+        }
+    /* 5 (hpp:311-318): DGu -> s3 */
+    for (int qz = 0; qz < F_Q; ++qz)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int qx = 0; qx < F_Q; ++qx) {
+          const int q = qx + F_Q * qy + F_Q * F_Q * qz;
+          const double O1 = De[q], O2 = De[q + C], O3 = De[q + 2 * C];
+          const int i = (qz * F_Q + qy) * F_Q + qx;
+          s3[i] = (O1 * s2[i]) + (O2 * s1[i]) + (O3 * s0[i]);
+        }
+    /* 6 (hpp:320-328): BDGu -> s4 [dz][qy][qx] */
+    for (int qx = 0; qx < F_Q; ++qx)
+      for (int qy = 0; qy < F_Q; ++qy)
+        for (int dz = 0; dz < F_D; ++dz) {
+          double acc = 0.0;
+          for (int qz = 0; qz < F_Q; ++qz)
+            acc += tBasis[dz + F_D * qz] * s3[(qz * F_Q + qy) * F_Q + qx];
+          s4[(dz * F_Q + qy) * F_Q + qx] = acc;
+        }
+    /* 7 (hpp:330-338): BBDGu -> s5 [dz][dy][qx] */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int qx = 0; qx < F_Q; ++qx)
+        for (int dy = 0; dy < F_D; ++dy) {
+          double acc = 0.0;
+          for (int qy = 0; qy < F_Q; ++qy)
+            acc += tBasis[dy + F_D * qy] * s4[(dz * F_Q + qy) * F_Q + qx];
+          s5[(dz * F_D + dy) * F_Q + qx] = acc;
+        }
+    /* 8 (hpp:340-348) */
+    for (int dz = 0; dz < F_D; ++dz)
+      for (int dy = 0; dy < F_D; ++dy)
+        for (int dx = 0; dx < F_D; ++dx) {
+          double acc = 0.0;
+          for (int qx = 0; qx < F_Q; ++qx)
+            acc += tBasis[dx + F_D * qx] * s5[(dz * F_D + dy) * F_Q + qx];
+          Ye[dx + F_D * dy + F_D * F_D * dz] += acc;
+        }
+  }
+}
+
+/* apps/LTIMES.hpp:33-45 (LTIMES_BODY), LTIMES-Seq.cpp:34-42: z,g,m,d nest with
+ * the running sum kept in phi itself (so the add order starts from old phi). */
+void orc_ltimes(double* phi, const double* ell, const double* psi,
+                int64_t num_d, int64_t num_g, int64_t num_m, int64_t num_z)
+{
+  for (int64_t z = 0; z < num_z; ++z)
+    for (int64_t g = 0; g < num_g; ++g)
+      for (int64_t m = 0; m < num_m; ++m) {
+        double acc = phi[m + g * num_m + z * num_m * num_g];
+        for (int64_t d = 0; d < num_d; ++d)
+          acc += ell[d + m * num_d] * psi[d + g * num_d + z * num_d * num_g];
+        phi[m + g * num_m + z * num_m * num_g] = acc;
+      }
+}
+
+/* ======================================================================== */
+/* Comm group                                                                */
+/* ======================================================================== */
+
+/* comm/HALO_base.cpp:82-116 : faces, edges, corners */
+const int orc_halo_offsets[ORC_HALO_NEIGHBORS][3] = {
+  {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+  {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0},
+  {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1},
+  {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+  {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1},
+  {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}
+};
+
+/* comm/HALO_base.cpp:31-35 : truncation of cbrt(size)+cbrt(3)-1 */
+void orc_halo_grid_dims(int64_t target_size, int64_t dims[3])
+{
+  const double c = cbrt((double)target_size) + cbrt(3.0) - 1;
+  dims[0] = dims[1] = dims[2] = (int64_t)c;
+}
+
+/* comm/HALO_base.cpp:118-166 : per-dimension [lo,hi) of a send or recv box */
+static void halo_bounds(int is_recv, int off, int64_t hw, int64_t dim, int64_t* lo, int64_t* hi)
+{
+  if (off < 0)      { *lo = is_recv ? 0 : hw;          *hi = *lo + hw; }
+  else if (off > 0) { *lo = is_recv ? hw + dim : dim;  *hi = *lo + hw; }
+  else              { *lo = hw;                        *hi = hw + dim; }
+}
+
+int64_t orc_halo_extent_len(int is_recv, int l, int64_t hw, const int64_t dims[3])
+{
+  int64_t len = 1;
+  for (int a = 0; a < 3; ++a) {
+    int64_t lo, hi; halo_bounds(is_recv, orc_halo_offsets[l][a], hw, dims[a], &lo, &hi);
+    len *= (hi - lo);
+  }
+  return len;
+}
+
+/* comm/HALO_base.cpp:197-254 / 262-288 : k outer, j, i inner; int indices */
+void orc_halo_make_list(int is_recv, int l, int64_t hw, const int64_t dims[3], int* list)
+{
+  int64_t lo[3], hi[3];
+  for (int a = 0; a < 3; ++a)
+    halo_bounds(is_recv, orc_halo_offsets[l][a], hw, dims[a], &lo[a], &hi[a]);
+  const int64_t sj = dims[0] + 2 * hw, sk = sj * (dims[1] + 2 * hw);
+  int64_t n = 0;
+  for (int64_t k = lo[2]; k < hi[2]; ++k)
+    for (int64_t j = lo[1]; j < hi[1]; ++j)
+      for (int64_t i = lo[0]; i < hi[0]; ++i) list[n++] = (int)(i + j * sj + k * sk);
+}
+
+static int halo_slot(const int o[3]) { return (o[0] + 1) + 3 * (o[1] + 1) + 9 * (o[2] + 1); }
+
+/* comm/HALO_base.cpp:183-227,260 : rank coords (x fastest), periodic wrap to
+ * 0 / dims-1, tag of a message = ordinal of the SENDER's boundary offset.    */
+void orc_halo_neighbors(int rank, const int pd[3], int ranks[ORC_HALO_NEIGHBORS],
+                        int send_tags[ORC_HALO_NEIGHBORS], int recv_tags[ORC_HALO_NEIGHBORS])
+{
+  int slot_to_l[27];
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) slot_to_l[halo_slot(orc_halo_offsets[l])] = l;
+  int me[3];
+  me[2] = rank / (pd[0] * pd[1]);
+  me[1] = (rank - me[2] * pd[0] * pd[1]) / pd[0];
+  me[0] = rank - me[2] * pd[0] * pd[1] - me[1] * pd[0];
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+    int nb[3], opp[3];
+    for (int a = 0; a < 3; ++a) {
+      nb[a] = me[a] + orc_halo_offsets[l][a];
+      if (nb[a] >= pd[a]) nb[a] = 0; else if (nb[a] < 0) nb[a] = pd[a] - 1;
+      opp[a] = -orc_halo_offsets[l][a];
+    }
+    ranks[l] = nb[0] + pd[0] * (nb[1] + pd[1] * nb[2]);
+    send_tags[l] = slot_to_l[halo_slot(orc_halo_offsets[l])];
+    recv_tags[l] = slot_to_l[halo_slot(opp)];
+  }
+}
+
+void orc_halo_pack(double* buffer, const int* list, const double* var, int64_t len)
+{ for (int64_t i = 0; i < len; ++i) buffer[i] = var[list[i]]; }
+
+void orc_halo_unpack(double* var, const int* list, const double* buffer, int64_t len)
+{ for (int64_t i = 0; i < len; ++i) var[list[i]] = buffer[i]; }
+
+/* ======================================================================== */
+/* Whole-kernel known-answer drivers (KernelBase::execute, KernelBase.cpp:359-377:
+ * reset init counter -> setUp -> reps -> updateChecksum)                      */
+/* ======================================================================== */
+
+static double* dalloc(int64_t n) { return (double*)malloc((size_t)(n > 0 ? n : 1) * sizeof(double)); }
+static int64_t tsize(int64_t target, int64_t dflt) { return target > 0 ? target : dflt; }
+
+long double orc_kat_stream_copy(int64_t target, int reps)     /* stream/COPY.cpp:21-85 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *a = dalloc(n), *c = dalloc(n);
+  orc_reset_init_count();
+  orc_init_real(a, n); orc_init_const(c, n, 0.0);
+  for (int r = 0; r < reps; ++r) orc_stream_copy(c, a, n);
+  long double ck = orc_checksum(c, n, 1.0);
+  free(a); free(c); return ck;
+}
+
+long double orc_kat_stream_mul(int64_t target, int reps)      /* stream/MUL.cpp:21-86 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *b = dalloc(n), *c = dalloc(n);
+  orc_reset_init_count();
+  orc_init_const(b, n, 0.0); orc_init_real(c, n);
+  const double alpha = orc_init_scalar();
+  for (int r = 0; r < reps; ++r) orc_stream_mul(b, c, alpha, n);
+  long double ck = orc_checksum(b, n, 1.0);
+  free(b); free(c); return ck;
+}
+
+long double orc_kat_stream_add(int64_t target, int reps)      /* stream/ADD.cpp:21-87 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *a = dalloc(n), *b = dalloc(n), *c = dalloc(n);
+  orc_reset_init_count();
+  orc_init_real(a, n); orc_init_real(b, n); orc_init_const(c, n, 0.0);
+  for (int r = 0; r < reps; ++r) orc_stream_add(c, a, b, n);
+  long double ck = orc_checksum(c, n, 1.0);
+  free(a); free(b); free(c); return ck;
+}
+
+long double orc_kat_stream_triad(int64_t target, int reps)    /* stream/TRIAD.cpp:21-92 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *a = dalloc(n), *b = dalloc(n), *c = dalloc(n);
+  orc_reset_init_count();
+  orc_init_const(a, n, 0.0); orc_init_real(b, n); orc_init_real(c, n);
+  const double alpha = orc_init_scalar();
+  for (int r = 0; r < reps; ++r) orc_stream_triad(a, b, c, alpha, n);
+  /* TRIAD.cpp:36-38: formed in long double (Checksum_type), narrowed to Real_type at the call */
+  const double scale = (double)(0.001 * ((long double)1000000 / n));
+  long double ck = orc_checksum(a, n, scale);
+  free(a); free(b); free(c); return ck;
+}
+
+long double orc_kat_stream_dot(int64_t target, int reps)      /* stream/DOT.cpp:21-88 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *a = dalloc(n), *b = dalloc(n);
+  orc_reset_init_count();
+  orc_init_real(a, n); orc_init_real(b, n);
+  double m_dot = 0.0;
+  for (int r = 0; r < reps; ++r) m_dot += orc_stream_dot(a, b, n, 0.0);  /* DOT-Seq.cpp:45 */
+  free(a); free(b);
+  return (long double)m_dot;                                   /* DOT.cpp:80 */
+}
+
+long double orc_kat_reduce_sum(int64_t target, int reps)      /* algorithm/REDUCE_SUM.cpp */
+{
+  const int64_t n = tsize(target, 1000000);
+  double* x = dalloc(n);
+  orc_reset_init_count();
+  orc_init_real(x, n);
+  double m_sum = 0.0;
+  for (int r = 0; r < reps; ++r) m_sum = orc_reduce_sum(x, n, 0.0);
+  free(x);
+  return orc_checksum(&m_sum, 1, 1.0);                         /* REDUCE_SUM.cpp:75 */
+}
+
+long double orc_kat_scan(int64_t target, int reps)            /* algorithm/SCAN.cpp:21-93 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *x = dalloc(n), *y = dalloc(n);
+  orc_reset_init_count();
+  orc_init_rand_value(x, n); orc_init_const(y, n, 0.0);
+  for (int r = 0; r < reps; ++r) orc_scan_exclusive(x, y, n);
+  const double scale = (double)(1e-2 * ((long double)1000000 / n) / n);  /* SCAN.cpp:36-39, long double then narrowed */
+  long double ck = orc_checksum(y, n, scale);
+  free(x); free(y); return ck;
+}
+
+long double orc_kat_sort(int64_t target, int reps)            /* algorithm/SORT.cpp:21-75 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double* x = dalloc(n * reps);
+  orc_reset_init_count();
+  orc_init_rand_value(x, n * reps);
+  for (int r = 0; r < reps; ++r) orc_sort(x + n * r, n);       /* SORT.hpp:21-25 */
+  long double ck = orc_checksum(x, n * reps, 1.0);
+  free(x); return ck;
+}
+
+long double orc_kat_sortpairs(int64_t target, int reps)       /* algorithm/SORTPAIRS.cpp */
+{
+  const int64_t n = tsize(target, 1000000);
+  double *x = dalloc(n * reps), *v = dalloc(n * reps);
+  orc_reset_init_count();
+  orc_init_rand_value(x, n * reps); orc_init_rand_value(v, n * reps);
+  for (int r = 0; r < reps; ++r) orc_sort_pairs(x + n * r, v + n * r, n);
+  long double ck = orc_checksum(x, n * reps, 1.0);
+  ck += orc_checksum(v, n * reps, 1.0);
+  free(x); free(v); return ck;
+}
+
+static int64_t round_div(int64_t target, int64_t unit)
+{ int64_t q = (target + unit / 2) / unit; return q > 1 ? q : 1; }
+
+long double orc_kat_mass3dpa(int64_t target, int reps)        /* apps/MASS3DPA.cpp:23-100 */
+{
+  const int64_t NE = round_div(tsize(target, 8000 * 125), 125);
+  double B[20], Bt[20];
+  double *D = dalloc(125 * NE), *X = dalloc(64 * NE), *Y = dalloc(64 * NE);
+  orc_reset_init_count();
+  orc_init_const(B, 20, 1.0); orc_init_const(Bt, 20, 1.0);
+  orc_init_const(D, 125 * NE, 1.0); orc_init_const(X, 64 * NE, 1.0); orc_init_const(Y, 64 * NE, 0.0);
+  for (int r = 0; r < reps; ++r) orc_mass3dpa(B, Bt, D, X, Y, NE);
+  long double ck = orc_checksum(Y, 64 * NE, 1.0);
+  free(D); free(X); free(Y); return ck;
+}
+
+long double orc_kat_diffusion3dpa(int64_t target, int reps)   /* apps/DIFFUSION3DPA.cpp:23-104 */
+{
+  const int64_t NE = round_div(tsize(target, 15625 * 64), 64);
+  double B[12], G[12];
+  double *D = dalloc(64 * 6 * NE), *X = dalloc(27 * NE), *Y = dalloc(27 * NE);
+  orc_reset_init_count();
+  orc_init_const(B, 12, 1.0); orc_init_const(G, 12, 1.0);
+  orc_init_const(D, 64 * 6 * NE, 1.0); orc_init_const(X, 27 * NE, 1.0); orc_init_const(Y, 27 * NE, 0.0);
+  for (int r = 0; r < reps; ++r) orc_diffusion3dpa(B, G, D, X, Y, NE, 1);
+  long double ck = orc_checksum(Y, 27 * NE, 1.0);
+  free(D); free(X); free(Y); return ck;
+}
+
+long double orc_kat_convection3dpa(int64_t target, int reps)  /* apps/CONVECTION3DPA.cpp:23-105 */
+{
+  const int64_t NE = round_div(tsize(target, 15625 * 64), 64);
+  double B[12], Bt[12], G[12];
+  double *D = dalloc(64 * 3 * NE), *X = dalloc(27 * NE), *Y = dalloc(27 * NE);
+  orc_reset_init_count();
+  orc_init_const(B, 12, 1.0); orc_init_const(Bt, 12, 1.0); orc_init_const(G, 12, 1.0);
+  orc_init_const(D, 64 * 3 * NE, 1.0); orc_init_const(X, 27 * NE, 1.0); orc_init_const(Y, 27 * NE, 0.0);
+  for (int r = 0; r < reps; ++r) orc_convection3dpa(B, Bt, G, D, X, Y, NE);
+  long double ck = orc_checksum(Y, 27 * NE, 1.0);
+  free(D); free(X); free(Y); return ck;
+}
+
+long double orc_kat_ltimes(int64_t target, int reps, int nd, int ng, int nm)  /* apps/LTIMES.cpp:23-107 */
+{
+  const int64_t dg = (int64_t)nd * ng;
+  const int64_t nz_default = round_div(1000000, dg);
+  const int64_t dflt = dg * nz_default;
+  const int64_t nz = round_div(tsize(target, dflt), dg);
+  const int64_t philen = (int64_t)nm * ng * nz, elllen = (int64_t)nd * nm, psilen = dg * nz;
+  double *phi = dalloc(philen), *ell = dalloc(elllen), *psi = dalloc(psilen);
+  orc_reset_init_count();
+  orc_init_const(phi, philen, 0.0); orc_init_real(ell, elllen); orc_init_real(psi, psilen);
+  for (int r = 0; r < reps; ++r) orc_ltimes(phi, ell, psi, nd, ng, nm, nz);
+  const double scale = (double)(0.001 * ((long double)dflt / psilen));   /* LTIMES.cpp:52-54 */
+  long double ck = orc_checksum(phi, philen, scale);
+  free(phi); free(ell); free(psi); return ck;
+}
+
+/* One simulated rank's halo state (comm/HALO_base.hpp members + the per-kernel
+ * vars / buffers of HALO_PACKING_FUSED.cpp:63-109).                           */
+typedef struct {
+  int64_t dims[3], hw, var_size;
+  int nvars;
+  int*    pack_list[ORC_HALO_NEIGHBORS];   int64_t pack_len[ORC_HALO_NEIGHBORS];
+  int*    unpack_list[ORC_HALO_NEIGHBORS]; int64_t unpack_len[ORC_HALO_NEIGHBORS];
+  double** vars;
+  double* pack_buf[ORC_HALO_NEIGHBORS];
+  double* unpack_buf[ORC_HALO_NEIGHBORS];
+  int ranks[ORC_HALO_NEIGHBORS], send_tags[ORC_HALO_NEIGHBORS], recv_tags[ORC_HALO_NEIGHBORS];
+} halo_rank_t;
+
+/* setUp order (HALO_base.cpp:52-67 then HALO_PACKING_FUSED.cpp:63-109): for each
+ * neighbour the pack list then the unpack list are allocAndInit'ed (2 counter
+ * bumps per l, contents overwritten); then the vars (1 bump each, overwritten
+ * with i+v); then 26 pack buffers; then 26 unpack buffers (initData fill).     */
+static void halo_rank_setup(halo_rank_t* h, int64_t target, int64_t hw, int nvars,
+                            int rank, const int pd[3])
+{
+  orc_halo_grid_dims(target, h->dims);
+  h->hw = hw; h->nvars = nvars;
+  h->var_size = (h->dims[0] + 2 * hw) * (h->dims[1] + 2 * hw) * (h->dims[2] + 2 * hw);
+  orc_halo_neighbors(rank, pd, h->ranks, h->send_tags, h->recv_tags);
+  orc_reset_init_count();
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+    h->pack_len[l] = orc_halo_extent_len(0, l, hw, h->dims);
+    h->pack_list[l] = (int*)malloc(sizeof(int) * (size_t)h->pack_len[l]);
+    orc_init_int(h->pack_list[l], h->pack_len[l]);
+    orc_halo_make_list(0, l, hw, h->dims, h->pack_list[l]);
+    h->unpack_len[l] = orc_halo_extent_len(1, l, hw, h->dims);
+    h->unpack_list[l] = (int*)malloc(sizeof(int) * (size_t)h->unpack_len[l]);
+    orc_init_int(h->unpack_list[l], h->unpack_len[l]);
+    orc_halo_make_list(1, l, hw, h->dims, h->unpack_list[l]);
+  }
+  h->vars = (double**)malloc(sizeof(double*) * (size_t)nvars);
+  for (int v = 0; v < nvars; ++v) {
+    h->vars[v] = dalloc(h->var_size);
+    orc_init_real(h->vars[v], h->var_size);
+    for (int64_t i = 0; i < h->var_size; ++i) h->vars[v][i] = (double)(i + v);
+  }
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+    h->pack_buf[l] = dalloc(nvars * h->pack_len[l]);
+    orc_init_real(h->pack_buf[l], nvars * h->pack_len[l]);
+  }
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+    h->unpack_buf[l] = dalloc(nvars * h->unpack_len[l]);
+    orc_init_real(h->unpack_buf[l], nvars * h->unpack_len[l]);
+  }
+}
+
+static void halo_rank_free(halo_rank_t* h)
+{
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+    free(h->pack_list[l]); free(h->unpack_list[l]); free(h->pack_buf[l]); free(h->unpack_buf[l]);
+  }
+  for (int v = 0; v < h->nvars; ++v) free(h->vars[v]);
+  free(h->vars);
+}
+
+/* HALO_PACKING_FUSED-Seq.cpp:43-61 : neighbour-major, variable-minor segments */
+static void halo_rank_pack(halo_rank_t* h)
+{
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l)
+    for (int v = 0; v < h->nvars; ++v)
+      orc_halo_pack(h->pack_buf[l] + v * h->pack_len[l], h->pack_list[l], h->vars[v], h->pack_len[l]);
+}
+/* HALO_PACKING_FUSED-Seq.cpp:71-97 */
+static void halo_rank_unpack(halo_rank_t* h)
+{
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l)
+    for (int v = 0; v < h->nvars; ++v)
+      orc_halo_unpack(h->vars[v], h->unpack_list[l], h->unpack_buf[l] + v * h->unpack_len[l], h->unpack_len[l]);
+}
+
+long double orc_kat_halo_packing_fused(int64_t target, int reps, int hw, int nvars)
+{
+  halo_rank_t h; const int pd[3] = {1, 1, 1};
+  halo_rank_setup(&h, tsize(target, 1000000), hw, nvars, 0, pd);
+  for (int r = 0; r < reps; ++r) { halo_rank_pack(&h); halo_rank_unpack(&h); }
+  long double ck = 0.0L;                         /* HALO_PACKING_FUSED.cpp:112-128 */
+  for (int v = 0; v < nvars; ++v) ck += orc_checksum(h.vars[v], h.var_size, 1.0);
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) ck += orc_checksum(h.pack_buf[l], nvars * h.pack_len[l], 1.0);
+  halo_rank_free(&h);
+  return ck;
+}
+
+/* HALO_EXCHANGE_FUSED-Seq.cpp:35-116 with MPI replaced by in-process delivery:
+ * receiver q's request l' (source ranks[l'], tag recv_tags[l']) is matched by
+ * the message its source sent with send tag == recv_tags[l'].                  */
+long double orc_kat_halo_exchange_fused(int64_t target, int reps, int hw, int nvars,
+                                        const int pd[3], long double* per_rank)
+{
+  const int P = pd[0] * pd[1] * pd[2];
+  halo_rank_t* R = (halo_rank_t*)malloc(sizeof(halo_rank_t) * (size_t)P);
+  for (int r = 0; r < P; ++r) halo_rank_setup(&R[r], tsize(target, 1000000), hw, nvars, r, pd);
+  for (int rep = 0; rep < reps; ++rep) {
+    for (int r = 0; r < P; ++r) halo_rank_pack(&R[r]);
+    for (int q = 0; q < P; ++q)
+      for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {
+        const halo_rank_t* src = &R[R[q].ranks[l]];
+        const int ls = R[q].recv_tags[l];            /* sender's l */
+        if (src->ranks[ls] != q || src->pack_len[ls] != R[q].unpack_len[l]) {
+          fprintf(stderr, "orc halo exchange: unmatched message\n"); abort();
+        }
+        memcpy(R[q].unpack_buf[l], src->pack_buf[ls], sizeof(double) * (size_t)(nvars * R[q].unpack_len[l]));
+      }
+    for (int r = 0; r < P; ++r) halo_rank_unpack(&R[r]);
+  }
+  long double avg = 0.0L;
+  for (int r = 0; r < P; ++r) {                  /* HALO_EXCHANGE_FUSED.cpp:123-128 */
+    long double ck = 0.0L;
+    for (int v = 0; v < nvars; ++v) ck += orc_checksum(R[r].vars[v], R[r].var_size, 1.0);
+    if (per_rank) per_rank[r] = ck;
+    avg += ck;
+    halo_rank_free(&R[r]);
+  }
+  free(R);
+  return avg / P;
+}
+
+/* ======================================================================== */
+/* Pointer-out wrappers: ctypes narrows a returned long double to double, so    */
+/* Python callers fetch the 80-bit value through memory instead.                */
+/* ======================================================================== */
+void orc_checksum_out(const double* p, int64_t n, double scale, long double* out)
+{ *out = orc_checksum(p, n, scale); }
+
+/* ip: ltimes {num_d,num_g,num_m}; halo_packing_fused {halo_width,num_vars};
+ * halo_exchange_fused {halo_width,num_vars,px,py,pz}.  Returns 0, or -1 for an
+ * unknown kernel name.                                                         */
+int orc_kat(const char* name, int64_t target, int reps, const int* ip, long double* out)
+{
+  if      (!strcmp(name, "Stream_COPY"))          *out = orc_kat_stream_copy(target, reps);
+  else if (!strcmp(name, "Stream_MUL"))           *out = orc_kat_stream_mul(target, reps);
+  else if (!strcmp(name, "Stream_ADD"))           *out = orc_kat_stream_add(target, reps);
+  else if (!strcmp(name, "Stream_TRIAD"))         *out = orc_kat_stream_triad(target, reps);
+  else if (!strcmp(name, "Stream_DOT"))           *out = orc_kat_stream_dot(target, reps);
+  else if (!strcmp(name, "Algorithm_REDUCE_SUM")) *out = orc_kat_reduce_sum(target, reps);
+  else if (!strcmp(name, "Algorithm_SCAN"))       *out = orc_kat_scan(target, reps);
+  else if (!strcmp(name, "Algorithm_SORT"))       *out = orc_kat_sort(target, reps);
+  else if (!strcmp(name, "Algorithm_SORTPAIRS"))  *out = orc_kat_sortpairs(target, reps);
+  else if (!strcmp(name, "Apps_MASS3DPA"))        *out = orc_kat_mass3dpa(target, reps);
+  else if (!strcmp(name, "Apps_DIFFUSION3DPA"))   *out = orc_kat_diffusion3dpa(target, reps);
+  else if (!strcmp(name, "Apps_CONVECTION3DPA"))  *out = orc_kat_convection3dpa(target, reps);
+  else if (!strcmp(name, "Apps_LTIMES"))
+    *out = orc_kat_ltimes(target, reps, ip ? ip[0] : 64, ip ? ip[1] : 32, ip ? ip[2] : 25);
+  else if (!strcmp(name, "Comm_HALO_PACKING_FUSED"))
+    *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
+  else if (!strcmp(name, "Comm_HALO_EXCHANGE_FUSED")) {
+    const int one[3] = {1, 1, 1};
+    *out = orc_kat_halo_exchange_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3,
+                                       ip ? ip + 2 : one, NULL);
+  }
+  else return -1;
+  return 0;
+}
+
+/* ======================================================================== */
+/* OpenMP timing legs (stream/<K>-OMP.cpp: "#pragma omp parallel for" /
+ * "reduction(+:dot)"; algorithm/REDUCE_SUM-OMP.cpp)                           */
+/* ======================================================================== */
+#ifdef _OPENMP
+#include <omp.h>
+int orc_omp_threads(void) { return omp_get_max_threads(); }
+#else
+int orc_omp_threads(void) { return 1; }
+#endif
+
+void orc_stream_copy_omp(double* c, const double* a, int64_t n)
+{
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) c[i] = a[i];
+}
+void orc_stream_mul_omp(double* b, const double* c, double alpha, int64_t n)
+{
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) b[i] = alpha * c[i];
+}
+void orc_stream_add_omp(double* c, const double* a, const double* b, int64_t n)
+{
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) c[i] = a[i] + b[i];
+}
+void orc_stream_triad_omp(double* a, const double* b, const double* c, double alpha, int64_t n)
+{
+#pragma omp parallel for
+  for (int64_t i = 0; i < n; ++i) a[i] = b[i] + alpha * c[i];
+}
+double orc_stream_dot_omp(const double* a, const double* b, int64_t n, double init)
+{
+  double dot = init;
+#pragma omp parallel for reduction(+:dot)
+  for (int64_t i = 0; i < n; ++i) dot += a[i] * b[i];
+  return dot;
+}
+double orc_reduce_sum_omp(const double* x, int64_t n, double init)
+{
+  double s = init;
+#pragma omp parallel for reduction(+:s)
+  for (int64_t i = 0; i < n; ++i) s += x[i];
+  return s;
+}
