@@ -1,0 +1,251 @@
+"""ctypes binding of the Base_B200 C ABI (include/rpb200.h).
+
+This is the Python-side stub a maintainer would write against ``librpb200.so``; it adds
+nothing of its own.  Device memory comes from the caller (torch tensors in the tests and
+in bench.py: ``tensor.data_ptr()``), streams from ``torch.cuda.current_stream().cuda_stream``.
+
+There is NO fallback: if the shared library is missing, or no sm_100 device is usable,
+loading / ``Context()`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t,
+                    c_ubyte, c_uint64, c_void_p)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librpb200.so")
+
+
+class RPB200Error(RuntimeError):
+    pass
+
+
+class HaloSeg(Structure):
+    """struct rpb200_halo_seg (include/rpb200.h)."""
+    _fields_ = [("buffer", c_void_p), ("list", c_void_p), ("var", c_void_p),
+                ("len", c_int64), ("work_begin", c_int64)]
+
+
+# name -> (restype, argtypes); must list every function declared in include/rpb200.h
+_P = c_void_p
+SIGNATURES = {
+    "rpb200_create": (c_int, [c_int, POINTER(_P)]),
+    "rpb200_destroy": (None, [_P]),
+    "rpb200_error_string": (c_char_p, [c_int]),
+    "rpb200_sm_count": (c_int, [_P]),
+    "rpb200_version": (c_char_p, []),
+    "rpb200_set_tuning": (c_int, [_P, c_char_p, c_int, c_int, c_int]),
+    "rpb200_stream_copy": (c_int, [_P, _P, _P, c_int64, _P]),
+    "rpb200_stream_mul": (c_int, [_P, _P, _P, c_double, c_int64, _P]),
+    "rpb200_stream_add": (c_int, [_P, _P, _P, _P, c_int64, _P]),
+    "rpb200_stream_triad": (c_int, [_P, _P, _P, _P, c_double, c_int64, _P]),
+    "rpb200_stream_dot": (c_int, [_P, _P, _P, c_int64, c_double, _P, c_int, _P]),
+    "rpb200_reduce_sum": (c_int, [_P, _P, c_int64, c_double, _P, _P]),
+    "rpb200_scan_exclusive": (c_int, [_P, _P, _P, c_int64, _P]),
+    "rpb200_sort_scratch_bytes": (c_size_t, [c_int64, c_int]),
+    "rpb200_sort_keys_f64": (c_int, [_P, _P, c_int64, _P, c_size_t, _P]),
+    "rpb200_sort_pairs_f64": (c_int, [_P, _P, _P, c_int64, _P, c_size_t, _P]),
+    "rpb200_mass3dpa": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rpb200_diffusion3dpa": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "rpb200_convection3dpa": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "rpb200_ltimes": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P]),
+    "rpb200_halo_chunk": (c_int, []),
+    "rpb200_halo_pack": (c_int, [_P, _P, c_int, c_int64, _P]),
+    "rpb200_halo_unpack": (c_int, [_P, _P, c_int, c_int64, _P]),
+    "rpb200_halo_pack_signal": (c_int, [_P, _P, c_int, c_int64, _P, c_int, c_uint64, _P]),
+    "rpb200_halo_wait_unpack": (c_int, [_P, _P, c_int, c_int64, _P, _P, c_int, c_uint64, _P]),
+    "rpb200_ipc_export": (c_int, [_P, POINTER(c_ubyte)]),
+    "rpb200_ipc_open": (c_int, [POINTER(c_ubyte), POINTER(_P)]),
+    "rpb200_ipc_close": (c_int, [_P]),
+    "rpb200_malloc": (c_int, [POINTER(_P), c_size_t]),
+    "rpb200_free": (c_int, [_P]),
+    "rpb200_malloc_host": (c_int, [POINTER(_P), c_size_t]),
+    "rpb200_free_host": (c_int, [_P]),
+    "rpb200_memcpy_h2d": (c_int, [_P, _P, c_size_t, _P]),
+    "rpb200_memcpy_d2h": (c_int, [_P, _P, c_size_t, _P]),
+    "rpb200_memset": (c_int, [_P, c_int, c_size_t, _P]),
+    "rpb200_stream_synchronize": (c_int, [_P]),
+    "rpb200_device_synchronize": (c_int, []),
+    "rpb200_timer_create": (c_int, [POINTER(_P)]),
+    "rpb200_timer_start": (c_int, [_P, _P]),
+    "rpb200_timer_stop": (c_int, [_P, _P]),
+    "rpb200_timer_elapsed_ms": (c_int, [_P, POINTER(c_float)]),
+    "rpb200_timer_destroy": (None, [_P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load librpb200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RPB200Error(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the Base_B200 kernels)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(err: int, what: str = "rpb200 call"):
+    if err != 0:
+        msg = load().rpb200_error_string(err)
+        raise RPB200Error(f"{what} failed: {err} ({msg.decode() if msg else '?'})")
+
+
+def _ptr(t):
+    """Device (or pinned host) pointer of a torch tensor / raw int / None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def _stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Context:
+    """Owns one rpb200_ctx.  Methods mirror the C entry points 1:1 and enqueue on torch's
+    current CUDA stream; tensors must be contiguous float64 CUDA tensors on this device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = c_void_p()
+        check(self.lib.rpb200_create(device, ctypes.byref(h)), "rpb200_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rpb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def sm_count(self) -> int:
+        return self.lib.rpb200_sm_count(self.h)
+
+    def set_tuning(self, kernel: str, block_size: int = -1, ctas_per_sm: int = -1, unroll: int = -1):
+        check(self.lib.rpb200_set_tuning(self.h, kernel.encode(), block_size, ctas_per_sm, unroll),
+              f"set_tuning({kernel})")
+
+    # ---- Stream --------------------------------------------------------------------------
+    def stream_copy(self, c, a, n=None):
+        n = a.numel() if n is None else n
+        check(self.lib.rpb200_stream_copy(self.h, _ptr(c), _ptr(a), n, _stream()), "stream_copy")
+
+    def stream_mul(self, b, c, alpha, n=None):
+        n = c.numel() if n is None else n
+        check(self.lib.rpb200_stream_mul(self.h, _ptr(b), _ptr(c), alpha, n, _stream()), "stream_mul")
+
+    def stream_add(self, c, a, b, n=None):
+        n = a.numel() if n is None else n
+        check(self.lib.rpb200_stream_add(self.h, _ptr(c), _ptr(a), _ptr(b), n, _stream()), "stream_add")
+
+    def stream_triad(self, a, b, c, alpha, n=None):
+        n = b.numel() if n is None else n
+        check(self.lib.rpb200_stream_triad(self.h, _ptr(a), _ptr(b), _ptr(c), alpha, n, _stream()),
+              "stream_triad")
+
+    def stream_dot(self, a, b, out, init=0.0, accumulate=False, n=None):
+        n = a.numel() if n is None else n
+        check(self.lib.rpb200_stream_dot(self.h, _ptr(a), _ptr(b), n, init, _ptr(out),
+                                         1 if accumulate else 0, _stream()), "stream_dot")
+
+    # ---- Algorithm -----------------------------------------------------------------------
+    def reduce_sum(self, x, out, init=0.0, n=None):
+        n = x.numel() if n is None else n
+        check(self.lib.rpb200_reduce_sum(self.h, _ptr(x), n, init, _ptr(out), _stream()), "reduce_sum")
+
+    def scan_exclusive(self, x, y, n=None):
+        n = x.numel() if n is None else n
+        check(self.lib.rpb200_scan_exclusive(self.h, _ptr(x), _ptr(y), n, _stream()), "scan_exclusive")
+
+    def sort_scratch_bytes(self, n: int, pairs: bool = False) -> int:
+        return self.lib.rpb200_sort_scratch_bytes(n, 1 if pairs else 0)
+
+    def sort_keys(self, keys, scratch, n=None):
+        n = keys.numel() if n is None else n
+        check(self.lib.rpb200_sort_keys_f64(self.h, _ptr(keys), n, _ptr(scratch),
+                                            scratch.numel() * scratch.element_size(), _stream()),
+              "sort_keys_f64")
+
+    def sort_pairs(self, keys, vals, scratch, n=None):
+        n = keys.numel() if n is None else n
+        check(self.lib.rpb200_sort_pairs_f64(self.h, _ptr(keys), _ptr(vals), n, _ptr(scratch),
+                                             scratch.numel() * scratch.element_size(), _stream()),
+              "sort_pairs_f64")
+
+    # ---- Apps ----------------------------------------------------------------------------
+    def mass3dpa(self, B, Bt, D, X, Y, NE):
+        check(self.lib.rpb200_mass3dpa(self.h, _ptr(B), _ptr(Bt), _ptr(D), _ptr(X), _ptr(Y), NE,
+                                       _stream()), "mass3dpa")
+
+    def diffusion3dpa(self, B, G, D, X, Y, NE, symmetric=True):
+        check(self.lib.rpb200_diffusion3dpa(self.h, _ptr(B), _ptr(G), _ptr(D), _ptr(X), _ptr(Y), NE,
+                                            1 if symmetric else 0, _stream()), "diffusion3dpa")
+
+    def convection3dpa(self, B, Bt, G, D, X, Y, NE):
+        check(self.lib.rpb200_convection3dpa(self.h, _ptr(B), _ptr(Bt), _ptr(G), _ptr(D), _ptr(X),
+                                             _ptr(Y), NE, _stream()), "convection3dpa")
+
+    def ltimes(self, phi, ell, psi, num_d, num_g, num_m, num_z):
+        check(self.lib.rpb200_ltimes(self.h, _ptr(phi), _ptr(ell), _ptr(psi), num_d, num_g, num_m,
+                                     num_z, _stream()), "ltimes")
+
+    # ---- Comm ----------------------------------------------------------------------------
+    def halo_chunk(self) -> int:
+        return self.lib.rpb200_halo_chunk()
+
+    def halo_pack(self, d_segs, nsegs, total_chunks):
+        check(self.lib.rpb200_halo_pack(self.h, _ptr(d_segs), nsegs, total_chunks, _stream()), "halo_pack")
+
+    def halo_unpack(self, d_segs, nsegs, total_chunks):
+        check(self.lib.rpb200_halo_unpack(self.h, _ptr(d_segs), nsegs, total_chunks, _stream()),
+              "halo_unpack")
+
+    def halo_pack_signal(self, d_segs, nsegs, total_chunks, d_peer_flags, npeers, epoch):
+        check(self.lib.rpb200_halo_pack_signal(self.h, _ptr(d_segs), nsegs, total_chunks,
+                                               _ptr(d_peer_flags), npeers, epoch, _stream()),
+              "halo_pack_signal")
+
+    def halo_wait_unpack(self, d_segs, nsegs, total_chunks, d_my_flags, d_src_ranks, nsrc, epoch):
+        check(self.lib.rpb200_halo_wait_unpack(self.h, _ptr(d_segs), nsegs, total_chunks,
+                                               _ptr(d_my_flags), _ptr(d_src_ranks), nsrc, epoch,
+                                               _stream()), "halo_wait_unpack")
+
+
+def ipc_export(d_ptr: int) -> bytes:
+    lib = load()
+    buf = (c_ubyte * 64)()
+    check(lib.rpb200_ipc_export(d_ptr, buf), "ipc_export")
+    return bytes(buf)
+
+
+def ipc_open(handle: bytes) -> int:
+    lib = load()
+    buf = (c_ubyte * 64).from_buffer_copy(handle)
+    out = c_void_p()
+    check(lib.rpb200_ipc_open(buf, ctypes.byref(out)), "ipc_open")
+    return out.value
+
+
+def ipc_close(d_ptr: int):
+    check(load().rpb200_ipc_close(d_ptr), "ipc_close")

@@ -1,0 +1,116 @@
+// common.cuh -- shared pieces of the Base_B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/rpb200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "rajaperf_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+#define RPB_CHECK(expr)                                   \
+  do {                                                    \
+    cudaError_t rpb_e_ = (expr);                          \
+    if (rpb_e_ != cudaSuccess) return (int)rpb_e_;        \
+  } while (0)
+
+#define RPB_LAUNCH_CHECK() RPB_CHECK(cudaGetLastError())
+
+// One launch tuning (reference analogue: the block_size tunings, GPUUtils.hpp:345-373).
+struct rpb_tuning {
+  int block_size;   // threads per CTA
+  int ctas_per_sm;  // persistent grid = sm_count * ctas_per_sm; 0 = one tile per CTA
+  int unroll;       // independent vector accesses in flight per thread
+};
+
+enum rpb_kernel_id {
+  RPB_K_COPY = 0, RPB_K_MUL, RPB_K_ADD, RPB_K_TRIAD, RPB_K_DOT,
+  RPB_K_REDUCE_SUM, RPB_K_SCAN, RPB_K_SORT, RPB_K_SORTPAIRS,
+  RPB_K_MASS3DPA, RPB_K_DIFFUSION3DPA, RPB_K_CONVECTION3DPA, RPB_K_LTIMES,
+  RPB_K_HALO_PACKING_FUSED, RPB_K_HALO_EXCHANGE_FUSED,
+  RPB_K_COUNT
+};
+
+struct rpb200_ctx {
+  int device;
+  int sm_count;
+  rpb_tuning tune[RPB_K_COUNT];
+  // reductions: per-CTA partials + a ticket counter (self-resetting)
+  double*       d_partials;      // RPB_MAX_PARTIALS doubles
+  unsigned int* d_ticket;        // 1 counter per reduction kernel kind (2)
+  // scan: per-tile look-back state, epoch-tagged so no memset is needed per call
+  void*         d_scan_state;    // allocated lazily, grows with n
+  size_t        scan_state_bytes;
+  unsigned int  scan_epoch;
+  unsigned int* d_scan_ticket;   // dynamic tile counter, reset by the last tile
+  // diffusion: effective basis tables (48 doubles) built per call by a 1-CTA prologue
+  double*       d_basis_tables;
+};
+
+#define RPB_MAX_PARTIALS 8192
+
+// ---------------------------------------------------------------------------------
+// 256-bit / 128-bit global accesses.  sm_100a has LDG/STG.256 (ld.global.v4.f64).
+// Streaming data is touched once: bypass L1 allocation on loads and stores.
+// ---------------------------------------------------------------------------------
+struct __align__(32) dbl4 { double x, y, z, w; };
+
+__device__ __forceinline__ dbl4 ldg256_stream(const double* p)
+{
+  dbl4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256_stream(double* p, const dbl4& v)
+{
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ dbl4 ldg256(const double* p)
+{
+  dbl4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(double* p, const dbl4& v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ double2 ldg128_stream(const double* p)
+{
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+               : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg128_stream(double* p, const double2& v)
+{
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};"
+               :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline bool rpb_aligned(const void* p, size_t a) { return (((uintptr_t)p) & (a - 1)) == 0; }
+
+static inline cudaStream_t rpb_stream(rpb200_stream_t s) { return (cudaStream_t)s; }
+
+// grid for a persistent tile loop
+static inline int rpb_grid(const rpb200_ctx* ctx, const rpb_tuning& t, int64_t tiles)
+{
+  if (tiles < 1) tiles = 1;
+  if (t.ctas_per_sm <= 0) return (int)(tiles > 0x7fffffff ? 0x7fffffff : tiles);
+  int64_t g = (int64_t)ctx->sm_count * t.ctas_per_sm;
+  return (int)(g < tiles ? g : tiles);
+}

@@ -1,0 +1,165 @@
+// ctx.cu -- context, tunings, device-memory / timing / IPC helpers of the C ABI.
+#include "common.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+static const char* const k_kernel_names[RPB_K_COUNT] = {
+  "Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT",
+  "Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS",
+  "Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA", "Apps_LTIMES",
+  "Comm_HALO_PACKING_FUSED", "Comm_HALO_EXCHANGE_FUSED"
+};
+
+// Built-in defaults; see profiles/ for the sweeps that picked them.
+static void default_tunings(rpb200_ctx* c)
+{
+  for (int k = 0; k < RPB_K_COUNT; ++k) c->tune[k] = rpb_tuning{256, 8, 4};
+  c->tune[RPB_K_COPY]       = rpb_tuning{512, 0, 2};
+  c->tune[RPB_K_MUL]        = rpb_tuning{512, 0, 2};
+  c->tune[RPB_K_ADD]        = rpb_tuning{512, 0, 2};
+  c->tune[RPB_K_TRIAD]      = rpb_tuning{512, 0, 2};
+  c->tune[RPB_K_DOT]        = rpb_tuning{512, 4, 4};
+  c->tune[RPB_K_REDUCE_SUM] = rpb_tuning{512, 4, 8};
+}
+
+extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }
+
+extern "C" int rpb200_create(int device, rpb200_ctx** out)
+{
+  if (!out) return RPB200_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  RPB_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return (int)cudaErrorInvalidDevice;
+  RPB_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RPB_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    // sm_100a cubins only: there is no other code path to fall back to.
+    return (int)cudaErrorNoKernelImageForDevice;
+  }
+  rpb200_ctx* c = (rpb200_ctx*)calloc(1, sizeof(rpb200_ctx));
+  if (!c) return (int)cudaErrorMemoryAllocation;
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  default_tunings(c);
+  cudaError_t e;
+  if ((e = cudaMalloc(&c->d_partials, sizeof(double) * RPB_MAX_PARTIALS * 2)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8)) != cudaSuccess ||
+      (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_scan_ticket, sizeof(unsigned int) * 8)) != cudaSuccess ||
+      (e = cudaMemset(c->d_scan_ticket, 0, sizeof(unsigned int) * 8)) != cudaSuccess ||
+      (e = cudaMalloc(&c->d_basis_tables, sizeof(double) * 64)) != cudaSuccess) {
+    rpb200_destroy(c);
+    return (int)e;
+  }
+  c->scan_epoch = 0;
+  *out = c;
+  return 0;
+}
+
+extern "C" void rpb200_destroy(rpb200_ctx* c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_partials);
+  cudaFree(c->d_ticket);
+  cudaFree(c->d_scan_ticket);
+  cudaFree(c->d_scan_state);
+  cudaFree(c->d_basis_tables);
+  free(c);
+}
+
+extern "C" const char* rpb200_error_string(int err)
+{
+  if (err == 0) return "success";
+  if (err == RPB200_EINVAL) return "rpb200: invalid argument";
+  return cudaGetErrorString((cudaError_t)err);
+}
+
+extern "C" int rpb200_sm_count(const rpb200_ctx* c) { return c ? c->sm_count : 0; }
+
+extern "C" int rpb200_set_tuning(rpb200_ctx* c, const char* kernel, int block_size,
+                                 int ctas_per_sm, int unroll)
+{
+  if (!c || !kernel) return RPB200_EINVAL;
+  for (int k = 0; k < RPB_K_COUNT; ++k) {
+    if (strcmp(kernel, k_kernel_names[k]) == 0) {
+      if (block_size > 0) {
+        if (block_size % 32 != 0 || block_size > 1024) return RPB200_EINVAL;
+        c->tune[k].block_size = block_size;
+      }
+      if (ctas_per_sm >= 0) c->tune[k].ctas_per_sm = ctas_per_sm;
+      if (unroll > 0) c->tune[k].unroll = unroll;
+      return 0;
+    }
+  }
+  return RPB200_EINVAL;
+}
+
+// ---- memory helpers ----------------------------------------------------------------
+extern "C" int rpb200_malloc(void** p, size_t bytes) { RPB_CHECK(cudaMalloc(p, bytes)); return 0; }
+extern "C" int rpb200_free(void* p) { RPB_CHECK(cudaFree(p)); return 0; }
+extern "C" int rpb200_malloc_host(void** p, size_t bytes) { RPB_CHECK(cudaMallocHost(p, bytes)); return 0; }
+extern "C" int rpb200_free_host(void* p) { RPB_CHECK(cudaFreeHost(p)); return 0; }
+extern "C" int rpb200_memcpy_h2d(void* d, const void* h, size_t bytes, rpb200_stream_t s)
+{ RPB_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, rpb_stream(s))); return 0; }
+extern "C" int rpb200_memcpy_d2h(void* h, const void* d, size_t bytes, rpb200_stream_t s)
+{ RPB_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, rpb_stream(s))); return 0; }
+extern "C" int rpb200_memset(void* d, int v, size_t bytes, rpb200_stream_t s)
+{ RPB_CHECK(cudaMemsetAsync(d, v, bytes, rpb_stream(s))); return 0; }
+extern "C" int rpb200_stream_synchronize(rpb200_stream_t s)
+{ RPB_CHECK(cudaStreamSynchronize(rpb_stream(s))); return 0; }
+extern "C" int rpb200_device_synchronize(void) { RPB_CHECK(cudaDeviceSynchronize()); return 0; }
+
+// ---- cudaEvent timer ---------------------------------------------------------------
+struct rpb200_timer { cudaEvent_t start, stop; };
+
+extern "C" int rpb200_timer_create(rpb200_timer** out)
+{
+  if (!out) return RPB200_EINVAL;
+  rpb200_timer* t = (rpb200_timer*)calloc(1, sizeof(rpb200_timer));
+  if (!t) return (int)cudaErrorMemoryAllocation;
+  cudaError_t e;
+  if ((e = cudaEventCreate(&t->start)) != cudaSuccess) { free(t); return (int)e; }
+  if ((e = cudaEventCreate(&t->stop)) != cudaSuccess) { cudaEventDestroy(t->start); free(t); return (int)e; }
+  *out = t;
+  return 0;
+}
+extern "C" int rpb200_timer_start(rpb200_timer* t, rpb200_stream_t s)
+{ RPB_CHECK(cudaEventRecord(t->start, rpb_stream(s))); return 0; }
+extern "C" int rpb200_timer_stop(rpb200_timer* t, rpb200_stream_t s)
+{ RPB_CHECK(cudaEventRecord(t->stop, rpb_stream(s))); return 0; }
+extern "C" int rpb200_timer_elapsed_ms(rpb200_timer* t, float* ms)
+{
+  RPB_CHECK(cudaEventSynchronize(t->stop));
+  RPB_CHECK(cudaEventElapsedTime(ms, t->start, t->stop));
+  return 0;
+}
+extern "C" void rpb200_timer_destroy(rpb200_timer* t)
+{
+  if (!t) return;
+  cudaEventDestroy(t->start);
+  cudaEventDestroy(t->stop);
+  free(t);
+}
+
+// ---- CUDA IPC ----------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == RPB200_IPC_HANDLE_BYTES, "IPC handle size");
+
+extern "C" int rpb200_ipc_export(void* d_ptr, unsigned char handle[RPB200_IPC_HANDLE_BYTES])
+{
+  cudaIpcMemHandle_t h;
+  RPB_CHECK(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, sizeof(h));
+  return 0;
+}
+extern "C" int rpb200_ipc_open(const unsigned char handle[RPB200_IPC_HANDLE_BYTES], void** out)
+{
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  RPB_CHECK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+extern "C" int rpb200_ipc_close(void* d_ptr) { RPB_CHECK(cudaIpcCloseMemHandle(d_ptr)); return 0; }

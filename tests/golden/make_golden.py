@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Mint known-answer checksums from the UNMODIFIED reference binary (Base_Seq variant).
+
+Usage (in the authoring container, where /root/reference exists):
+    python tests/golden/make_golden.py [--exe oracle/_ref/raja-perf.exe]
+
+The binary is the reference's own raja-perf.exe built CPU-only from /root/reference
+(oracle/build_ref.sh).  Every case runs
+    raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [kernel flags]
+and the Base_Seq checksum printed in RAJAPerf-checksum.txt is recorded verbatim (20 digits).
+Output: tests/golden/ref_checksums.json.  The GPU box never runs this script.
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+# (kernel, size or 0 for default, reps, extra flags)
+CASES = []
+for k in ["Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT",
+          "Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS"]:
+    CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 1, 1, []), (k, 1000, 2, []), (k, 123457, 2, [])]
+for k in ["Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA"]:
+    CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 1, 1, []), (k, 5000, 2, [])]
+CASES += [("Apps_LTIMES", 0, 1, []), ("Apps_LTIMES", 0, 3, []), ("Apps_LTIMES", 5000, 2, []),
+          ("Apps_LTIMES", 100000, 1, ["--ltimes_num_d", "32", "--ltimes_num_g", "8", "--ltimes_num_m", "17"])]
+CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, []), ("Comm_HALO_PACKING_FUSED", 0, 3, []),
+          ("Comm_HALO_PACKING_FUSED", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
+          ("Comm_HALO_PACKING_FUSED", 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1"])]
+
+
+def run_case(exe, kernel, size, reps, extra, workdir):
+    out = os.path.join(workdir, "out")
+    shutil.rmtree(out, ignore_errors=True)
+    cmd = [exe, "--checkrun", str(reps), "--disable-warmup", "-k", kernel, "-v", "Base_Seq",
+           "--outdir", out] + (["--size", str(size)] if size else []) + extra
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                   env=dict(os.environ, OMP_NUM_THREADS="1"))
+    txt = open(os.path.join(out, "RAJAPerf-checksum.txt")).read()
+    m = re.search(r"^Base_Seq-\S+\s+(\S+)", txt, re.M)
+    if not m:
+        raise RuntimeError(f"no Base_Seq checksum for {kernel}:\n{txt}")
+    return m.group(1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--exe", default=os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "ref_checksums.json"))
+    a = ap.parse_args()
+    work = os.path.join(ROOT, "build", "golden_work")
+    os.makedirs(work, exist_ok=True)
+    rows = []
+    for kernel, size, reps, extra in CASES:
+        ck = run_case(a.exe, kernel, size, reps, extra, work)
+        rows.append({"kernel": kernel, "size": size, "reps": reps, "flags": extra, "variant": "Base_Seq",
+                     "checksum": ck})
+        print(kernel, size, reps, extra, ck, file=sys.stderr)
+    ver = subprocess.run([a.exe, "--help"], capture_output=True, text=True).stdout.splitlines()[:1]
+    json.dump({"source": "reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build, "
+                         "g++ 13.3 -O3, glibc rand(), x87 long double",
+               "command": "raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [flags]",
+               "cases": rows}, open(a.out, "w"), indent=1)
+    print(f"wrote {len(rows)} cases to {a.out}", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,60 @@
+"""Pin the CPU oracle to the reference: every case in tests/golden/ref_checksums.json is a
+checksum printed by the reference's own raja-perf.exe (Base_Seq); the oracle's restatement of
+setUp -> reps -> updateChecksum must reproduce it to the printed 20 significant digits."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums.json")))
+
+
+def _iparams(kernel, flags):
+    f = dict(zip(flags[0::2], flags[1::2]))
+    if kernel == "Apps_LTIMES":
+        return [int(f.get("--ltimes_num_d", 64)), int(f.get("--ltimes_num_g", 32)), int(f.get("--ltimes_num_m", 25))]
+    if kernel.startswith("Comm_HALO"):
+        return [int(f.get("--halo_width", 1)), int(f.get("--halo_num_vars", 3)), 1, 1, 1]
+    return None
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}")
+def test_oracle_reproduces_reference_checksum(case):
+    got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"]))
+    ref = np.longdouble(case["checksum"])
+    # 20 printed digits of an 80-bit long double: allow 2 units in the 19th significant digit
+    assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19) + np.longdouble(0), (got, ref)
+
+
+def test_halo_exchange_single_rank_matches_any_rank_grid():
+    """All ranks hold identical vars, so the P-rank exchange equals the 1-rank periodic
+    self-exchange; and pack results match HALO_PACKING_FUSED's send buffers."""
+    base = oracle.kat("Comm_HALO_EXCHANGE_FUSED", 8000, 2, [1, 3, 1, 1, 1])
+    for pd in ([2, 1, 1], [2, 2, 1], [2, 2, 2], [3, 1, 2]):
+        got = oracle.kat("Comm_HALO_EXCHANGE_FUSED", 8000, 2, [1, 3] + pd)
+        # the report averages P identical checksums in long double: allow that rounding
+        assert abs(got - base) <= abs(base) * np.longdouble(1e-18), (pd, got, base)
+
+
+def test_diffusion_basis_fill_covers_all_entries():
+    """The reference's aliased 12-double basis array starts uninitialised; fill #1 must write
+    every entry (else Base_Seq would read garbage).  SURVEY appendix A.3 tables for b=g=1."""
+    L = oracle.lib()
+    b = np.ones(12)
+    g = np.ones(12)
+    f1 = np.empty(12)
+    f2 = np.empty(12)
+    L.orc_diffusion3dpa_tables(b, g, f1, f2)
+    assert not np.isnan(f1).any() and not np.isnan(f2).any()
+    assert f1.tolist() == [1, 1, 1, -1, 1, 1, -1, 1, 1, -1, 1, 1]
+    assert f2.tolist() == [1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, 1]
+
+
+def test_init_counter_parity():
+    """DataUtils.cpp:504-513: factor 0.2 on even call counts, 0.1 on odd."""
+    a0 = oracle.init_real(4, 0)
+    a1 = oracle.init_real(4, 1)
+    assert a0[0] == 0.2 * 1.1 / 1.12345 and a1[0] == 0.1 * 1.1 / 1.12345
