@@ -1,0 +1,68 @@
+"""Suite-generated inputs for each kernel, produced by the oracle's restatement of the
+reference setUp() sequences.  Test infrastructure only."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle
+
+
+def _seq(calls):
+    """Run a setUp-like sequence of init calls after a counter reset.
+    calls: list of ('real', n) | ('const', n, v) | ('rand', n) | ('scalar',)"""
+    L = oracle.lib()
+    L.orc_reset_init_count()
+    out = []
+    for c in calls:
+        if c[0] == "real":
+            a = np.empty(c[1]); L.orc_init_real(a, c[1]); out.append(a)
+        elif c[0] == "const":
+            a = np.empty(c[1]); L.orc_init_const(a, c[1], c[2]); out.append(a)
+        elif c[0] == "rand":
+            a = np.empty(c[1]); L.orc_init_rand_value(a, c[1]); out.append(a)
+        elif c[0] == "scalar":
+            out.append(L.orc_init_scalar())
+    return out
+
+
+def stream_copy(n):   # stream/COPY.cpp:71-72
+    a, c = _seq([("real", n), ("const", n, 0.0)])
+    return dict(a=a, c=c)
+
+
+def stream_mul(n):    # stream/MUL.cpp:71-73
+    b, c, alpha = _seq([("const", n, 0.0), ("real", n), ("scalar",)])
+    return dict(b=b, c=c, alpha=alpha)
+
+
+def stream_add(n):    # stream/ADD.cpp:71-73
+    a, b, c = _seq([("real", n), ("real", n), ("const", n, 0.0)])
+    return dict(a=a, b=b, c=c)
+
+
+def stream_triad(n):  # stream/TRIAD.cpp:75-78
+    a, b, c, alpha = _seq([("const", n, 0.0), ("real", n), ("real", n), ("scalar",)])
+    return dict(a=a, b=b, c=c, alpha=alpha)
+
+
+def stream_dot(n):    # stream/DOT.cpp:64-69
+    a, b = _seq([("real", n), ("real", n)])
+    return dict(a=a, b=b)
+
+
+def reduce_sum(n):    # algorithm/REDUCE_SUM.cpp:62-66
+    (x,) = _seq([("real", n)])
+    return dict(x=x)
+
+
+def scan(n):          # algorithm/SCAN.cpp:68-71
+    x, y = _seq([("rand", n), ("const", n, 0.0)])
+    return dict(x=x, y=y)
+
+
+def triad_scale(n):   # stream/TRIAD.cpp:36-38 (long double, narrowed to double at the call)
+    return float(np.longdouble(0.001) * (np.longdouble(1000000) / np.longdouble(n)))
+
+
+def scan_scale(n):    # algorithm/SCAN.cpp:36-39
+    return float(np.longdouble(1e-2) * (np.longdouble(1000000) / np.longdouble(n)) / np.longdouble(n))

@@ -1,0 +1,180 @@
+"""GPU parity: Stream group + REDUCE_SUM through the C ABI vs the CPU oracle and the
+reference's golden checksums.  Elementwise kernels are bit-exact; DOT / REDUCE_SUM are in the
+tolerance class: 1e-7 absolute on the suite checksum at default size."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import suite_data as sd
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLD = {(c["kernel"], c["size"], c["reps"]): c["checksum"]
+        for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums.json")))["cases"]
+        if not c["flags"]}
+
+SIZES = [1, 3, 4, 5, 1000, 4097, 123457, 1000000, (1 << 22) + 5]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.int64)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_copy_mul_add_triad_bit_exact(ctx, n):
+    L = oracle.lib()
+    d = sd.stream_copy(n); c = dev(d["c"]); ctx.stream_copy(c, dev(d["a"]))
+    ref = d["c"].copy(); L.orc_stream_copy(ref, d["a"], n)
+    assert np.array_equal(bits(c.cpu().numpy()), bits(ref))
+
+    d = sd.stream_mul(n); b = dev(d["b"]); ctx.stream_mul(b, dev(d["c"]), d["alpha"])
+    ref = d["b"].copy(); L.orc_stream_mul(ref, d["c"], d["alpha"], n)
+    assert np.array_equal(bits(b.cpu().numpy()), bits(ref))
+
+    d = sd.stream_add(n); c = dev(d["c"]); ctx.stream_add(c, dev(d["a"]), dev(d["b"]))
+    ref = d["c"].copy(); L.orc_stream_add(ref, d["a"], d["b"], n)
+    assert np.array_equal(bits(c.cpu().numpy()), bits(ref))
+
+    d = sd.stream_triad(n); a = dev(d["a"]); ctx.stream_triad(a, dev(d["b"]), dev(d["c"]), d["alpha"])
+    ref = d["a"].copy(); L.orc_stream_triad(ref, d["b"], d["c"], d["alpha"], n)
+    assert np.array_equal(bits(a.cpu().numpy()), bits(ref))
+
+
+@pytest.mark.parametrize("tune", [(128, 0, 1), (256, 2, 2), (512, 8, 4), (256, 1, 8), (512, 0, 4)])
+def test_triad_bit_exact_for_every_tuning(ctx, tune):
+    n = 777777
+    ctx.set_tuning("Stream_TRIAD", *tune)
+    d = sd.stream_triad(n); a = dev(d["a"]); ctx.stream_triad(a, dev(d["b"]), dev(d["c"]), d["alpha"])
+    ref = d["a"].copy(); oracle.lib().orc_stream_triad(ref, d["b"], d["c"], d["alpha"], n)
+    ctx.set_tuning("Stream_TRIAD", 512, 0, 2)
+    assert np.array_equal(bits(a.cpu().numpy()), bits(ref))
+
+
+def test_unaligned_pointers_take_the_scalar_path(ctx):
+    n = 10001
+    d = sd.stream_triad(n + 1)
+    A, B, C = dev(d["a"]), dev(d["b"]), dev(d["c"])
+    ctx.stream_triad(A[1:], B[1:], C[1:], d["alpha"], n=n)      # 8-byte aligned only
+    ref = d["a"].copy(); oracle.lib().orc_stream_triad(ref[1:], d["b"][1:].copy(), d["c"][1:].copy(), d["alpha"], n)
+    got = A.cpu().numpy()
+    assert got[0] == 0.0 and np.array_equal(bits(got[1:]), bits(ref[1:]))
+
+
+def test_empty_input_is_a_no_op(ctx):
+    a = torch.zeros(8, dtype=torch.float64, device="cuda")
+    ctx.stream_copy(a, a, n=0)
+    out = torch.full((1,), 7.0, dtype=torch.float64, device="cuda")
+    ctx.stream_dot(a, a, out, init=1.5, n=0)
+    assert out.item() == 1.5
+
+
+@pytest.mark.parametrize("kernel,size,reps", [k for k in GOLD if k[0].startswith("Stream_") and k[0] != "Stream_DOT"])
+def test_suite_checksum_matches_reference_golden(ctx, kernel, size, reps):
+    """setUp -> reps x runKernel -> updateChecksum, like KernelBase::execute; the checksum must
+    equal what the reference's Base_Seq printed (bit-exact class)."""
+    n = size or 1000000
+    if kernel == "Stream_COPY":
+        d = sd.stream_copy(n); out = dev(d["c"]); a = dev(d["a"])
+        for _ in range(reps): ctx.stream_copy(out, a)
+        scale = 1.0
+    elif kernel == "Stream_MUL":
+        d = sd.stream_mul(n); out = dev(d["b"]); c = dev(d["c"])
+        for _ in range(reps): ctx.stream_mul(out, c, d["alpha"])
+        scale = 1.0
+    elif kernel == "Stream_ADD":
+        d = sd.stream_add(n); out = dev(d["c"]); a, b = dev(d["a"]), dev(d["b"])
+        for _ in range(reps): ctx.stream_add(out, a, b)
+        scale = 1.0
+    else:
+        d = sd.stream_triad(n); out = dev(d["a"]); b, c = dev(d["b"]), dev(d["c"])
+        for _ in range(reps): ctx.stream_triad(out, b, c, d["alpha"])
+        scale = sd.triad_scale(n)
+    got = oracle.checksum(out.cpu().numpy(), scale)
+    ref = np.longdouble(GOLD[(kernel, size, reps)])
+    assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19), (got, ref)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_dot_and_reduce_sum_tolerance_class(ctx, n):
+    L = oracle.lib()
+    d = sd.stream_dot(n)
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.stream_dot(dev(d["a"]), dev(d["b"]), out)
+    ref = L.orc_stream_dot(d["a"], d["b"], n, 0.0)
+    exact = math.fsum((d["a"] * d["b"]).tolist()) if n <= 1000000 else ref
+    assert abs(out.item() - ref) <= 1e-12 * abs(ref) + 1e-300
+    if n <= 1000000:   # at least as accurate as Base_Seq's left-to-right sum (up to product rounding)
+        assert abs(out.item() - exact) <= max(abs(ref - exact), 4e-16 * abs(exact))
+
+    x = sd.reduce_sum(n)["x"]
+    ctx.reduce_sum(dev(x), out)
+    ref = L.orc_reduce_sum(x, n, 0.0)
+    exact = math.fsum(x.tolist()) if n <= 1000000 else ref
+    assert abs(out.item() - ref) <= 1e-12 * abs(ref)
+    if n <= 1000000:
+        assert abs(out.item() - exact) <= max(abs(ref - exact), 4e-16 * abs(exact))
+
+
+def test_dot_accumulates_over_reps_like_m_dot(ctx):
+    """DOT-Seq.cpp:45: m_dot += dot each rep; checksum = m_dot (DOT.cpp:80); golden: 3 reps."""
+    n = 1000000
+    d = sd.stream_dot(n); a, b = dev(d["a"]), dev(d["b"])
+    m_dot = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        ctx.stream_dot(a, b, m_dot, init=0.0, accumulate=True)
+    ref = np.longdouble(GOLD[("Stream_DOT", 0, 3)])
+    assert abs(np.longdouble(m_dot.item()) - ref) < 1e-7      # the suite's own tolerance
+    one = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.stream_dot(a, b, one)
+    assert abs(np.longdouble(one.item()) - np.longdouble(GOLD[("Stream_DOT", 0, 1)])) < 1e-7
+
+
+def test_reduce_sum_suite_checksum(ctx):
+    n = 1000000
+    x = dev(sd.reduce_sum(n)["x"])
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        ctx.reduce_sum(x, out)                      # m_sum = sum (last rep wins)
+    got = oracle.checksum(out.cpu().numpy(), 1.0)   # REDUCE_SUM.cpp:75
+    assert abs(got - np.longdouble(GOLD[("Algorithm_REDUCE_SUM", 0, 3)])) < 1e-7
+
+
+def test_reductions_are_deterministic(ctx):
+    n = 3000001
+    d = sd.stream_dot(n); a, b = dev(d["a"]), dev(d["b"])
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    vals = set()
+    for _ in range(5):
+        ctx.stream_dot(a, b, out); vals.add(out.item())
+    assert len(vals) == 1
+
+
+def test_full_size_stream_properties(ctx):
+    """BASELINE config #2 size (2^28 doubles): size-independent properties instead of the oracle.
+    COPY is an identity; TRIAD/ADD/MUL equal the two-rounding IEEE result computed independently."""
+    n = 1 << 28
+    b = torch.empty(n, dtype=torch.float64, device="cuda").uniform_(0.05, 0.2)
+    c = torch.empty(n, dtype=torch.float64, device="cuda").uniform_(0.05, 0.2)
+    a = torch.zeros(n, dtype=torch.float64, device="cuda")
+    alpha = 0.1 * 1.1 / 1.12345
+    ctx.stream_copy(a, b); assert torch.equal(a, b)
+    ctx.stream_triad(a, b, c, alpha)
+    ref = torch.mul(c, alpha); ref.add_(b)            # separate roundings
+    assert torch.equal(a, ref)
+    ctx.stream_add(a, b, c); torch.add(b, c, out=ref); assert torch.equal(a, ref)
+    ctx.stream_mul(a, c, alpha); torch.mul(c, alpha, out=ref); assert torch.equal(a, ref)
+    del ref
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ctx.stream_dot(b, c, out)
+    assert abs(out.item() - torch.dot(b, c).item()) <= 1e-10 * abs(out.item())
+    ctx.reduce_sum(b, out)
+    assert abs(out.item() - b.sum().item()) <= 1e-10 * abs(out.item())
