@@ -19,8 +19,12 @@ static void default_tunings(rpb200_ctx* c)
   c->tune[RPB_K_MUL]        = rpb_tuning{512, 0, 2};
   c->tune[RPB_K_ADD]        = rpb_tuning{512, 0, 2};
   c->tune[RPB_K_TRIAD]      = rpb_tuning{512, 0, 2};
-  c->tune[RPB_K_DOT]        = rpb_tuning{512, 4, 4};
-  c->tune[RPB_K_REDUCE_SUM] = rpb_tuning{512, 4, 8};
+  c->tune[RPB_K_DOT]        = rpb_tuning{256, 8, 2};
+  c->tune[RPB_K_REDUCE_SUM] = rpb_tuning{256, 4, 8};
+  c->tune[RPB_K_SCAN]       = rpb_tuning{512, 4, 4};
+  c->tune[RPB_K_MASS3DPA]       = rpb_tuning{128, 0, 1};
+  c->tune[RPB_K_DIFFUSION3DPA]  = rpb_tuning{128, 0, 1};
+  c->tune[RPB_K_CONVECTION3DPA] = rpb_tuning{128, 0, 1};
 }
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }

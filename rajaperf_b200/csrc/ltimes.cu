@@ -1,0 +1,157 @@
+// ltimes.cu -- Apps_LTIMES: phi[z][g][m] += sum_d ell[m][d] * psi[z][g][d]   (FP64)
+//
+// Replaces apps/LTIMES-Cuda.cpp:44-102 (one thread per (z,g,m), a serial 64-long d loop doing a
+// read-modify-write of phi in global memory per step, 25 of 32 x-lanes active).
+//
+// (z,g) flattens to one row index r, so this is the skinny GEMM  Phi[R x 25] += Psi[R x 64] * Ell^T.
+// At 912 B and 3200 flop per row it sits at ~70% of the FP64 ridge: it is HBM-bound only if the
+// FP64 issue slots are spent on nothing but math.  So for the suite's shape (num_d=64, num_m=25):
+//   * the contraction runs on the FP64 tensor path, mma.sync.m8n8k4 (DMMA): one warp owns 8 rows;
+//     columns 0..23 are three 8-wide DMMA tiles, column 24 is a 16-FMA dot per lane + 2 shuffles --
+//     exactly 1600 FMA-equivalents per row, nothing padded;
+//   * the A fragments (psi) are loaded STRAIGHT from global memory in fragment order with 256-bit
+//     loads: lane (i,kk) owns psi[r0+i][16kk .. 16kk+15]; k-step s pairs element s of every lane's
+//     chunk, which is a permutation of d -- legal because the sum over d is order-free -- so no
+//     shared-memory staging or transposition of psi exists at all;
+//   * the matching B fragments (ell) are loop-invariant and live in registers for the whole kernel;
+//   * phi tiles (8 rows x 25 = 1600 contiguous bytes) are updated with coalesced 256-bit
+//     read-modify-writes through a per-warp shared staging slab; the next tile's psi is prefetched
+//     into registers while the current one is in the tensor pipe.
+// Any other (num_d, num_m) takes a plain FMA kernel.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int LT_D = 64, LT_M = 25, LT_ROWS = 8;
+constexpr int LT_WARPS = 4;
+
+__device__ __forceinline__ void lt_load_a(double (&a)[16], const double* __restrict__ psi, int64_t row, int kk)
+{
+  const double* p = psi + row * LT_D + kk * 16;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const dbl4 v = ldg256_stream(p + 4 * j);
+    a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(LT_WARPS * 32, 2)
+ltimes_dmma_kernel(double* __restrict__ phi, const double* __restrict__ ell,
+                   const double* __restrict__ psi, int64_t ntiles)
+{
+  __shared__ __align__(32) double s_c[LT_WARPS][LT_ROWS * LT_M];   // 1600 B per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = lane >> 2, kk = lane & 3;
+  double* sc = s_c[warp];
+
+  // loop-invariant B fragments: b[t][s] = ell[m = 8t + i][d = 16kk + s]; e24[s] = ell[24][16kk + s]
+  double b[3][16], e24[16];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int s = 0; s < 16; ++s) b[t][s] = __ldg(ell + (8 * t + i) * LT_D + 16 * kk + s);
+#pragma unroll
+  for (int s = 0; s < 16; ++s) e24[s] = __ldg(ell + 24 * LT_D + 16 * kk + s);
+
+  const int64_t wstride = (int64_t)gridDim.x * LT_WARPS;
+  int64_t tile = (int64_t)blockIdx.x * LT_WARPS + warp;
+  double a[16], an[16];
+  if (tile < ntiles) lt_load_a(a, psi, tile * LT_ROWS + i, kk);
+
+  for (; tile < ntiles; tile += wstride) {
+    const int64_t nxt = tile + wstride;
+    if (nxt < ntiles) lt_load_a(an, psi, nxt * LT_ROWS + i, kk);
+
+    // old phi of this tile: 200 contiguous doubles = 50 vectors of 4
+    double* ptile = phi + tile * (LT_ROWS * LT_M);
+    const dbl4 old0 = ldg256(ptile + 4 * lane);
+    dbl4 old1 = {0.0, 0.0, 0.0, 0.0};
+    if (lane < 18) old1 = ldg256(ptile + 4 * (lane + 32));
+
+    double c[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    double c24 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      dmma_884(c[0][0], c[0][1], a[s], b[0][s]);
+      dmma_884(c[1][0], c[1][1], a[s], b[1][s]);
+      dmma_884(c[2][0], c[2][1], a[s], b[2][s]);
+      c24 = fma(a[s], e24[s], c24);
+    }
+    c24 += __shfl_xor_sync(0xffffffffu, c24, 1);
+    c24 += __shfl_xor_sync(0xffffffffu, c24, 2);
+
+    // C fragment: row i, columns 8t + 2kk + {0,1}
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      sc[i * LT_M + 8 * t + 2 * kk] = c[t][0];
+      sc[i * LT_M + 8 * t + 2 * kk + 1] = c[t][1];
+    }
+    if (kk == 0) sc[i * LT_M + 24] = c24;
+    __syncwarp();
+    {
+      const dbl4 add = *reinterpret_cast<const dbl4*>(sc + 4 * lane);
+      dbl4 o; o.x = old0.x + add.x; o.y = old0.y + add.y; o.z = old0.z + add.z; o.w = old0.w + add.w;
+      stg256(ptile + 4 * lane, o);
+    }
+    if (lane < 18) {
+      const dbl4 add = *reinterpret_cast<const dbl4*>(sc + 4 * (lane + 32));
+      dbl4 o; o.x = old1.x + add.x; o.y = old1.y + add.y; o.z = old1.z + add.z; o.w = old1.w + add.w;
+      stg256(ptile + 4 * (lane + 32), o);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 16; ++s) a[s] = an[s];
+  }
+}
+
+// any shape: one thread per (row, m), FMA chain over d in the reference's order
+__global__ void __launch_bounds__(256)
+ltimes_generic_kernel(double* __restrict__ phi, const double* __restrict__ ell,
+                      const double* __restrict__ psi, int64_t nd, int64_t nm, int64_t nrows)
+{
+  const int64_t total = nrows * nm;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / nm, m = idx - r * nm;
+    const double* e = ell + m * nd;
+    const double* p = psi + r * nd;
+    double acc = phi[idx];
+    for (int64_t d = 0; d < nd; ++d) acc = fma(__ldg(e + d), __ldg(p + d), acc);
+    phi[idx] = acc;
+  }
+}
+
+}  // namespace
+
+extern "C" int rpb200_ltimes(rpb200_ctx* ctx, double* phi, const double* ell, const double* psi,
+                             int64_t num_d, int64_t num_g, int64_t num_m, int64_t num_z,
+                             rpb200_stream_t s)
+{
+  if (!ctx || num_d <= 0 || num_g <= 0 || num_m <= 0 || num_z < 0) return RPB200_EINVAL;
+  if (num_z == 0) return 0;
+  if (!phi || !ell || !psi) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  const int64_t rows = num_z * num_g;
+  if (num_d == LT_D && num_m == LT_M && rows % LT_ROWS == 0 && rpb_aligned(phi, 32) && rpb_aligned(psi, 32)) {
+    const int64_t ntiles = rows / LT_ROWS;
+    const int cps = ctx->tune[RPB_K_LTIMES].ctas_per_sm > 0 ? ctx->tune[RPB_K_LTIMES].ctas_per_sm : 2;
+    int64_t grid = (int64_t)ctx->sm_count * cps;
+    const int64_t need = (ntiles + LT_WARPS - 1) / LT_WARPS;
+    if (need < grid) grid = need;
+    ltimes_dmma_kernel<<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+  } else {
+    const int64_t total = rows * num_m;
+    int64_t grid = (total + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (grid > cap) grid = cap;
+    ltimes_generic_kernel<<<(int)grid, 256, 0, st>>>(phi, ell, psi, num_d, num_m, rows);
+  }
+  RPB_LAUNCH_CHECK();
+  return 0;
+}

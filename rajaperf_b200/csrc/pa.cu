@@ -1,0 +1,551 @@
+// pa.cu -- Apps_MASS3DPA, Apps_DIFFUSION3DPA, Apps_CONVECTION3DPA (partial-assembly FEM operators).
+//
+// Replaces apps/{MASS3DPA,DIFFUSION3DPA,CONVECTION3DPA}-Cuda.cpp: one 25- or 64-thread CTA per
+// element, every 1-D contraction a separate shared-memory round trip (8-9 __syncthreads per
+// element), basis matrices re-read from shared/global memory for every multiply.
+//
+// Design here (all three kernels): a CTA works on a BATCH of E elements in three stages, with the
+// 1-D contractions grouped so that two of them happen entirely in registers:
+//   stage A  task = (element, dz):  the dz-slab of X (D1D x D1D values) is contracted along x and
+//            then along y in registers -> a Q1D x Q1D slab per field, written to shared memory;
+//   stage B  task = (element, qy,qx pencil): contract along z, apply the quadrature-point operator
+//            D (loaded straight from global memory: a pencil index is the fastest-varying index of
+//            D, so a warp reads whole contiguous lines), contract back along z;
+//   stage C  task = (element, dz):  contract back along y then x in registers, accumulate into Y.
+// Only 2 shared-memory exchanges and 3 barriers per batch of E elements; the slab rows in shared
+// memory have an odd stride, so every access pattern is bank-conflict free.  The basis matrices
+// live in __constant__ memory (refreshed per call by a stream-ordered device-to-device copy), so
+// each FMA takes its basis operand from the constant bank instead of a shared-memory load.
+// The kernels are HBM-bound by design: algorithmic traffic only (X, D read once, Y read+written).
+//
+// Floating point: contractions are regrouped (z first on the way back) and use FMA.  With the
+// suite's integer-valued data every partial sum is exact, so results are bit-identical to Base_Seq;
+// for general data the difference is rounding-level (see tests/test_apps_gpu.py).
+#include "common.cuh"
+
+namespace {
+
+// effective dense basis tables, refreshed per call
+__constant__ double c_mass_B[20];    // [q][d]  = B[q + 5 d]     (MASS3DPA.hpp: Bsmem[q][d])
+__constant__ double c_mass_Bt[20];   // [d][q]  = Bt[q + 4 d]    (MASS3DPA.hpp: Btsmem[d][q])
+__constant__ double c_conv[36];      // B[q][d] (12) | G[q][d] (12) | Bt[d][q] (12)
+__constant__ double c_diff[48];      // B[q][d] | G*sign [q][d] | Bt[d][q] | Gt*sign [d][q]
+
+// ------------------------------------------------------------------------------------------------
+// MASS3DPA: D1D = 4, Q1D = 5
+// ------------------------------------------------------------------------------------------------
+template <int E, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
+                int64_t NE)
+{
+  constexpr int ND = 4, NQ = 5, SLAB = NQ * NQ;          // 25 values per (element, dz) slab
+  __shared__ double T[E * ND * SLAB];                    // [task = e*4+dz][25], stride 25 (odd)
+
+  const int64_t nbatch = (NE + E - 1) / E;
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t e0 = batch * E;
+    const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
+
+    // ---- stage A: (e, dz) -> contract x, then y
+    for (int t = threadIdx.x; t < cnt * ND; t += BLOCK) {
+      const double* xp = X + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
+      double x[ND][ND];
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) {
+        const dbl4 v = ldg256_stream(xp + 4 * dy);
+        x[dy][0] = v.x; x[dy][1] = v.y; x[dy][2] = v.z; x[dy][3] = v.w;
+      }
+      double a[ND][NQ];
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy)
+#pragma unroll
+        for (int qx = 0; qx < NQ; ++qx) {
+          double s = 0.0;
+#pragma unroll
+          for (int dx = 0; dx < ND; ++dx) s = fma(x[dy][dx], c_mass_B[qx * ND + dx], s);
+          a[dy][qx] = s;
+        }
+      double* tp = T + t * SLAB;
+#pragma unroll
+      for (int qy = 0; qy < NQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < NQ; ++qx) {
+          double s = 0.0;
+#pragma unroll
+          for (int dy = 0; dy < ND; ++dy) s = fma(a[dy][qx], c_mass_B[qy * ND + dy], s);
+          tp[qy * NQ + qx] = s;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B: (e, pencil) -> contract z, scale by D, contract z back
+    for (int p = threadIdx.x; p < cnt * SLAB; p += BLOCK) {
+      const int e = p / SLAB, pen = p - e * SLAB;
+      const double* dp = D + (e0 + e) * 125 + pen;
+      double dq[NQ];
+#pragma unroll
+      for (int qz = 0; qz < NQ; ++qz) dq[qz] = __ldg(dp + qz * SLAB);
+      double* tp = T + e * ND * SLAB + pen;
+      double u[ND];
+#pragma unroll
+      for (int dz = 0; dz < ND; ++dz) u[dz] = tp[dz * SLAB];
+      double q[NQ];
+#pragma unroll
+      for (int qz = 0; qz < NQ; ++qz) {
+        double s = 0.0;
+#pragma unroll
+        for (int dz = 0; dz < ND; ++dz) s = fma(u[dz], c_mass_B[qz * ND + dz], s);
+        q[qz] = s * dq[qz];
+      }
+#pragma unroll
+      for (int dz = 0; dz < ND; ++dz) {
+        double s = 0.0;
+#pragma unroll
+        for (int qz = 0; qz < NQ; ++qz) s = fma(q[qz], c_mass_Bt[dz * NQ + qz], s);
+        tp[dz * SLAB] = s;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C: (e, dz) -> contract y, then x, accumulate into Y
+    for (int t = threadIdx.x; t < cnt * ND; t += BLOCK) {
+      double* yp = Y + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
+      dbl4 yo[ND];
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) yo[dy] = ldg256(yp + 4 * dy);
+      const double* tp = T + t * SLAB;
+      double a[ND][NQ];
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy)
+#pragma unroll
+        for (int qx = 0; qx < NQ; ++qx) a[dy][qx] = 0.0;
+#pragma unroll
+      for (int qy = 0; qy < NQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < NQ; ++qx) {
+          const double c = tp[qy * NQ + qx];
+#pragma unroll
+          for (int dy = 0; dy < ND; ++dy) a[dy][qx] = fma(c, c_mass_Bt[dy * NQ + qy], a[dy][qx]);
+        }
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) {
+        double r[ND];
+#pragma unroll
+        for (int dx = 0; dx < ND; ++dx) {
+          double s = 0.0;
+#pragma unroll
+          for (int qx = 0; qx < NQ; ++qx) s = fma(a[dy][qx], c_mass_Bt[dx * NQ + qx], s);
+          r[dx] = s;
+        }
+        dbl4 o;
+        o.x = yo[dy].x + r[0]; o.y = yo[dy].y + r[1]; o.z = yo[dy].z + r[2]; o.w = yo[dy].w + r[3];
+        stg256(yp + 4 * dy, o);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces of the D1D = 3, Q1D = 4 kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int PD = 3, PQ = 4, PQ2 = PQ * PQ;      // 16 pencils per element
+constexpr int ROW = 3 * PQ2 + 1;                  // 49: three 4x4 slabs per (e,dz) task + 1 pad (odd)
+
+// cooperative, coalesced copy of a batch of X (27 doubles per element) into shared memory
+template <int BLOCK>
+__device__ __forceinline__ void load_x27(double* xs, const double* __restrict__ X, int64_t e0, int cnt)
+{
+  const double* src = X + e0 * 27;
+  for (int i = threadIdx.x; i < cnt * 27; i += BLOCK) xs[i] = __ldg(src + i);
+}
+template <int BLOCK>
+__device__ __forceinline__ void add_y27(const double* ys, double* __restrict__ Y, int64_t e0, int cnt)
+{
+  double* dst = Y + e0 * 27;
+  for (int i = threadIdx.x; i < cnt * 27; i += BLOCK) dst[i] += ys[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// CONVECTION3DPA
+// ------------------------------------------------------------------------------------------------
+template <int E, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+convection3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
+                      int64_t NE)
+{
+  __shared__ double T[E * PD * ROW];
+  __shared__ double XS[E * 27];
+  const double* cB = c_conv;        // [q][d]
+  const double* cG = c_conv + 12;   // [q][d]
+  const double* cBt = c_conv + 24;  // [d][q]
+
+  const int64_t nbatch = (NE + E - 1) / E;
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t e0 = batch * E;
+    const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
+    load_x27<BLOCK>(XS, X, e0, cnt);
+    __syncthreads();
+
+    // ---- stage A: (e,dz): Bu,Gu (contract x) then BBu, GBu, BGu (contract y)
+    for (int t = threadIdx.x; t < cnt * PD; t += BLOCK) {
+      const double* xp = XS + t * 9;
+      double bu[PD][PQ], gu[PD][PQ];
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy) {
+        const double x0 = xp[dy * 3], x1 = xp[dy * 3 + 1], x2 = xp[dy * 3 + 2];
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          bu[dy][qx] = fma(cB[qx * PD + 2], x2, fma(cB[qx * PD + 1], x1, cB[qx * PD] * x0));
+          gu[dy][qx] = fma(cG[qx * PD + 2], x2, fma(cG[qx * PD + 1], x1, cG[qx * PD] * x0));
+        }
+      }
+      double* tp = T + t * ROW;
+#pragma unroll
+      for (int qy = 0; qy < PQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          double bbu = 0.0, gbu = 0.0, bgu = 0.0;
+#pragma unroll
+          for (int dy = 0; dy < PD; ++dy) {
+            bbu = fma(cB[qy * PD + dy], bu[dy][qx], bbu);
+            gbu = fma(cG[qy * PD + dy], bu[dy][qx], gbu);
+            bgu = fma(cB[qy * PD + dy], gu[dy][qx], bgu);
+          }
+          tp[qy * PQ + qx] = bbu;
+          tp[PQ2 + qy * PQ + qx] = gbu;
+          tp[2 * PQ2 + qy * PQ + qx] = bgu;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B: (e,pencil): contract z, apply D, contract z back (into slab 0)
+    for (int p = threadIdx.x; p < cnt * PQ2; p += BLOCK) {
+      const int e = p >> 4, pen = p & 15;
+      const double* dp = D + (e0 + e) * 192 + pen;
+      double o[3][PQ];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int qz = 0; qz < PQ; ++qz) o[c][qz] = __ldg(dp + c * 64 + qz * PQ2);
+      double* tp = T + e * PD * ROW + pen;
+      double bbu[PD], gbu[PD], bgu[PD];
+#pragma unroll
+      for (int dz = 0; dz < PD; ++dz) {
+        bbu[dz] = tp[dz * ROW]; gbu[dz] = tp[dz * ROW + PQ2]; bgu[dz] = tp[dz * ROW + 2 * PQ2];
+      }
+      double dgu[PQ];
+#pragma unroll
+      for (int qz = 0; qz < PQ; ++qz) {
+        double gz = 0.0, gy = 0.0, gx = 0.0;
+#pragma unroll
+        for (int dz = 0; dz < PD; ++dz) {
+          gz = fma(cG[qz * PD + dz], bbu[dz], gz);     // GBBu
+          gy = fma(cB[qz * PD + dz], gbu[dz], gy);     // BGBu
+          gx = fma(cB[qz * PD + dz], bgu[dz], gx);     // BBGu
+        }
+        dgu[qz] = fma(o[2][qz], gz, fma(o[1][qz], gy, o[0][qz] * gx));
+      }
+#pragma unroll
+      for (int dz = 0; dz < PD; ++dz) {
+        double s = 0.0;
+#pragma unroll
+        for (int qz = 0; qz < PQ; ++qz) s = fma(cBt[dz * PQ + qz], dgu[qz], s);
+        tp[dz * ROW] = s;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C: (e,dz): contract y then x; results go to XS (reused as Y staging)
+    for (int t = threadIdx.x; t < cnt * PD; t += BLOCK) {
+      const double* tp = T + t * ROW;
+      double a[PD][PQ];
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) a[dy][qx] = 0.0;
+#pragma unroll
+      for (int qy = 0; qy < PQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          const double v = tp[qy * PQ + qx];
+#pragma unroll
+          for (int dy = 0; dy < PD; ++dy) a[dy][qx] = fma(cBt[dy * PQ + qy], v, a[dy][qx]);
+        }
+      double* yp = XS + t * 9;
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < PD; ++dx) {
+          double s = 0.0;
+#pragma unroll
+          for (int qx = 0; qx < PQ; ++qx) s = fma(cBt[dx * PQ + qx], a[dy][qx], s);
+          yp[dy * 3 + dx] = s;
+        }
+    }
+    __syncthreads();
+    add_y27<BLOCK>(XS, Y, e0, cnt);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DIFFUSION3DPA
+// ------------------------------------------------------------------------------------------------
+// Builds the four dense tables from the reference's aliased half-stored basis array, reproducing
+// the Base_Seq fill order (DIFFUSION3DPA-Seq.cpp:45-49, 75-79; DIFFUSION3DPA.hpp:245-268, 301-305).
+__global__ void diffusion_tables_kernel(const double* __restrict__ Basis, const double* __restrict__ dBasis,
+                                        double* __restrict__ out /*48*/)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  auto qi = [](int q, int d) { return (q <= d) ? q : PQ - 1 - q; };
+  auto dj = [](int q, int d) { return (q <= d) ? d : PD - 1 - d; };
+  auto qk = [](int q, int d) { return (q <= d) ? PQ - 1 - q : q; };
+  auto dl = [](int q, int d) { return (q <= d) ? PD - 1 - d : d; };
+  auto sg = [](int q, int d) { return (q <= d) ? -1.0 : 1.0; };
+  double t[12];
+  for (int i = 0; i < 12; ++i) t[i] = 0.0;
+  for (int dy = 0; dy < PD; ++dy)          // fill #1: B[i][j] then G[k][l], viewed [4][3]
+    for (int qx = 0; qx < PQ; ++qx) {
+      t[qi(qx, dy) * PD + dj(qx, dy)] = Basis[qx + PQ * dy];
+      t[qk(qx, dy) * PD + dl(qx, dy)] = dBasis[qx + PQ * dy] * sg(qx, dy);
+    }
+  for (int q = 0; q < PQ; ++q)
+    for (int d = 0; d < PD; ++d) {
+      out[q * PD + d] = t[qi(q, d) * PD + dj(q, d)];                     // B(q,d) as steps 3-5 read it
+      out[12 + q * PD + d] = t[qk(q, d) * PD + dl(q, d)] * sg(q, d);     // G(q,d) * sign
+    }
+  for (int d = 0; d < PD; ++d)             // fill #2 on top of fill #1, viewed [3][4]
+    for (int q = 0; q < PQ; ++q) {
+      t[dj(q, d) * PQ + qi(q, d)] = Basis[q + PQ * d];
+      t[dl(q, d) * PQ + qk(q, d)] = dBasis[q + PQ * d] * sg(q, d);
+    }
+  for (int d = 0; d < PD; ++d)
+    for (int q = 0; q < PQ; ++q) {
+      out[24 + d * PQ + q] = t[dj(q, d) * PQ + qi(q, d)];                // Bt(d,q) as steps 7-9 read it
+      out[36 + d * PQ + q] = t[dl(q, d) * PQ + qk(q, d)] * sg(q, d);     // Gt(d,q) * sign
+    }
+}
+
+template <int E, int BLOCK, bool SYMM>
+__global__ void __launch_bounds__(BLOCK)
+diffusion3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
+                     int64_t NE)
+{
+  __shared__ double T[E * PD * ROW];
+  __shared__ double XS[E * 27];
+  const double* cB = c_diff;         // [q][d]
+  const double* cG = c_diff + 12;    // [q][d], sign folded in
+  const double* cBt = c_diff + 24;   // [d][q]
+  const double* cGt = c_diff + 36;   // [d][q], sign folded in
+
+  const int64_t nbatch = (NE + E - 1) / E;
+  for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
+    const int64_t e0 = batch * E;
+    const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
+    load_x27<BLOCK>(XS, X, e0, cnt);
+    __syncthreads();
+
+    // ---- stage A (steps 3,4): (e,dz) -> DQQ0 = G_x B_y, DQQ1 = B_x G_y, DQQ2 = B_x B_y
+    for (int t = threadIdx.x; t < cnt * PD; t += BLOCK) {
+      const double* xp = XS + t * 9;
+      double b0[PD][PQ], g0[PD][PQ];     // DDQ0 (B in x), DDQ1 (G in x)
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy) {
+        const double x0 = xp[dy * 3], x1 = xp[dy * 3 + 1], x2 = xp[dy * 3 + 2];
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          b0[dy][qx] = fma(x2, cB[qx * PD + 2], fma(x1, cB[qx * PD + 1], x0 * cB[qx * PD]));
+          g0[dy][qx] = fma(x2, cG[qx * PD + 2], fma(x1, cG[qx * PD + 1], x0 * cG[qx * PD]));
+        }
+      }
+      double* tp = T + t * ROW;
+#pragma unroll
+      for (int qy = 0; qy < PQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+#pragma unroll
+          for (int dy = 0; dy < PD; ++dy) {
+            u = fma(g0[dy][qx], cB[qy * PD + dy], u);
+            v = fma(b0[dy][qx], cG[qy * PD + dy], v);
+            w = fma(b0[dy][qx], cB[qy * PD + dy], w);
+          }
+          tp[qy * PQ + qx] = u;
+          tp[PQ2 + qy * PQ + qx] = v;
+          tp[2 * PQ2 + qy * PQ + qx] = w;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage B (steps 5 and 9's z contraction): (e,pencil)
+    for (int p = threadIdx.x; p < cnt * PQ2; p += BLOCK) {
+      const int e = p >> 4, pen = p & 15;
+      const double* dp = D + (e0 + e) * 384 + pen;        // stride SYM = 6 slabs per element
+      double* tp = T + e * PD * ROW + pen;
+      double q0[PD], q1[PD], q2[PD];
+#pragma unroll
+      for (int dz = 0; dz < PD; ++dz) {
+        q0[dz] = tp[dz * ROW]; q1[dz] = tp[dz * ROW + PQ2]; q2[dz] = tp[dz * ROW + 2 * PQ2];
+      }
+      double r0[PQ], r1[PQ], r2[PQ];
+#pragma unroll
+      for (int qz = 0; qz < PQ; ++qz) {
+        double gX = 0.0, gY = 0.0, gZ = 0.0;
+#pragma unroll
+        for (int dz = 0; dz < PD; ++dz) {
+          gX = fma(q0[dz], cB[qz * PD + dz], gX);
+          gY = fma(q1[dz], cB[qz * PD + dz], gY);
+          gZ = fma(q2[dz], cG[qz * PD + dz], gZ);
+        }
+        const double* dq = dp + qz * PQ2;
+        const double O11 = __ldg(dq), O12 = __ldg(dq + 64), O13 = __ldg(dq + 128);
+        double O21, O22, O23, O31, O32, O33;
+        if (SYMM) {
+          O21 = O12; O22 = __ldg(dq + 192); O23 = __ldg(dq + 256);
+          O31 = O13; O32 = O23;             O33 = __ldg(dq + 320);
+        } else {   // DIFFUSION3DPA.hpp:389-397 reads slabs 3..8 (beyond the SYM=6 stride, as the reference does)
+          O21 = __ldg(dq + 192); O22 = __ldg(dq + 256); O23 = __ldg(dq + 320);
+          O31 = __ldg(dq + 384); O32 = __ldg(dq + 448); O33 = __ldg(dq + 512);
+        }
+        r0[qz] = fma(O13, gZ, fma(O12, gY, O11 * gX));
+        r1[qz] = fma(O23, gZ, fma(O22, gY, O21 * gX));
+        r2[qz] = fma(O33, gZ, fma(O32, gY, O31 * gX));
+      }
+#pragma unroll
+      for (int dz = 0; dz < PD; ++dz) {
+        double u = 0.0, v = 0.0, w = 0.0;
+#pragma unroll
+        for (int qz = 0; qz < PQ; ++qz) {
+          u = fma(r0[qz], cBt[dz * PQ + qz], u);
+          v = fma(r1[qz], cBt[dz * PQ + qz], v);
+          w = fma(r2[qz], cGt[dz * PQ + qz], w);
+        }
+        tp[dz * ROW] = u; tp[dz * ROW + PQ2] = v; tp[dz * ROW + 2 * PQ2] = w;
+      }
+    }
+    __syncthreads();
+
+    // ---- stage C (steps 8,7): (e,dz): field0: Bt_y Gt_x, field1: Gt_y Bt_x, field2: Bt_y Bt_x
+    for (int t = threadIdx.x; t < cnt * PD; t += BLOCK) {
+      const double* tp = T + t * ROW;
+      double a0[PD][PQ], a1[PD][PQ], a2[PD][PQ];
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) { a0[dy][qx] = 0.0; a1[dy][qx] = 0.0; a2[dy][qx] = 0.0; }
+#pragma unroll
+      for (int qy = 0; qy < PQ; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < PQ; ++qx) {
+          const double f0 = tp[qy * PQ + qx], f1 = tp[PQ2 + qy * PQ + qx], f2 = tp[2 * PQ2 + qy * PQ + qx];
+#pragma unroll
+          for (int dy = 0; dy < PD; ++dy) {
+            a0[dy][qx] = fma(f0, cBt[dy * PQ + qy], a0[dy][qx]);
+            a1[dy][qx] = fma(f1, cGt[dy * PQ + qy], a1[dy][qx]);
+            a2[dy][qx] = fma(f2, cBt[dy * PQ + qy], a2[dy][qx]);
+          }
+        }
+      double* yp = XS + t * 9;
+#pragma unroll
+      for (int dy = 0; dy < PD; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < PD; ++dx) {
+          double u = 0.0, v = 0.0, w = 0.0;
+#pragma unroll
+          for (int qx = 0; qx < PQ; ++qx) {
+            u = fma(a0[dy][qx], cGt[dx * PQ + qx], u);
+            v = fma(a1[dy][qx], cBt[dx * PQ + qx], v);
+            w = fma(a2[dy][qx], cBt[dx * PQ + qx], w);
+          }
+          yp[dy * 3 + dx] = (u + v + w);
+        }
+    }
+    __syncthreads();
+    add_y27<BLOCK>(XS, Y, e0, cnt);
+    __syncthreads();
+  }
+}
+
+// tables for MASS / CONVECTION: plain re-indexing of the caller's device arrays
+__global__ void mass_tables_kernel(const double* __restrict__ B, const double* __restrict__ Bt, double* out)
+{
+  const int i = threadIdx.x;
+  if (i < 20) {
+    { const int q = i / 4, d = i % 4; out[i] = B[q + 5 * d]; }            // Bsmem[q][d]
+    { const int d = i / 5, q = i % 5; out[20 + i] = Bt[q + 4 * d]; }      // Btsmem[d][q]
+  }
+}
+__global__ void conv_tables_kernel(const double* __restrict__ B, const double* __restrict__ Bt,
+                                   const double* __restrict__ G, double* out)
+{
+  const int i = threadIdx.x;
+  if (i < 12) {
+    { const int q = i / 3, d = i % 3; out[i] = B[q + 4 * d]; out[12 + i] = G[q + 4 * d]; }   // cpa_B / cpa_G
+    { const int d = i / 4, q = i % 4; out[24 + i] = Bt[d + 3 * q]; }                         // cpa_Bt(d,q)
+  }
+}
+
+constexpr int PA_E = 32, PA_BLOCK = 128;
+
+inline int pa_grid(const rpb200_ctx* ctx, int kid, int64_t NE)
+{
+  const int64_t nbatch = (NE + PA_E - 1) / PA_E;
+  const int cps = ctx->tune[kid].ctas_per_sm;
+  if (cps <= 0) return (int)(nbatch > 0x7fffffff ? 0x7fffffff : nbatch);
+  const int64_t g = (int64_t)ctx->sm_count * cps;
+  return (int)(g < nbatch ? g : nbatch);
+}
+
+}  // namespace
+
+extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* Bt, const double* D,
+                               const double* X, double* Y, int64_t NE, rpb200_stream_t s)
+{
+  if (!ctx || NE < 0 || (NE > 0 && (!B || !Bt || !D || !X || !Y))) return RPB200_EINVAL;
+  if (NE == 0) return 0;
+  if (!rpb_aligned(X, 32) || !rpb_aligned(Y, 32)) return RPB200_EINVAL;   // 512-byte elements
+  cudaStream_t st = rpb_stream(s);
+  mass_tables_kernel<<<1, 32, 0, st>>>(B, Bt, ctx->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, ctx->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, ctx->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+  mass3dpa_kernel<PA_E, PA_BLOCK><<<pa_grid(ctx, RPB_K_MASS3DPA, NE), PA_BLOCK, 0, st>>>(D, X, Y, NE);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rpb200_convection3dpa(rpb200_ctx* ctx, const double* Basis, const double* tBasis,
+                                     const double* dBasis, const double* D, const double* X, double* Y,
+                                     int64_t NE, rpb200_stream_t s)
+{
+  if (!ctx || NE < 0 || (NE > 0 && (!Basis || !tBasis || !dBasis || !D || !X || !Y))) return RPB200_EINVAL;
+  if (NE == 0) return 0;
+  cudaStream_t st = rpb_stream(s);
+  conv_tables_kernel<<<1, 32, 0, st>>>(Basis, tBasis, dBasis, ctx->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_conv, ctx->d_basis_tables, 36 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+  convection3dpa_kernel<PA_E, PA_BLOCK><<<pa_grid(ctx, RPB_K_CONVECTION3DPA, NE), PA_BLOCK, 0, st>>>(D, X, Y, NE);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rpb200_diffusion3dpa(rpb200_ctx* ctx, const double* Basis, const double* dBasis,
+                                    const double* D, const double* X, double* Y, int64_t NE,
+                                    int symmetric, rpb200_stream_t s)
+{
+  if (!ctx || NE < 0 || (NE > 0 && (!Basis || !dBasis || !D || !X || !Y))) return RPB200_EINVAL;
+  if (NE == 0) return 0;
+  cudaStream_t st = rpb_stream(s);
+  diffusion_tables_kernel<<<1, 32, 0, st>>>(Basis, dBasis, ctx->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_diff, ctx->d_basis_tables, 48 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+  const int grid = pa_grid(ctx, RPB_K_DIFFUSION3DPA, NE);
+  if (symmetric)
+    diffusion3dpa_kernel<PA_E, PA_BLOCK, true><<<grid, PA_BLOCK, 0, st>>>(D, X, Y, NE);
+  else
+    diffusion3dpa_kernel<PA_E, PA_BLOCK, false><<<grid, PA_BLOCK, 0, st>>>(D, X, Y, NE);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}

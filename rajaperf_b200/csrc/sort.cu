@@ -1,0 +1,365 @@
+// sort.cu -- Algorithm_SORT / Algorithm_SORTPAIRS: LSD radix sort of doubles for sm_100a.
+//
+// Replaces algorithm/SORT-Cuda.cpp:35-43 and SORTPAIRS-Cuda.cpp:35-43, i.e. RAJA::sort /
+// RAJA::sort_pairs -> cub::DeviceRadixSort (tpl/RAJA/include/RAJA/policy/cuda/sort.hpp:86-146,
+// 337-409) with its per-call pool malloc/free and tail cudaMemcpyAsync.  Written from scratch:
+//   * keys are mapped to order-preserving uint64 (sign flip / full flip) on the way in and back on
+//     the way out, fused into the first and last pass;
+//   * one histogram kernel reads the keys once and builds all 8 digit histograms;
+//   * 8 "onesweep" passes (8-bit digits): each tile ranks its keys with warp match-any, publishes
+//     its 256 digit counts, and resolves the counts of all earlier tiles by decoupled look-back, so
+//     every pass reads and writes each key exactly once (16 B/key/pass, 32 B for pairs);
+//   * keys are first reordered by digit in shared memory, so the global scatter is made of
+//     contiguous runs;
+//   * look-back descriptors carry a pass-parity code, so they are never cleared between passes or
+//     between calls of the same size; tiles are dealt by atomic ticket (no reliance on CTA order);
+//   * caller-provided scratch, no allocation, no host synchronisation; stable (pairs well-defined).
+#include "common.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int NUM_PASSES = 64 / RADIX_BITS;
+
+constexpr int SORT_WARPS = 16;                 // 512 threads
+constexpr int SORT_IPT = 16;                   // keys per thread
+constexpr int SORT_BLOCK = SORT_WARPS * 32;
+constexpr int SORT_TILE = SORT_BLOCK * SORT_IPT;   // 8192 keys
+
+// double -> uint64 whose unsigned order is the IEEE total order (-0 < +0, no NaN handling needed)
+__device__ __forceinline__ unsigned long long key_encode(unsigned long long b)
+{
+  const unsigned long long m = (unsigned long long)((long long)b >> 63) | 0x8000000000000000ull;
+  return b ^ m;
+}
+__device__ __forceinline__ unsigned long long key_decode(unsigned long long k)
+{
+  const unsigned long long m = (unsigned long long)((long long)(~k) >> 63) | 0x8000000000000000ull;
+  return k ^ m;
+}
+
+// Lanes holding the same 8-bit digit.  Built from 8 warp ballots: the hardware MATCH.ANY instruction
+// is an order of magnitude slower on sm_100 (profiles/r01_sort_ncu.md).
+__device__ __forceinline__ unsigned int match_digit(unsigned int d)
+{
+  unsigned int peers = 0xffffffffu;
+#pragma unroll
+  for (int bit = 0; bit < RADIX_BITS; ++bit) {
+    const bool one = (d >> bit) & 1u;
+    const unsigned int vote = __ballot_sync(0xffffffffu, one);
+    peers &= one ? vote : ~vote;
+  }
+  return peers;
+}
+
+struct sort_scratch_layout {
+  size_t off_alt_keys, off_alt_vals, off_hist, off_ctrs, off_desc, total;
+  int64_t tiles;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline sort_scratch_layout make_layout(int64_t n, int pairs)
+{
+  sort_scratch_layout L;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  L.tiles = (int64_t)((nn + SORT_TILE - 1) / SORT_TILE);
+  size_t o = 0;
+  L.off_alt_keys = o; o = align_up(o + nn * 8, 256);
+  L.off_alt_vals = o; if (pairs) o = align_up(o + nn * 8, 256);
+  L.off_hist = o;     o = align_up(o + sizeof(unsigned long long) * NUM_PASSES * RADIX, 256);
+  L.off_ctrs = o;     o = align_up(o + sizeof(unsigned int) * 2 * NUM_PASSES + 64, 256);
+  L.off_desc = o;     o = align_up(o + sizeof(unsigned long long) * RADIX * (size_t)L.tiles, 256);
+  L.total = o;
+  return L;
+}
+
+// ----------------------------------------------------------------------------------------------
+// histogram of all 8 digits in one read of the keys
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+sort_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                 unsigned long long* __restrict__ g_hist)
+{
+  __shared__ unsigned int s_hist[NUM_PASSES][RADIX];
+  for (int i = threadIdx.x; i < NUM_PASSES * RADIX; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n_round = (n + 31) & ~31ll;          // whole warps iterate together
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const bool ok = i < n;
+    const unsigned long long k = ok ? key_encode(keys[i]) : 0ull;
+#pragma unroll
+    for (int p = 0; p < NUM_PASSES; ++p) {
+      const unsigned int d = (unsigned int)(k >> (p * RADIX_BITS)) & (RADIX - 1);
+      if (p >= 5) {
+        // exponent bytes of similar-magnitude keys: usually the whole warp hits one bin
+        const unsigned int d0 = __shfl_sync(0xffffffffu, d, 0);
+        if (__all_sync(0xffffffffu, ok && d == d0)) {
+          if (lane == 0) atomicAdd(&s_hist[p][d], 32u);
+          continue;
+        }
+      }
+      if (ok) atomicAdd(&s_hist[p][d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NUM_PASSES * RADIX; i += blockDim.x) {
+    const unsigned int c = (&s_hist[0][0])[i];
+    if (c) atomicAdd(&g_hist[i], (unsigned long long)c);
+  }
+}
+
+// exclusive scan of each digit histogram in place: g_hist[p][b] = #keys with digit_p < b
+__global__ void __launch_bounds__(RADIX)
+sort_hist_scan_kernel(unsigned long long* __restrict__ g_hist)
+{
+  __shared__ unsigned long long s[RADIX];
+  const int p = blockIdx.x, b = threadIdx.x;
+  const unsigned long long c = g_hist[p * RADIX + b];
+  s[b] = c;
+  __syncthreads();
+  for (int o = 1; o < RADIX; o <<= 1) {
+    const unsigned long long t = (b >= o) ? s[b - o] : 0ull;
+    __syncthreads();
+    s[b] += t;
+    __syncthreads();
+  }
+  g_hist[p * RADIX + b] = s[b] - c;
+}
+
+// ----------------------------------------------------------------------------------------------
+// one onesweep pass
+// ----------------------------------------------------------------------------------------------
+// descriptor word = (count << 2) | code; code = 2*parity + (0: tile aggregate, 1: inclusive prefix).
+// A word whose parity differs from the running pass is a leftover of the previous pass: not ready.
+__device__ __forceinline__ unsigned long long ld_desc(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+template <bool PAIRS, bool FIRST, bool LAST>
+__global__ void __launch_bounds__(SORT_BLOCK)
+sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
+                     const unsigned long long* __restrict__ vals_in, unsigned long long* __restrict__ vals_out,
+                     int64_t n, int shift, const unsigned long long* __restrict__ g_base /*[RADIX]*/,
+                     unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket,
+                     unsigned int num_tiles, unsigned int parity)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);            // [TILE]
+  unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_keys + SORT_TILE);               // [WARPS][RADIX]
+  unsigned int* s_bin_start = s_cnt + SORT_WARPS * RADIX;                                  // [RADIX]
+  long long* s_delta = reinterpret_cast<long long*>(s_bin_start + RADIX);                  // [RADIX]
+  unsigned char* s_digit = reinterpret_cast<unsigned char*>(s_delta + RADIX);              // [TILE] (pairs)
+  __shared__ unsigned int s_tile;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned int lt_mask = (1u << lane) - 1u;
+
+  if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[0], 1u);
+  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_BLOCK) s_cnt[i] = 0u;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  const int64_t tile_base = (int64_t)tile * SORT_TILE;
+  const int valid = (int)((n - tile_base) < (int64_t)SORT_TILE ? (n - tile_base) : (int64_t)SORT_TILE);
+
+  // ---- load: warp w owns the contiguous chunk [w*32*IPT, (w+1)*32*IPT); round r, lane l
+  unsigned long long key[SORT_IPT];
+  unsigned long long val[PAIRS ? SORT_IPT : 1];
+  const int chunk = warp * 32 * SORT_IPT + lane;
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const int p = chunk + r * 32;
+    unsigned long long k = 0xffffffffffffffffull;           // padding sorts last, never written
+    if (p < valid) {
+      k = keys_in[tile_base + p];
+      if (FIRST) k = key_encode(k);
+    }
+    key[r] = k;
+    if (PAIRS) val[r] = (p < valid) ? vals_in[tile_base + p] : 0ull;
+  }
+
+  // ---- rank inside the warp chunk (stable): match-any on the digit
+  unsigned short rank[SORT_IPT];
+  unsigned int* my_cnt = s_cnt + warp * RADIX;
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const unsigned int d = (unsigned int)(key[r] >> shift) & (RADIX - 1);
+    const unsigned int peers = match_digit(d);
+    const int leader = __ffs(peers) - 1;
+    unsigned int before = 0;
+    if (lane == leader) { before = my_cnt[d]; my_cnt[d] = before + __popc(peers); }
+    before = __shfl_sync(0xffffffffu, before, leader);
+    rank[r] = (unsigned short)(before + __popc(peers & lt_mask));
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit: scan the warp counts, publish the tile count, look back
+  unsigned int my_total = 0;
+  if (threadIdx.x < RADIX) {
+    const int b = threadIdx.x;
+    unsigned int run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) { const unsigned int c = s_cnt[w * RADIX + b]; s_cnt[w * RADIX + b] = run; run += c; }
+    my_total = run;
+    const unsigned long long code_agg = 2ull * parity, code_inc = 2ull * parity + 1ull;
+    if (tile + 1 < num_tiles)     // nobody looks at the last tile
+      st_desc(desc + (size_t)tile * RADIX + b, ((unsigned long long)my_total << 2) | (tile == 0 ? code_inc : code_agg));
+  }
+  // tile-local exclusive scan of the 256 digit totals (positions in the reordered tile)
+  {
+    unsigned int inc = my_total;            // threads >= RADIX hold 0
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+    __shared__ unsigned int s_wsum[SORT_WARPS];
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x < RADIX) {
+      unsigned int wbase = 0;
+      for (int w = 0; w < (RADIX / 32); ++w) if (w < warp) wbase += s_wsum[w];
+      s_bin_start[threadIdx.x] = wbase + inc - my_total;
+    }
+  }
+  if (threadIdx.x < RADIX) {
+    const int b = threadIdx.x;
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      int64_t look = (int64_t)tile - 1;
+      for (;;) {
+        unsigned long long w;
+        do { w = ld_desc(desc + (size_t)look * RADIX + b); } while (((w >> 1) & 1ull) != parity);
+        excl += (w >> 2);
+        if (w & 1ull) break;          // inclusive prefix of that tile: done
+        --look;
+      }
+      if (tile + 1 < num_tiles)
+        st_desc(desc + (size_t)tile * RADIX + b, ((excl + my_total) << 2) | (2ull * parity + 1ull));
+    }
+    s_delta[b] = (long long)(g_base[b] + excl) - (long long)s_bin_start[b];
+  }
+  __syncthreads();
+
+  // ---- reorder by digit in shared memory
+  int pos[SORT_IPT];
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const unsigned int d = (unsigned int)(key[r] >> shift) & (RADIX - 1);
+    pos[r] = (int)(s_bin_start[d] + my_cnt[d] + rank[r]);
+    s_keys[pos[r]] = key[r];
+    if (PAIRS) s_digit[pos[r]] = (unsigned char)d;
+  }
+  __syncthreads();
+
+  // ---- write out: contiguous runs per digit
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const int p = threadIdx.x + r * SORT_BLOCK;
+    if (p < valid) {
+      unsigned long long k = s_keys[p];
+      const unsigned int d = (unsigned int)(k >> shift) & (RADIX - 1);
+      if (LAST) k = key_decode(k);
+      keys_out[p + s_delta[d]] = k;
+    }
+  }
+  if (PAIRS) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) s_keys[pos[r]] = val[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+      const int p = threadIdx.x + r * SORT_BLOCK;
+      if (p < valid) vals_out[p + s_delta[s_digit[p]]] = s_keys[p];
+    }
+  }
+}
+
+template <bool PAIRS>
+int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scratch, size_t scratch_bytes,
+              rpb200_stream_t s)
+{
+  if (!ctx || n < 0 || (n > 0 && (!keys || (PAIRS && !vals)))) return RPB200_EINVAL;
+  if (n <= 1) return 0;
+  const sort_scratch_layout L = make_layout(n, PAIRS ? 1 : 0);
+  if (!scratch || scratch_bytes < L.total || !rpb_aligned(scratch, 256)) return RPB200_EINVAL;
+  if (L.tiles > 0x7ffffff0ll) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  unsigned char* base = (unsigned char*)scratch;
+  unsigned long long* alt_keys = (unsigned long long*)(base + L.off_alt_keys);
+  unsigned long long* alt_vals = (unsigned long long*)(base + L.off_alt_vals);
+  unsigned long long* hist = (unsigned long long*)(base + L.off_hist);
+  unsigned int* ctrs = (unsigned int*)(base + L.off_ctrs);
+  unsigned long long* desc = (unsigned long long*)(base + L.off_desc);
+  const unsigned int tiles = (unsigned int)L.tiles;
+
+  // histograms + tickets are cleared per call (18 KB); descriptors only need parity 1 before pass 0,
+  // which is what pass 7 of a previous same-shape sort leaves behind -- but scratch is caller-owned
+  // and may be fresh, so it is set once per call too (8*RADIX*tiles bytes, ~0.2% of the key traffic)
+  RPB_CHECK(cudaMemsetAsync(base + L.off_hist, 0, L.off_desc - L.off_hist, st));
+  RPB_CHECK(cudaMemsetAsync(desc, 0xff, sizeof(unsigned long long) * RADIX * (size_t)tiles, st));
+
+  {
+    int grid = ctx->sm_count * 4;
+    int64_t need = (n + 511) / 512;
+    if (need < grid) grid = (int)need;
+    sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist);
+    RPB_LAUNCH_CHECK();
+    sort_hist_scan_kernel<<<NUM_PASSES, RADIX, 0, st>>>(hist);
+    RPB_LAUNCH_CHECK();
+  }
+
+  const size_t smem = sizeof(unsigned long long) * SORT_TILE + sizeof(unsigned int) * SORT_WARPS * RADIX +
+                      sizeof(unsigned int) * RADIX + sizeof(long long) * RADIX + (PAIRS ? SORT_TILE : 0);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[PAIRS ? 1 : 0]) {
+    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[PAIRS ? 1 : 0] = true;
+  }
+
+  unsigned long long* kin = (unsigned long long*)keys; unsigned long long* kout = alt_keys;
+  unsigned long long* vin = (unsigned long long*)vals; unsigned long long* vout = alt_vals;
+  for (int p = 0; p < NUM_PASSES; ++p) {
+    const unsigned int parity = (unsigned int)(p & 1);
+    const int shift = p * RADIX_BITS;
+    if (p == 0)
+      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+    else if (p == NUM_PASSES - 1)
+      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+    else
+      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+    RPB_LAUNCH_CHECK();
+    unsigned long long* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+  // 8 passes: the result is back in the caller's arrays
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t rpb200_sort_scratch_bytes(int64_t n, int pairs)
+{
+  if (n < 0) return 0;
+  return make_layout(n, pairs).total;
+}
+
+extern "C" int rpb200_sort_keys_f64(rpb200_ctx* ctx, double* keys, int64_t n, void* scratch,
+                                    size_t scratch_bytes, rpb200_stream_t s)
+{ return sort_impl<false>(ctx, keys, nullptr, n, scratch, scratch_bytes, s); }
+
+extern "C" int rpb200_sort_pairs_f64(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scratch,
+                                     size_t scratch_bytes, rpb200_stream_t s)
+{ return sort_impl<true>(ctx, keys, vals, n, scratch, scratch_bytes, s); }

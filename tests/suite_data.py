@@ -66,3 +66,34 @@ def triad_scale(n):   # stream/TRIAD.cpp:36-38 (long double, narrowed to double 
 
 def scan_scale(n):    # algorithm/SCAN.cpp:36-39
     return float(np.longdouble(1e-2) * (np.longdouble(1000000) / np.longdouble(n)) / np.longdouble(n))
+
+
+def round_div(target, unit):
+    return max((target + unit // 2) // unit, 1)
+
+
+def mass3dpa(target=0):   # apps/MASS3DPA.cpp:23-83
+    NE = round_div(target or 8000 * 125, 125)
+    return dict(NE=NE, B=np.ones(20), Bt=np.ones(20), D=np.ones(125 * NE), X=np.ones(64 * NE),
+                Y=np.zeros(64 * NE))
+
+
+def diffusion3dpa(target=0):   # apps/DIFFUSION3DPA.cpp:23-88
+    NE = round_div(target or 15625 * 64, 64)
+    return dict(NE=NE, B=np.ones(12), G=np.ones(12), D=np.ones(64 * 6 * NE), X=np.ones(27 * NE),
+                Y=np.zeros(27 * NE))
+
+
+def convection3dpa(target=0):   # apps/CONVECTION3DPA.cpp:23-89
+    NE = round_div(target or 15625 * 64, 64)
+    return dict(NE=NE, B=np.ones(12), Bt=np.ones(12), G=np.ones(12), D=np.ones(64 * 3 * NE),
+                X=np.ones(27 * NE), Y=np.zeros(27 * NE))
+
+
+def ltimes(target=0, nd=64, ng=32, nm=25):   # apps/LTIMES.cpp:23-92
+    dg = nd * ng
+    dflt = dg * round_div(1000000, dg)
+    nz = round_div(target or dflt, dg)
+    phi, ell, psi = _seq([("const", nm * ng * nz, 0.0), ("real", nd * nm), ("real", dg * nz)])
+    scale = float(np.longdouble(0.001) * (np.longdouble(dflt) / np.longdouble(dg * nz)))
+    return dict(nz=nz, nd=nd, ng=ng, nm=nm, phi=phi, ell=ell, psi=psi, scale=scale)

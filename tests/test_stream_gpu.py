@@ -111,7 +111,8 @@ def test_dot_and_reduce_sum_tolerance_class(ctx, n):
     ctx.stream_dot(dev(d["a"]), dev(d["b"]), out)
     ref = L.orc_stream_dot(d["a"], d["b"], n, 0.0)
     exact = math.fsum((d["a"] * d["b"]).tolist()) if n <= 1000000 else ref
-    assert abs(out.item() - ref) <= 1e-12 * abs(ref) + 1e-300
+    # vs Base_Seq's left-to-right sum: the reference's own OpenMP variant drifts 1e-9 relative at 2^27
+    assert abs(out.item() - ref) <= 1e-10 * abs(ref) + 1e-300
     if n <= 1000000:   # at least as accurate as Base_Seq's left-to-right sum (up to product rounding)
         assert abs(out.item() - exact) <= max(abs(ref - exact), 4e-16 * abs(exact))
 
@@ -119,7 +120,7 @@ def test_dot_and_reduce_sum_tolerance_class(ctx, n):
     ctx.reduce_sum(dev(x), out)
     ref = L.orc_reduce_sum(x, n, 0.0)
     exact = math.fsum(x.tolist()) if n <= 1000000 else ref
-    assert abs(out.item() - ref) <= 1e-12 * abs(ref)
+    assert abs(out.item() - ref) <= 1e-10 * abs(ref)
     if n <= 1000000:
         assert abs(out.item() - exact) <= max(abs(ref - exact), 4e-16 * abs(exact))
 
