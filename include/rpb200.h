@@ -27,6 +27,7 @@ extern "C" {
 #endif
 
 #define RPB200_EINVAL (-22)
+#define RPB200_ETIMEDOUT (-110)
 
 typedef struct rpb200_ctx rpb200_ctx;   /* per-device context (scratch, SM count, tunings) */
 typedef void* rpb200_stream_t;          /* cudaStream_t */
@@ -97,38 +98,78 @@ int rpb200_ltimes(rpb200_ctx*, double* phi, const double* ell, const double* psi
 
 /* ---- Comm group ------------------------------------------------------------------
  * comm/HALO_PACKING_FUSED-Cuda.cpp:52-197, HALO_EXCHANGE_FUSED-Cuda.cpp:52-206.
- * One descriptor per (neighbour, variable) segment -- the reference's
- * (buffer, list, var, len) tuples (HALO_PACKING_FUSED.hpp:62-71), held in DEVICE
- * memory.  pack:   buffer[i] = var[list[i]];  unpack: var[list[i]] = buffer[i].     */
+ *
+ * (1) Generic fused pack / unpack over the reference's (buffer, list, var, len) tuples
+ *     (HALO_PACKING_FUSED-Cuda.cpp:24-40 keeps them in pinned host arrays the kernel reads
+ *     over PCIe and refills every rep).  Here a WORK LIST holds them in device memory next
+ *     to a chunk -> tuple map, so one launch covers every tuple with no search and no idle
+ *     CTA:  pack:  buffer[i] = var[list[i]]      unpack:  var[list[i]] = buffer[i].       */
 typedef struct rpb200_halo_seg {
-  double*    buffer;   /* contiguous message segment (may be a peer-GPU pointer)      */
-  const int* list;     /* index list (Int_type, HALO_base.cpp:197-254)                */
-  double*    var;      /* the grid variable                                           */
-  int64_t    len;      /* elements in this segment                                    */
-  int64_t    work_begin; /* exclusive prefix of ceil(len/chunk) over segments          */
+  double*    buffer;   /* contiguous message segment (device; may be a peer-GPU pointer)  */
+  const int* list;     /* index list (Int_type, HALO_base.cpp:197-254), device            */
+  double*    var;      /* the grid variable, device                                       */
+  int64_t    len;      /* elements in this segment                                        */
+  int32_t    msg;      /* message (neighbour) ordinal 0..25 this segment belongs to       */
+  int32_t    flags;    /* filled by the library (alignment classes); pass 0               */
 } rpb200_halo_seg;
 
-/* elements one work chunk covers; the host fills work_begin in these units            */
-int     rpb200_halo_chunk(void);
-int rpb200_halo_pack  (rpb200_ctx*, const rpb200_halo_seg* d_segs, int nsegs, int64_t total_chunks,
-                       rpb200_stream_t);
-int rpb200_halo_unpack(rpb200_ctx*, const rpb200_halo_seg* d_segs, int nsegs, int64_t total_chunks,
-                       rpb200_stream_t);
+typedef struct rpb200_halo_worklist rpb200_halo_worklist;
+int     rpb200_halo_chunk(void);          /* elements one CTA moves                       */
+/* h_segs: HOST array of nsegs tuples (copied).  update() re-uploads tuples of the same
+ * lengths (stream-ordered; what the reference does every rep).                            */
+int rpb200_halo_worklist_create(rpb200_ctx*, const rpb200_halo_seg* h_segs, int nsegs,
+                                rpb200_halo_worklist** out);
+int rpb200_halo_worklist_update(rpb200_halo_worklist*, const rpb200_halo_seg* h_segs, int nsegs,
+                                rpb200_stream_t);
+void rpb200_halo_worklist_destroy(rpb200_halo_worklist*);
+int rpb200_halo_pack  (rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t);
+int rpb200_halo_unpack(rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t);
 
-/* Fused exchange over NVLink peer memory (replaces MPI_Irecv/Isend/Waitall,
- * HALO_EXCHANGE_FUSED-Cuda.cpp:109-196).  The pack kernel stores straight into the
- * receiving rank's unpack buffers through peer pointers (segment.buffer), then
- * publishes `epoch` to one flag per destination rank; the unpack kernel waits until
- * every source rank's flag in ITS OWN flag array reached `epoch`.
- *   d_peer_flags[r] : device pointer (peer-mapped) to rank r's flag array, entry [my_rank]
- *   d_my_flags      : this rank's flag array, one uint64 per rank
- *   d_src_ranks     : the nsrc distinct ranks this rank receives from                */
-int rpb200_halo_pack_signal(rpb200_ctx*, const rpb200_halo_seg* d_segs, int nsegs,
-                            int64_t total_chunks, uint64_t* const* d_peer_flags, int npeers,
-                            uint64_t epoch, rpb200_stream_t);
-int rpb200_halo_wait_unpack(rpb200_ctx*, const rpb200_halo_seg* d_segs, int nsegs,
-                            int64_t total_chunks, const uint64_t* d_my_flags,
-                            const int* d_src_ranks, int nsrc, uint64_t epoch, rpb200_stream_t);
+/* (2) HALO_base: the 26-neighbour periodic decomposition and its index lists
+ *     (comm/HALO_base.cpp:31-35 grid dims, :82-116 offsets, :118-166 extents, :169-291
+ *     create_lists).  A plan owns the 52 device index lists of one rank.                  */
+#define RPB200_HALO_NEIGHBORS 26
+typedef struct rpb200_halo_plan rpb200_halo_plan;
+void rpb200_halo_grid_dims(int64_t target_problem_size, int64_t dims[3]);
+int  rpb200_halo_plan_create(rpb200_ctx*, const int64_t grid_dims[3], int64_t halo_width,
+                             int num_vars, int my_rank, const int rank_dims[3],
+                             rpb200_halo_plan** out);
+void rpb200_halo_plan_destroy(rpb200_halo_plan*);
+int64_t rpb200_halo_plan_var_size(const rpb200_halo_plan*);   /* (nx+2h)(ny+2h)(nz+2h)     */
+/* neighbour l: its rank, the send/recv tags, list lengths and DEVICE list pointers        */
+int  rpb200_halo_plan_neighbor(const rpb200_halo_plan*, int l, int* rank, int* send_tag,
+                               int* recv_tag, int64_t* pack_len, int64_t* unpack_len,
+                               const int** d_pack_list, const int** d_unpack_list);
+/* HALO_PACKING_FUSED: bind the caller's vars[num_vars], pack_buffers[26], unpack_buffers[26]
+ * (device pointers; buffer l holds num_vars segments of pack_len/unpack_len, variable-minor,
+ * HALO_PACKING_FUSED-Seq.cpp:43-61, 71-97), then run the two fused launches of one rep.    */
+int  rpb200_halo_plan_bind(rpb200_halo_plan*, double* const* vars, double* const* pack_buffers,
+                           double* const* unpack_buffers);
+int  rpb200_halo_plan_pack(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_plan_unpack(rpb200_halo_plan*, rpb200_stream_t);
+
+/* (3) HALO_EXCHANGE_FUSED over NVLink peer memory (replaces MPI_Irecv / MPI_Isend /
+ *     MPI_Waitall on host-pinned buffers, HALO_EXCHANGE_FUSED-Cuda.cpp:109-196).
+ *     Every rank owns a WINDOW in device memory: 26 arrival flags + two generations of its 26
+ *     receive buffers.  The pack kernel of rank r stores message l straight into the window
+ *     of rank ranks[l] (receive slot = the opposite neighbour, i.e. the slot whose recv_tag is
+ *     l, HALO_base.cpp:260) and, when the last chunk of a message has been written, releases
+ *     that slot's flag with the exchange epoch.  The unpack kernel acquires each slot's flag
+ *     before scattering it.  Two buffer generations + the symmetric neighbour relation make a
+ *     separate "buffer free" acknowledgement unnecessary (Comm).
+ *     Set-up: window() -> exchange the 64-byte IPC handles between ranks by any means (MPI,
+ *     torch.distributed, a file) -> connect().  connect_ptrs() is the same for ranks that
+ *     live in one process (plain device pointers, e.g. several ranks simulated on one GPU). */
+int  rpb200_halo_exchange_window(rpb200_halo_plan*, double* const* vars, void** d_window,
+                                 size_t* bytes, unsigned char ipc_handle[64]);
+int  rpb200_halo_exchange_connect(rpb200_halo_plan*, int nranks, const unsigned char* ipc_handles);
+int  rpb200_halo_exchange_connect_ptrs(rpb200_halo_plan*, int nranks, void* const* d_windows);
+/* one rep = pack_signal then wait_unpack (or exchange() for both); all stream-ordered      */
+int  rpb200_halo_exchange_pack(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_exchange_unpack(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_exchange(rpb200_halo_plan*, rpb200_stream_t);
+/* 0, or RPB200_ETIMEDOUT if an unpack CTA gave up waiting for a flag (synchronises)        */
+int  rpb200_halo_exchange_status(rpb200_halo_plan*);
 
 /* CUDA IPC plumbing so one-process-per-GPU ranks can map each other's buffers
  * (what `--cuda-mpi-data-space CudaDevice` + CUDA-aware MPI would do underneath,
