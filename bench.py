@@ -1,0 +1,540 @@
+#!/usr/bin/env python
+"""bench.py -- the Base_B200 hot path measured on B200(s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the Stream group -- COPY, MUL, ADD, TRIAD, DOT -- of the RAJA
+Performance Suite at --size 268435456 doubles per GPU, suite-generated data
+(factor*(i+1.1)/(i+1.12345), common/DataUtils.cpp:504-513).  One STEP = one pass over the five
+kernels (one rep of each, in suite order).  Every rank runs its own --size problem (the suite's
+SPMD model: weak scaling); DOT's scalar is all-reduced across ranks when N > 1.
+
+The ONE JSON line printed by rank 0 carries:
+  value      aggregate algorithmic GB/s of the step (96 B per element per step), inputs resident in HBM
+  e2e        the same step through the C ABI starting from PINNED HOST buffers: H2D of both inputs,
+             the five kernels, D2H of the four output arrays + the DOT scalar, pipelined in chunks
+  roofline   the dominant kernel of the step (largest share of device time) against the measured
+             HBM copy bandwidth of MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement of the reference's Base_OpenMP Stream kernels (oracle/, test
+             infrastructure) timed on this box's host cores on the same workload
+  kernels    every kernel of the hot path at its BASELINE size: ms, GB/s, fraction of measured peak
+  halo_exchange  HALO_EXCHANGE_FUSED time per rep on the N-rank 3-D grid (512^3 cells per GPU)
+
+--impl reference times the CPU side alone (the reference arm of the comparison).
+There is no CPU fallback on the b200 arm: without librpb200.so or a B200 it raises.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAM_N = 1 << 28                     # BASELINE.json: "--size 256M doubles"
+ALGO_N = 1 << 27                       # "128M elements"
+STREAM_BYTES_PER_ELEM = {"Stream_COPY": 16, "Stream_MUL": 16, "Stream_ADD": 24, "Stream_TRIAD": 24, "Stream_DOT": 16}
+STEP_BYTES_PER_ELEM = sum(STREAM_BYTES_PER_ELEM.values())      # 96
+METRIC = "Stream group (COPY/MUL/ADD/TRIAD/DOT) aggregate HBM GB/s"
+UNIT = "GB/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        if not sm:       # region shorter than the sampling period: use every sample we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); smax.append(float(f[1]))
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# suite data on the device (bit-identical to initData: (factor*(i+1.1))/(i+1.12345) in IEEE double)
+# ------------------------------------------------------------------------------------------------
+def init_real_dev(torch, n, factor, device):
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    step = 1 << 24
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        i = torch.arange(s, e, dtype=torch.float64, device=device)
+        out[s:e] = (factor * (i + 1.1)) / (i + 1.12345)
+    return out
+
+
+def init_scalar(factor):
+    return (factor * 1.1) / 1.12345
+
+
+def time_events(torch, fn, reps, warm, setup=None):
+    """Average device ms of fn() over reps launches (CUDA events on the current stream)."""
+    for _ in range(warm):
+        if setup:
+            setup()
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    if setup is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    for _ in range(reps):
+        setup()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference arm / cpu_baseline (oracle = test infrastructure, used only here)
+# ------------------------------------------------------------------------------------------------
+def cpu_stream_group(n, steps, warmup, host_arrays=None):
+    """Times the Stream group on the host cores with the OpenMP restatement of the reference's
+    Base_OpenMP variants (stream/*-OMP.cpp).  Returns (GB/s, ms_per_step, threads, kind, sample)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    L = oracle.lib()
+    threads = L.orc_omp_threads()
+    if host_arrays is None:
+        x0, x1, y = np.empty(n), np.empty(n), np.empty(n)
+        L.orc_reset_init_count()
+        L.orc_init_real(x0, n)            # factor 0.2
+        L.orc_init_real(x1, n)            # factor 0.1
+        L.orc_stream_copy_omp(y, x0, n)   # first touch of y by the worker threads
+    else:
+        x0, x1, y = host_arrays
+    alpha = init_scalar(0.2)
+
+    def step():
+        L.orc_stream_copy_omp(y, x0, n)
+        L.orc_stream_mul_omp(y, x1, alpha, n)
+        L.orc_stream_add_omp(y, x0, x1, n)
+        L.orc_stream_triad_omp(y, x1, x0, alpha, n)
+        return L.orc_stream_dot_omp(x0, x1, n, 0.0)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    gbs = STEP_BYTES_PER_ELEM * n * steps / dt / 1e9
+    sample = f"{steps} full passes of the Stream group at n={n} doubles ({dt:.1f} s of CPU work)"
+    return gbs, dt / steps * 1e3, threads, "port", sample
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    n = STREAM_N
+    gbs, ms, threads, kind, sample = cpu_stream_group(n, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (suite initData formula)",
+        "config": {"workload": f"Stream group COPY/MUL/ADD/TRIAD/DOT, --size {n} doubles, Base_OpenMP on host cores",
+                   "threads": threads},
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def rank_grid(P):
+    """The suite's default --mpi_3d_division (RunParams.cpp:1211-1251): prime factors in non-decreasing
+    order, each multiplied into the currently smallest dimension (first one on ties)."""
+    factors, number, f = [], P, 2
+    while f * f <= number:
+        if number % f == 0:
+            factors.append(f); number //= f
+        else:
+            f += 1
+    factors.append(number)
+    dims = [1, 1, 1]
+    for f in factors:
+        dims[dims.index(min(dims))] *= f
+    return dims
+
+
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from rajaperf_b200 import Context, cabi
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (Base_B200 arm) needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = Context(local_rank)
+    peak, peak_src = measured_peak()
+    n = STREAM_N
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- main workload: Stream group, inputs resident in HBM --------------------------------------
+    x0 = init_real_dev(torch, n, 0.2, dev)
+    x1 = init_real_dev(torch, n, 0.1, dev)
+    y = torch.zeros(n, dtype=torch.float64, device=dev)
+    dot = torch.zeros(1, dtype=torch.float64, device=dev)
+    alpha = init_scalar(0.2)
+    names = list(STREAM_BYTES_PER_ELEM)
+
+    def stream_step(ev=None):
+        if ev: ev[0].record()
+        ctx.stream_copy(y, x0)
+        if ev: ev[1].record()
+        ctx.stream_mul(y, x1, alpha)
+        if ev: ev[2].record()
+        ctx.stream_add(y, x0, x1)
+        if ev: ev[3].record()
+        ctx.stream_triad(y, x1, x0, alpha)
+        if ev: ev[4].record()
+        ctx.stream_dot(x0, x1, dot)
+        if world > 1:
+            dist.all_reduce(dot)          # the global DOT: one double over NCCL
+        if ev: ev[5].record()
+
+    for _ in range(W):
+        stream_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25 if rank == 0 else 0.0)
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    t_wall0 = time.time()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for k in range(K):
+        stream_step(evs[k])
+    e_stop.record()
+    barrier()
+    t_wall1 = time.time()
+    total_ms = e_start.elapsed_time(e_stop)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    per_kernel_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i in range(5)]
+    dot_value = float(dot.item())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * STEP_BYTES_PER_ELEM * n / (ms_per_step * 1e6)
+
+    kernels = {}
+    for i, nm in enumerate(names):
+        gbs = STREAM_BYTES_PER_ELEM[nm] * n / (per_kernel_ms[i] * 1e6)
+        kernels[nm] = {"n": n, "ms": per_kernel_ms[i], "bytes_per_rep": STREAM_BYTES_PER_ELEM[nm] * n, "gbs": gbs,
+                       "frac_of_measured_peak": gbs / peak, "frac_of_8TBs": gbs / 8000.0, "timed": "inside the step"}
+    dom = max(range(5), key=lambda i: per_kernel_ms[i])
+    roofline = {"kernel": names[dom], "bound": "hbm", "achieved": kernels[names[dom]]["gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[names[dom]]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "share_of_step": per_kernel_ms[dom] / sum(per_kernel_ms),
+                "algorithmic_bytes_per_launch": STREAM_BYTES_PER_ELEM[names[dom]] * n}
+    prof = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(names[dom], {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- e2e: the same step from pinned host buffers ----------------------------------------------
+    e2e = run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, min(K, 4))
+
+    # ---- every other kernel of the hot path at its BASELINE size -----------------------------------
+    halo = None
+    if not args.no_extras:
+        del x0, x1, y
+        torch.cuda.empty_cache()
+        extras, halo = run_extras(torch, dist, ctx, dev, rank, world, peak)
+        kernels.update(extras)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu = STREAM_N
+        gbs, ms, threads, kind, sample = cpu_stream_group(n_cpu, 3, 1)
+        cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "ms_per_step": ms}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (suite initData formula, generated on the device)",
+            "config": {"workload": f"Stream group COPY/MUL/ADD/TRIAD/DOT, Base_B200, --size {n} doubles per GPU "
+                                   "(BASELINE.json configs[1]); one step = one rep of each kernel",
+                       "bytes_per_step_per_gpu": STEP_BYTES_PER_ELEM * n,
+                       "l2": "each array is 2 GiB >> 126 MB L2: no flush needed between iterations",
+                       "parallelism": f"{world} independent --size problems (suite SPMD model), DOT all-reduced"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 5 * K, "clocks": clocks,
+            "kernels": kernels, "halo_exchange": halo, "dot_value": dot_value,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, steps):
+    """Host-resident inputs -> results back on the host, through the C ABI.  16 chunks round-robin over
+    4 streams so H2D, kernels and D2H of different chunks overlap (PCIe is full duplex)."""
+    nchunk, nstream = 16, 4
+    cs = n // nchunk
+    h0 = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h1 = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    hy = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    h0.copy_(x0); h1.copy_(x1)
+    hdot = torch.zeros(nchunk, dtype=torch.float64, pin_memory=True)
+    ddot = torch.zeros(nchunk, dtype=torch.float64, device=dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(nstream)]
+    torch.cuda.synchronize()
+
+    def step():
+        for j in range(nchunk):
+            s = streams[j % nstream]
+            sl = slice(j * cs, (j + 1) * cs)
+            with torch.cuda.stream(s):
+                x0[sl].copy_(h0[sl], non_blocking=True)
+                x1[sl].copy_(h1[sl], non_blocking=True)
+                ctx.stream_copy(y[sl], x0[sl], n=cs)
+                hy[sl].copy_(y[sl], non_blocking=True)
+                ctx.stream_mul(y[sl], x1[sl], alpha, n=cs)
+                hy[sl].copy_(y[sl], non_blocking=True)
+                ctx.stream_add(y[sl], x0[sl], x1[sl], n=cs)
+                hy[sl].copy_(y[sl], non_blocking=True)
+                ctx.stream_triad(y[sl], x1[sl], x0[sl], alpha, n=cs)
+                hy[sl].copy_(y[sl], non_blocking=True)
+                ctx.stream_dot(x0[sl], x1[sl], ddot[j:j + 1], n=cs)
+                hdot[j:j + 1].copy_(ddot[j:j + 1], non_blocking=True)
+        for s in streams:
+            s.synchronize()
+        return float(hdot.sum())
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    del h0, h1, hy
+    return {"value": world * STEP_BYTES_PER_ELEM * n * steps / dt / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n + 8 * nchunk, "steps": steps,
+            "ms_per_step": dt / steps * 1e3,
+            "how": "pinned host -> 16 chunks over 4 streams (H2D x0,x1; COPY,MUL,ADD,TRIAD each followed by D2H "
+                   "of the output; DOT + D2H of the partial) -> host; wall clock around stream syncs, max over ranks"}
+
+
+def run_extras(torch, dist, ctx, dev, rank, world, peak):
+    """Per-kernel GB/s at BASELINE sizes (configs[2..4]) and the halo exchange on the N-rank grid."""
+    out = {}
+
+    def rec(name, n, bytes_per_rep, ms, **kw):
+        gbs = bytes_per_rep / (ms * 1e6)
+        out[name] = dict(n=n, ms=ms, bytes_per_rep=bytes_per_rep, gbs=gbs, frac_of_measured_peak=gbs / peak,
+                         frac_of_8TBs=gbs / 8000.0, **kw)
+
+    f64 = dict(dtype=torch.float64, device=dev)
+    n = ALGO_N
+    x = init_real_dev(torch, n, 0.2, dev)
+    res = torch.zeros(1, **f64)
+    rec("Algorithm_REDUCE_SUM", n, 8 * n, time_events(torch, lambda: ctx.reduce_sum(x, res), 20, 3))
+    x = torch.randint(0, 2**31 - 1, (n,), device=dev).to(torch.float64).div_(2147483647.0)   # rand()/RAND_MAX
+    yv = torch.empty_like(x)
+    rec("Algorithm_SCAN", n, 16 * n, time_events(torch, lambda: ctx.scan_exclusive(x, yv), 20, 3))
+    scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
+    ms = time_events(torch, lambda: ctx.sort_keys(yv, scratch), 5, 2, setup=lambda: yv.copy_(x))
+    rec("Algorithm_SORT", n, 16 * n, ms, mkeys_per_s=n / ms / 1e3, note="16 B/key is the suite's nominal count")
+    vals = torch.empty_like(x)
+    ms = time_events(torch, lambda: ctx.sort_pairs(yv, vals, scratch), 5, 2, setup=lambda: (yv.copy_(x), vals.copy_(x)))
+    rec("Algorithm_SORTPAIRS", n, 32 * n, ms, mkeys_per_s=n / ms / 1e3, note="32 B/pair is the suite's nominal count")
+    del x, yv, vals, scratch
+    torch.cuda.empty_cache()
+
+    one = lambda m: torch.ones(m, **f64)
+    NE = 4000000
+    B, Bt, D, X, Y = one(20), one(20), one(125 * NE), one(64 * NE), torch.zeros(64 * NE, **f64)
+    ms = time_events(torch, lambda: ctx.mass3dpa(B, Bt, D, X, Y, NE), 10, 3)
+    rec("Apps_MASS3DPA", NE, 2536 * NE, ms, gflops=5069 * NE / ms / 1e6)
+    del D, X, Y
+    B, G, D, X, Y = one(12), one(12), one(384 * NE), one(27 * NE), torch.zeros(27 * NE, **f64)
+    ms = time_events(torch, lambda: ctx.diffusion3dpa(B, G, D, X, Y, NE), 10, 3)
+    rec("Apps_DIFFUSION3DPA", NE, 3720 * NE, ms, gflops=7065 * NE / ms / 1e6)
+    del D
+    D = one(192 * NE)
+    ms = time_events(torch, lambda: ctx.convection3dpa(B, B, G, D, X, Y, NE), 10, 3)
+    rec("Apps_CONVECTION3DPA", NE, 2184 * NE, ms, gflops=3683 * NE / ms / 1e6)
+    del D, X, Y
+    torch.cuda.empty_cache()
+    nz = 500000
+    phi = torch.zeros(800 * nz, **f64)
+    ell = init_real_dev(torch, 1600, 0.1, dev)
+    psi = init_real_dev(torch, 2048 * nz, 0.2, dev)
+    ms = time_events(torch, lambda: ctx.ltimes(phi, ell, psi, 64, 32, 25, nz), 10, 3)
+    rec("Apps_LTIMES", 32 * nz, 912 * 32 * nz, ms, gflops=3200 * 32 * nz / ms / 1e6)
+    del phi, psi
+    torch.cuda.empty_cache()
+
+    # ---- Comm: 512^3 cells per GPU, halo 1, 3 variables ----------------------------------------------
+    g, hw, nv = 512, 1, 3
+    plan = ctx.halo_plan((g, g, g), hw, nv, rank, rank_grid(world))
+    vars_ = [torch.arange(plan.var_size, **f64) + v for v in range(nv)]
+    halo_elems = sum(nb["pack_len"] for nb in plan.neighbors) * nv
+    pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
+    ub = [torch.zeros(nv * nb["unpack_len"], **f64) for nb in plan.neighbors]
+    plan.bind(vars_, pb, ub)
+
+    def packing():
+        plan.pack(); plan.unpack()
+    rec("Comm_HALO_PACKING_FUSED", halo_elems, 40 * halo_elems, time_events(torch, packing, 50, 5),
+        grid=[g, g, g], launches_per_rep=2)
+
+    _, _, handle = plan.window(vars_)
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        plan.connect(handles)
+        dist.barrier()
+    else:
+        plan.connect_ptrs([0])
+    reps = 100
+    for _ in range(10):
+        plan.exchange()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        plan.exchange()
+    e1.record()
+    torch.cuda.synchronize()
+    plan.status()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        t = torch.tensor([ms], **f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    rec("Comm_HALO_EXCHANGE_FUSED", halo_elems, 56 * halo_elems, ms, grid=[g, g, g], launches_per_rep=2)
+    halo = {"ms_per_rep": ms, "n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": [g, g, g],
+            "halo_width": hw, "num_vars": nv, "bytes_sent_per_gpu_per_rep": 8 * halo_elems,
+            "transport": "pack kernel stores into the peer's receive window over NVLink (CUDA IPC), "
+                         "per-message release/acquire flags; no host sync, no MPI"}
+    plan.close()
+    return out, halo
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table and the halo exchange")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@ class RPB200Error(RuntimeError):
 class HaloSeg(Structure):
     """struct rpb200_halo_seg (include/rpb200.h)."""
     _fields_ = [("buffer", c_void_p), ("list", c_void_p), ("var", c_void_p),
-                ("len", c_int64), ("work_begin", c_int64)]
+                ("len", c_int64), ("msg", c_int), ("flags", c_int)]
 
 
 # name -> (restype, argtypes); must list every function declared in include/rpb200.h
@@ -52,10 +52,27 @@ SIGNATURES = {
     "rpb200_convection3dpa": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpb200_ltimes": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P]),
     "rpb200_halo_chunk": (c_int, []),
-    "rpb200_halo_pack": (c_int, [_P, _P, c_int, c_int64, _P]),
-    "rpb200_halo_unpack": (c_int, [_P, _P, c_int, c_int64, _P]),
-    "rpb200_halo_pack_signal": (c_int, [_P, _P, c_int, c_int64, _P, c_int, c_uint64, _P]),
-    "rpb200_halo_wait_unpack": (c_int, [_P, _P, c_int, c_int64, _P, _P, c_int, c_uint64, _P]),
+    "rpb200_halo_worklist_create": (c_int, [_P, _P, c_int, POINTER(_P)]),
+    "rpb200_halo_worklist_update": (c_int, [_P, _P, c_int, _P]),
+    "rpb200_halo_worklist_destroy": (None, [_P]),
+    "rpb200_halo_pack": (c_int, [_P, _P, _P]),
+    "rpb200_halo_unpack": (c_int, [_P, _P, _P]),
+    "rpb200_halo_grid_dims": (None, [c_int64, POINTER(c_int64)]),
+    "rpb200_halo_plan_create": (c_int, [_P, POINTER(c_int64), c_int64, c_int, c_int, POINTER(c_int), POINTER(_P)]),
+    "rpb200_halo_plan_destroy": (None, [_P]),
+    "rpb200_halo_plan_var_size": (c_int64, [_P]),
+    "rpb200_halo_plan_neighbor": (c_int, [_P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                          POINTER(c_int64), POINTER(c_int64), POINTER(_P), POINTER(_P)]),
+    "rpb200_halo_plan_bind": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(_P)]),
+    "rpb200_halo_plan_pack": (c_int, [_P, _P]),
+    "rpb200_halo_plan_unpack": (c_int, [_P, _P]),
+    "rpb200_halo_exchange_window": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(c_size_t), POINTER(c_ubyte)]),
+    "rpb200_halo_exchange_connect": (c_int, [_P, c_int, POINTER(c_ubyte)]),
+    "rpb200_halo_exchange_connect_ptrs": (c_int, [_P, c_int, POINTER(_P)]),
+    "rpb200_halo_exchange_pack": (c_int, [_P, _P]),
+    "rpb200_halo_exchange_unpack": (c_int, [_P, _P]),
+    "rpb200_halo_exchange": (c_int, [_P, _P]),
+    "rpb200_halo_exchange_status": (c_int, [_P]),
     "rpb200_ipc_export": (c_int, [_P, POINTER(c_ubyte)]),
     "rpb200_ipc_open": (c_int, [POINTER(c_ubyte), POINTER(_P)]),
     "rpb200_ipc_close": (c_int, [_P]),
@@ -214,22 +231,148 @@ class Context:
     def halo_chunk(self) -> int:
         return self.lib.rpb200_halo_chunk()
 
-    def halo_pack(self, d_segs, nsegs, total_chunks):
-        check(self.lib.rpb200_halo_pack(self.h, _ptr(d_segs), nsegs, total_chunks, _stream()), "halo_pack")
+    def halo_worklist(self, segs):
+        """segs: iterable of (buffer_ptr, list_ptr, var_ptr, len, msg) -> HaloWorklist."""
+        return HaloWorklist(self, segs)
 
-    def halo_unpack(self, d_segs, nsegs, total_chunks):
-        check(self.lib.rpb200_halo_unpack(self.h, _ptr(d_segs), nsegs, total_chunks, _stream()),
-              "halo_unpack")
+    def halo_pack(self, wl):
+        check(self.lib.rpb200_halo_pack(self.h, wl.h, _stream()), "halo_pack")
 
-    def halo_pack_signal(self, d_segs, nsegs, total_chunks, d_peer_flags, npeers, epoch):
-        check(self.lib.rpb200_halo_pack_signal(self.h, _ptr(d_segs), nsegs, total_chunks,
-                                               _ptr(d_peer_flags), npeers, epoch, _stream()),
-              "halo_pack_signal")
+    def halo_unpack(self, wl):
+        check(self.lib.rpb200_halo_unpack(self.h, wl.h, _stream()), "halo_unpack")
 
-    def halo_wait_unpack(self, d_segs, nsegs, total_chunks, d_my_flags, d_src_ranks, nsrc, epoch):
-        check(self.lib.rpb200_halo_wait_unpack(self.h, _ptr(d_segs), nsegs, total_chunks,
-                                               _ptr(d_my_flags), _ptr(d_src_ranks), nsrc, epoch,
-                                               _stream()), "halo_wait_unpack")
+    def halo_plan(self, grid_dims, halo_width=1, num_vars=3, rank=0, rank_dims=(1, 1, 1)):
+        return HaloPlan(self, grid_dims, halo_width, num_vars, rank, rank_dims)
+
+
+def halo_grid_dims(target_size: int):
+    """HALO_base.cpp:31-35."""
+    d = (c_int64 * 3)()
+    load().rpb200_halo_grid_dims(target_size, d)
+    return [int(x) for x in d]
+
+
+def _seg_array(segs):
+    arr = (HaloSeg * max(len(segs), 1))()
+    for i, (buf, lst, var, ln, msg) in enumerate(segs):
+        arr[i] = HaloSeg(_ptr(buf), _ptr(lst), _ptr(var), ln, msg, 0)
+    return arr
+
+
+class HaloWorklist:
+    """rpb200_halo_worklist: the reference's (buffer, list, var, len) tuples, device-resident."""
+
+    def __init__(self, ctx, segs):
+        self.ctx = ctx
+        segs = list(segs)
+        self.n = len(segs)
+        h = c_void_p()
+        check(ctx.lib.rpb200_halo_worklist_create(ctx.h, ctypes.cast(_seg_array(segs), c_void_p), self.n,
+                                                  ctypes.byref(h)), "halo_worklist_create")
+        self.h = h
+
+    def update(self, segs):
+        segs = list(segs)
+        check(self.ctx.lib.rpb200_halo_worklist_update(self.h, ctypes.cast(_seg_array(segs), c_void_p), len(segs),
+                                                       _stream()), "halo_worklist_update")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.rpb200_halo_worklist_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HaloPlan:
+    """rpb200_halo_plan: HALO_base (index lists + rank grid) and the fused pack/unpack/exchange."""
+
+    def __init__(self, ctx, grid_dims, halo_width, num_vars, rank, rank_dims):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.num_vars, self.rank = num_vars, rank
+        self.nranks = rank_dims[0] * rank_dims[1] * rank_dims[2]
+        gd = (c_int64 * 3)(*grid_dims)
+        rd = (c_int * 3)(*rank_dims)
+        h = c_void_p()
+        check(self.lib.rpb200_halo_plan_create(ctx.h, gd, halo_width, num_vars, rank, rd, ctypes.byref(h)),
+              "halo_plan_create")
+        self.h = h
+        self.var_size = self.lib.rpb200_halo_plan_var_size(h)
+        self.neighbors = []
+        for l in range(26):
+            r, st, rt = c_int(), c_int(), c_int()
+            pl, ul = c_int64(), c_int64()
+            dp, du = c_void_p(), c_void_p()
+            check(self.lib.rpb200_halo_plan_neighbor(h, l, ctypes.byref(r), ctypes.byref(st), ctypes.byref(rt),
+                                                     ctypes.byref(pl), ctypes.byref(ul), ctypes.byref(dp),
+                                                     ctypes.byref(du)), "halo_plan_neighbor")
+            self.neighbors.append(dict(rank=r.value, send_tag=st.value, recv_tag=rt.value, pack_len=pl.value,
+                                       unpack_len=ul.value, d_pack_list=dp.value, d_unpack_list=du.value))
+        self._keep = None
+
+    @staticmethod
+    def _ptr_array(items):
+        arr = (c_void_p * len(items))()
+        for i, t in enumerate(items):
+            arr[i] = _ptr(t)
+        return arr
+
+    def bind(self, vars_, pack_buffers, unpack_buffers):
+        self._keep = (vars_, pack_buffers, unpack_buffers)
+        check(self.lib.rpb200_halo_plan_bind(self.h, self._ptr_array(vars_), self._ptr_array(pack_buffers),
+                                             self._ptr_array(unpack_buffers)), "halo_plan_bind")
+
+    def pack(self):
+        check(self.lib.rpb200_halo_plan_pack(self.h, _stream()), "halo_plan_pack")
+
+    def unpack(self):
+        check(self.lib.rpb200_halo_plan_unpack(self.h, _stream()), "halo_plan_unpack")
+
+    def window(self, vars_, want_handle=True):
+        """Allocate this rank's receive window; returns (device pointer, bytes, ipc handle bytes)."""
+        self._keep_x = vars_
+        w, nb = c_void_p(), c_size_t()
+        hbuf = (c_ubyte * 64)()
+        check(self.lib.rpb200_halo_exchange_window(self.h, self._ptr_array(vars_), ctypes.byref(w), ctypes.byref(nb),
+                                                   hbuf if want_handle else None), "halo_exchange_window")
+        return w.value, nb.value, bytes(hbuf)
+
+    def connect(self, handles):
+        """handles: list of nranks 64-byte IPC handles, indexed by rank."""
+        blob = b"".join(handles)
+        buf = (c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self.lib.rpb200_halo_exchange_connect(self.h, len(handles), buf), "halo_exchange_connect")
+
+    def connect_ptrs(self, windows):
+        arr = (c_void_p * len(windows))(*windows)
+        check(self.lib.rpb200_halo_exchange_connect_ptrs(self.h, len(windows), arr), "halo_exchange_connect_ptrs")
+
+    def exchange_pack(self):
+        check(self.lib.rpb200_halo_exchange_pack(self.h, _stream()), "halo_exchange_pack")
+
+    def exchange_unpack(self):
+        check(self.lib.rpb200_halo_exchange_unpack(self.h, _stream()), "halo_exchange_unpack")
+
+    def exchange(self):
+        check(self.lib.rpb200_halo_exchange(self.h, _stream()), "halo_exchange")
+
+    def status(self):
+        check(self.lib.rpb200_halo_exchange_status(self.h), "halo_exchange_status")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.rpb200_halo_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ipc_export(d_ptr: int) -> bytes:

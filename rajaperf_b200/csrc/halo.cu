@@ -1,0 +1,607 @@
+// halo.cu -- Comm group: HALO_base index lists, HALO_PACKING_FUSED, HALO_EXCHANGE_FUSED for sm_100a.
+//
+// Replaces comm/HALO_PACKING_FUSED-Cuda.cpp:52-197 and HALO_EXCHANGE_FUSED-Cuda.cpp:52-206:
+//   reference                                         here
+//   ------------------------------------------------  ----------------------------------------------
+//   (buffer,list,var,len) tuples in pinned HOST        tuples + a chunk->tuple map in DEVICE memory
+//   memory, read by every CTA over PCIe                (one 4-byte and one 32-byte load per CTA)
+//   grid (ceil(avg_len/1024), 78): CTAs of short       one CTA per 2048-element chunk of real work,
+//   tuples idle, CTAs of long ones loop                nothing idle, nothing loops
+//   scalar 4-byte index loads, 8-byte stores           128-bit index loads, 8 gathers in flight per
+//                                                      thread, 256-bit stores
+//   cudaStreamSynchronize after pack and after unpack  no host synchronisation at all
+//   MPI_Isend/Irecv through pinned host buffers        pack stores straight into the peer GPU's
+//                                                      receive buffer over NVLink; per-message
+//                                                      release/acquire flags replace MPI_Waitall
+#include "common.cuh"
+
+#include <math.h>
+#include <new>
+#include <stdlib.h>
+#include <vector>
+
+namespace {
+
+constexpr int HALO_BLOCK = 256;
+constexpr int HALO_CHUNK = 2048;      // elements per CTA: 8 per thread
+constexpr int NNB = RPB200_HALO_NEIGHBORS;
+
+enum { SEG_LIST16 = 1, SEG_BUF32 = 2 };
+
+__device__ __forceinline__ int4 ldg_idx4(const int* p)
+{
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// receive buffers are written by a peer GPU while this kernel may be resident: never through L1
+__device__ __forceinline__ double ld_cg(const double* p)
+{
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ dbl4 ld_cg4(const double* p)
+{
+  dbl4 v;
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+// per-message signalling state of an exchange (device)
+struct halo_msg {
+  unsigned long long* remote_flag;   // pack: flag of the receive slot in the DESTINATION window
+  const unsigned long long* my_flag; // unpack: flag of this slot in MY window
+  unsigned int chunks;               // pack chunks of this message (all variables)
+  unsigned int pad;
+};
+
+// MODE 0: plain;  MODE 1: pack + signal;  MODE 2: wait + unpack
+template <bool PACK, int MODE>
+__global__ void __launch_bounds__(HALO_BLOCK)
+halo_kernel(const rpb200_halo_seg* __restrict__ segs, const int* __restrict__ chunk_seg,
+            const long long* __restrict__ seg_first_chunk, const halo_msg* __restrict__ msgs,
+            unsigned int* __restrict__ msg_done, unsigned long long epoch, int* __restrict__ error)
+{
+  const int c = blockIdx.x;
+  const int s = __ldg(chunk_seg + c);
+  const rpb200_halo_seg seg = segs[s];
+  const int64_t i0 = ((int64_t)c - __ldg(seg_first_chunk + s)) * HALO_CHUNK;
+  const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+
+  if (MODE == 2) {
+    if (threadIdx.x == 0) {
+      const unsigned long long* f = msgs[seg.msg].my_flag;
+      unsigned int spins = 0;
+      while (ld_acquire_sys(f) < epoch) {
+        __nanosleep(40);
+        if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }   // > 1 s: give up loudly
+      }
+    }
+    __syncthreads();
+  }
+
+  const int* __restrict__ list = seg.list + i0;
+  double* __restrict__ buf = seg.buffer + i0;
+  double* __restrict__ var = seg.var;
+
+  const bool vec = (seg.flags & (SEG_LIST16 | SEG_BUF32)) == (SEG_LIST16 | SEG_BUF32);
+  int done = 0;
+  if (vec) {
+    // two independent groups of 4 per thread: 8 gathers / scatters in flight
+    const int nvec = cnt >> 2;
+    const int v0 = threadIdx.x, v1 = threadIdx.x + HALO_BLOCK;
+    const bool ok0 = v0 < nvec, ok1 = v1 < nvec;
+    int4 ia = make_int4(0, 0, 0, 0), ib = ia;
+    if (ok0) ia = ldg_idx4(list + 4 * v0);
+    if (ok1) ib = ldg_idx4(list + 4 * v1);
+    if (PACK) {
+      dbl4 a, b;
+      if (ok0) { a.x = var[ia.x]; a.y = var[ia.y]; a.z = var[ia.z]; a.w = var[ia.w]; }
+      if (ok1) { b.x = var[ib.x]; b.y = var[ib.y]; b.z = var[ib.z]; b.w = var[ib.w]; }
+      if (ok0) stg256(buf + 4 * v0, a);
+      if (ok1) stg256(buf + 4 * v1, b);
+    } else {
+      dbl4 a, b;
+      if (ok0) a = ld_cg4(buf + 4 * v0);
+      if (ok1) b = ld_cg4(buf + 4 * v1);
+      if (ok0) { var[ia.x] = a.x; var[ia.y] = a.y; var[ia.z] = a.z; var[ia.w] = a.w; }
+      if (ok1) { var[ib.x] = b.x; var[ib.y] = b.y; var[ib.z] = b.z; var[ib.w] = b.w; }
+    }
+    done = nvec << 2;
+  }
+  for (int i = done + threadIdx.x; i < cnt; i += HALO_BLOCK) {
+    if (PACK) buf[i] = var[list[i]];
+    else      var[list[i]] = ld_cg(buf + i);
+  }
+
+  if (MODE == 1) {
+    // all stores of this CTA -> barrier -> system fence -> count the chunk; whoever completes the
+    // message publishes the epoch to the destination's flag (release at system scope)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      const halo_msg m = msgs[seg.msg];
+      const unsigned int prev = atomicAdd(msg_done + seg.msg, 1u);
+      if (prev == m.chunks - 1) {
+        msg_done[seg.msg] = 0u;          // re-armed for the next rep (stream-ordered launches)
+        __threadfence_system();
+        st_release_sys(m.remote_flag, epoch);
+      }
+    }
+  }
+}
+
+struct worklist_dev {
+  rpb200_halo_seg* d_segs = nullptr;
+  int* d_chunk_seg = nullptr;
+  long long* d_first = nullptr;
+  rpb200_halo_seg* h_stage = nullptr;   // pinned staging for update()
+  int nsegs = 0;
+  int64_t total_chunks = 0;
+  std::vector<int64_t> lens;
+};
+
+int worklist_free(worklist_dev& w)
+{
+  cudaFree(w.d_segs); cudaFree(w.d_chunk_seg); cudaFree(w.d_first);
+  if (w.h_stage) cudaFreeHost(w.h_stage);
+  w = worklist_dev();
+  return 0;
+}
+
+void classify(rpb200_halo_seg& s)
+{
+  s.flags = 0;
+  if (rpb_aligned(s.list, 16)) s.flags |= SEG_LIST16;
+  if (rpb_aligned(s.buffer, 32)) s.flags |= SEG_BUF32;
+}
+
+int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
+{
+  if (nsegs < 0 || (nsegs > 0 && !h_segs)) return RPB200_EINVAL;
+  w.nsegs = nsegs;
+  std::vector<rpb200_halo_seg> segs(h_segs, h_segs + nsegs);
+  std::vector<long long> first(nsegs > 0 ? nsegs : 1, 0);
+  std::vector<int> map;
+  w.lens.resize(nsegs);
+  int64_t chunks = 0;
+  for (int s = 0; s < nsegs; ++s) {
+    if (segs[s].len < 0 || (segs[s].len > 0 && (!segs[s].buffer || !segs[s].list || !segs[s].var))) return RPB200_EINVAL;
+    classify(segs[s]);
+    w.lens[s] = segs[s].len;
+    first[s] = chunks;
+    const int64_t nc = (segs[s].len + HALO_CHUNK - 1) / HALO_CHUNK;
+    for (int64_t k = 0; k < nc; ++k) map.push_back(s);
+    chunks += nc;
+  }
+  if (chunks > 0x7fffffffll) return RPB200_EINVAL;
+  w.total_chunks = chunks;
+  const size_t nb = sizeof(rpb200_halo_seg) * (size_t)(nsegs > 0 ? nsegs : 1);
+  RPB_CHECK(cudaMalloc(&w.d_segs, nb));
+  RPB_CHECK(cudaMallocHost(&w.h_stage, nb));
+  RPB_CHECK(cudaMalloc(&w.d_first, sizeof(long long) * first.size()));
+  RPB_CHECK(cudaMalloc(&w.d_chunk_seg, sizeof(int) * (map.size() ? map.size() : 1)));
+  if (nsegs > 0) {
+    RPB_CHECK(cudaMemcpy(w.d_segs, segs.data(), sizeof(rpb200_halo_seg) * nsegs, cudaMemcpyHostToDevice));
+    RPB_CHECK(cudaMemcpy(w.d_first, first.data(), sizeof(long long) * nsegs, cudaMemcpyHostToDevice));
+  }
+  if (!map.empty()) RPB_CHECK(cudaMemcpy(w.d_chunk_seg, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <bool PACK, int MODE>
+int worklist_launch(const worklist_dev& w, const halo_msg* msgs, unsigned int* msg_done,
+                    unsigned long long epoch, int* error, cudaStream_t st)
+{
+  if (w.total_chunks == 0) return 0;
+  halo_kernel<PACK, MODE><<<(int)w.total_chunks, HALO_BLOCK, 0, st>>>(w.d_segs, w.d_chunk_seg, w.d_first, msgs,
+                                                                     msg_done, epoch, error);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// comm/HALO_base.cpp:82-116
+const int k_offsets[NNB][3] = {
+  {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+  {-1, -1, 0}, {-1, 1, 0}, {1, -1, 0}, {1, 1, 0},
+  {-1, 0, -1}, {-1, 0, 1}, {1, 0, -1}, {1, 0, 1},
+  {0, -1, -1}, {0, -1, 1}, {0, 1, -1}, {0, 1, 1},
+  {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1}, {-1, 1, 1},
+  {1, -1, -1}, {1, -1, 1}, {1, 1, -1}, {1, 1, 1}
+};
+
+struct box { int64_t lo[3], hi[3]; int64_t len() const { return (hi[0]-lo[0])*(hi[1]-lo[1])*(hi[2]-lo[2]); } };
+
+// comm/HALO_base.cpp:118-166: the send box is the outermost `hw` owned layers, the recv box the ghost layers
+box make_box(bool recv, const int off[3], int64_t hw, const int64_t dims[3])
+{
+  box b;
+  for (int a = 0; a < 3; ++a) {
+    if (off[a] < 0)      { b.lo[a] = recv ? 0 : hw;                 b.hi[a] = b.lo[a] + hw; }
+    else if (off[a] > 0) { b.lo[a] = recv ? hw + dims[a] : dims[a]; b.hi[a] = b.lo[a] + hw; }
+    else                 { b.lo[a] = hw;                            b.hi[a] = hw + dims[a]; }
+  }
+  return b;
+}
+
+// the index lists are generated on the device (comm/HALO_base.cpp:228-254, 262-288: k outer, i inner)
+__global__ void halo_fill_list_kernel(int* __restrict__ list, int64_t len, int64_t lo0, int64_t lo1, int64_t lo2,
+                                      int64_t e0, int64_t e1, int64_t sj, int64_t sk)
+{
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < len; n += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = n % e0, t = n / e0, j = t % e1, k = t / e1;
+    list[n] = (int)((lo0 + i) + (lo1 + j) * sj + (lo2 + k) * sk);
+  }
+}
+
+}  // namespace
+
+struct rpb200_halo_worklist { worklist_dev w; };
+
+struct rpb200_halo_plan {
+  rpb200_ctx* ctx = nullptr;
+  int64_t dims[3] = {0, 0, 0}, hw = 0, var_size = 0;
+  int nvars = 0, my_rank = 0, rank_dims[3] = {1, 1, 1}, nranks = 1;
+  int ranks[NNB], send_tags[NNB], recv_tags[NNB], opposite[NNB];
+  int64_t pack_len[NNB], unpack_len[NNB];
+  int* d_pack_list[NNB];
+  int* d_unpack_list[NNB];
+  int* d_lists = nullptr;                  // one allocation, 256-byte aligned sub-lists
+  // HALO_PACKING_FUSED binding
+  worklist_dev pack_wl, unpack_wl;
+  bool bound = false;
+  // HALO_EXCHANGE_FUSED
+  std::vector<double*> vars;
+  unsigned char* d_window = nullptr; size_t window_bytes = 0;
+  size_t recv_off[2][NNB];                 // byte offsets of receive slot l, generation g, in ANY rank's window
+  std::vector<void*> peer_windows; std::vector<bool> peer_opened;
+  worklist_dev xpack_wl[2], xunpack_wl[2];
+  halo_msg* d_pack_msgs = nullptr; halo_msg* d_unpack_msgs = nullptr;
+  unsigned int* d_msg_done = nullptr;
+  int* d_error = nullptr;
+  unsigned long long epoch = 0;
+  bool connected = false;
+};
+
+extern "C" int rpb200_halo_chunk(void) { return HALO_CHUNK; }
+
+extern "C" int rpb200_halo_worklist_create(rpb200_ctx* ctx, const rpb200_halo_seg* h_segs, int nsegs,
+                                           rpb200_halo_worklist** out)
+{
+  if (!ctx || !out) return RPB200_EINVAL;
+  *out = nullptr;
+  rpb200_halo_worklist* wl = new (std::nothrow) rpb200_halo_worklist();
+  if (!wl) return (int)cudaErrorMemoryAllocation;
+  const int rc = worklist_build(wl->w, h_segs, nsegs);
+  if (rc != 0) { worklist_free(wl->w); delete wl; return rc; }
+  *out = wl;
+  return 0;
+}
+
+extern "C" int rpb200_halo_worklist_update(rpb200_halo_worklist* wl, const rpb200_halo_seg* h_segs, int nsegs,
+                                           rpb200_stream_t s)
+{
+  if (!wl || nsegs != wl->w.nsegs || (nsegs > 0 && !h_segs)) return RPB200_EINVAL;
+  for (int i = 0; i < nsegs; ++i) {
+    if (h_segs[i].len != wl->w.lens[i]) return RPB200_EINVAL;    // the chunk map depends on the lengths
+    wl->w.h_stage[i] = h_segs[i];
+    classify(wl->w.h_stage[i]);
+  }
+  if (nsegs > 0)
+    RPB_CHECK(cudaMemcpyAsync(wl->w.d_segs, wl->w.h_stage, sizeof(rpb200_halo_seg) * nsegs, cudaMemcpyHostToDevice, rpb_stream(s)));
+  return 0;
+}
+
+extern "C" void rpb200_halo_worklist_destroy(rpb200_halo_worklist* wl)
+{
+  if (!wl) return;
+  worklist_free(wl->w);
+  delete wl;
+}
+
+extern "C" int rpb200_halo_pack(rpb200_ctx* ctx, const rpb200_halo_worklist* wl, rpb200_stream_t s)
+{
+  if (!ctx || !wl) return RPB200_EINVAL;
+  return worklist_launch<true, 0>(wl->w, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+}
+
+extern "C" int rpb200_halo_unpack(rpb200_ctx* ctx, const rpb200_halo_worklist* wl, rpb200_stream_t s)
+{
+  if (!ctx || !wl) return RPB200_EINVAL;
+  return worklist_launch<false, 0>(wl->w, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+}
+
+// comm/HALO_base.cpp:31-35: the double is truncated when stored into the Index_type dims
+extern "C" void rpb200_halo_grid_dims(int64_t target, int64_t dims[3])
+{
+  const double c = cbrt((double)target) + cbrt(3.0) - 1;
+  dims[0] = dims[1] = dims[2] = (int64_t)c;
+}
+
+extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
+{
+  if (!p) return;
+  cudaFree(p->d_lists);
+  worklist_free(p->pack_wl); worklist_free(p->unpack_wl);
+  for (int g = 0; g < 2; ++g) { worklist_free(p->xpack_wl[g]); worklist_free(p->xunpack_wl[g]); }
+  for (size_t r = 0; r < p->peer_windows.size(); ++r)
+    if (p->peer_opened[r] && p->peer_windows[r]) cudaIpcCloseMemHandle(p->peer_windows[r]);
+  cudaFree(p->d_window);
+  cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
+  delete p;
+}
+
+extern "C" int rpb200_halo_plan_create(rpb200_ctx* ctx, const int64_t grid_dims[3], int64_t halo_width,
+                                       int num_vars, int my_rank, const int rank_dims[3],
+                                       rpb200_halo_plan** out)
+{
+  if (!ctx || !grid_dims || !rank_dims || !out || halo_width < 1 || num_vars < 1) return RPB200_EINVAL;
+  *out = nullptr;
+  const int P = rank_dims[0] * rank_dims[1] * rank_dims[2];
+  if (rank_dims[0] < 1 || rank_dims[1] < 1 || rank_dims[2] < 1 || my_rank < 0 || my_rank >= P) return RPB200_EINVAL;
+  for (int a = 0; a < 3; ++a) if (grid_dims[a] < halo_width) return RPB200_EINVAL;
+  rpb200_halo_plan* p = new (std::nothrow) rpb200_halo_plan();
+  if (!p) return (int)cudaErrorMemoryAllocation;
+  p->ctx = ctx; p->hw = halo_width; p->nvars = num_vars; p->my_rank = my_rank; p->nranks = P;
+  for (int a = 0; a < 3; ++a) { p->dims[a] = grid_dims[a]; p->rank_dims[a] = rank_dims[a]; }
+  const int64_t ext[3] = {grid_dims[0] + 2 * halo_width, grid_dims[1] + 2 * halo_width, grid_dims[2] + 2 * halo_width};
+  p->var_size = ext[0] * ext[1] * ext[2];
+  if (p->var_size > 0x7fffffffll) { delete p; return RPB200_EINVAL; }     // Int_type index lists
+
+  // rank coordinates, x fastest (HALO_base.cpp:183-186); periodic wrap (:214-221); tags (:192-195, 227, 260)
+  int me[3];
+  me[2] = my_rank / (rank_dims[0] * rank_dims[1]);
+  me[1] = (my_rank - me[2] * rank_dims[0] * rank_dims[1]) / rank_dims[0];
+  me[0] = my_rank - me[2] * rank_dims[0] * rank_dims[1] - me[1] * rank_dims[0];
+  auto slot = [](const int o[3]) { return (o[0] + 1) + 3 * (o[1] + 1) + 9 * (o[2] + 1); };
+  int slot_to_l[27];
+  for (int l = 0; l < NNB; ++l) slot_to_l[slot(k_offsets[l])] = l;
+  size_t total_ints = 0;
+  size_t list_off[2][NNB];
+  for (int l = 0; l < NNB; ++l) {
+    int nb[3], opp[3];
+    for (int a = 0; a < 3; ++a) {
+      nb[a] = me[a] + k_offsets[l][a];
+      if (nb[a] >= rank_dims[a]) nb[a] = 0; else if (nb[a] < 0) nb[a] = rank_dims[a] - 1;
+      opp[a] = -k_offsets[l][a];
+    }
+    p->ranks[l] = nb[0] + rank_dims[0] * (nb[1] + rank_dims[1] * nb[2]);
+    p->send_tags[l] = l;
+    p->opposite[l] = p->recv_tags[l] = slot_to_l[slot(opp)];
+    p->pack_len[l] = make_box(false, k_offsets[l], halo_width, grid_dims).len();
+    p->unpack_len[l] = make_box(true, k_offsets[l], halo_width, grid_dims).len();
+    list_off[0][l] = total_ints; total_ints += ((size_t)p->pack_len[l] + 63) / 64 * 64;
+    list_off[1][l] = total_ints; total_ints += ((size_t)p->unpack_len[l] + 63) / 64 * 64;
+  }
+  cudaError_t e = cudaMalloc(&p->d_lists, sizeof(int) * total_ints);
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  for (int l = 0; l < NNB; ++l) {
+    p->d_pack_list[l] = p->d_lists + list_off[0][l];
+    p->d_unpack_list[l] = p->d_lists + list_off[1][l];
+    for (int r = 0; r < 2; ++r) {
+      const box b = make_box(r == 1, k_offsets[l], halo_width, grid_dims);
+      const int64_t len = b.len();
+      int* dst = r ? p->d_unpack_list[l] : p->d_pack_list[l];
+      int64_t blocks = (len + 255) / 256; if (blocks > 4096) blocks = 4096;
+      halo_fill_list_kernel<<<(int)blocks, 256>>>(dst, len, b.lo[0], b.lo[1], b.lo[2], b.hi[0] - b.lo[0],
+                                                  b.hi[1] - b.lo[1], ext[0], ext[0] * ext[1]);
+    }
+  }
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { rpb200_halo_plan_destroy(p); return (int)e; }
+  *out = p;
+  return 0;
+}
+
+extern "C" int64_t rpb200_halo_plan_var_size(const rpb200_halo_plan* p) { return p ? p->var_size : 0; }
+
+extern "C" int rpb200_halo_plan_neighbor(const rpb200_halo_plan* p, int l, int* rank, int* send_tag, int* recv_tag,
+                                         int64_t* pack_len, int64_t* unpack_len, const int** d_pack_list,
+                                         const int** d_unpack_list)
+{
+  if (!p || l < 0 || l >= NNB) return RPB200_EINVAL;
+  if (rank) *rank = p->ranks[l];
+  if (send_tag) *send_tag = p->send_tags[l];
+  if (recv_tag) *recv_tag = p->recv_tags[l];
+  if (pack_len) *pack_len = p->pack_len[l];
+  if (unpack_len) *unpack_len = p->unpack_len[l];
+  if (d_pack_list) *d_pack_list = p->d_pack_list[l];
+  if (d_unpack_list) *d_unpack_list = p->d_unpack_list[l];
+  return 0;
+}
+
+// neighbour-major, variable-minor segments (HALO_PACKING_FUSED-Seq.cpp:43-61, 71-97)
+static int plan_segments(const rpb200_halo_plan* p, bool pack, double* const* vars, double* const* buffers,
+                         std::vector<rpb200_halo_seg>& segs)
+{
+  segs.clear();
+  for (int l = 0; l < NNB; ++l) {
+    const int64_t len = pack ? p->pack_len[l] : p->unpack_len[l];
+    if (!buffers[l]) return RPB200_EINVAL;
+    for (int v = 0; v < p->nvars; ++v) {
+      if (!vars[v]) return RPB200_EINVAL;
+      rpb200_halo_seg s;
+      s.buffer = buffers[l] + (int64_t)v * len;
+      s.list = pack ? p->d_pack_list[l] : p->d_unpack_list[l];
+      s.var = vars[v];
+      s.len = len;
+      s.msg = l;
+      s.flags = 0;
+      segs.push_back(s);
+    }
+  }
+  return 0;
+}
+
+extern "C" int rpb200_halo_plan_bind(rpb200_halo_plan* p, double* const* vars, double* const* pack_buffers,
+                                     double* const* unpack_buffers)
+{
+  if (!p || !vars || !pack_buffers || !unpack_buffers) return RPB200_EINVAL;
+  worklist_free(p->pack_wl); worklist_free(p->unpack_wl);
+  p->bound = false;
+  std::vector<rpb200_halo_seg> segs;
+  int rc = plan_segments(p, true, vars, pack_buffers, segs);
+  if (rc == 0) rc = worklist_build(p->pack_wl, segs.data(), (int)segs.size());
+  if (rc == 0) rc = plan_segments(p, false, vars, unpack_buffers, segs);
+  if (rc == 0) rc = worklist_build(p->unpack_wl, segs.data(), (int)segs.size());
+  if (rc != 0) { worklist_free(p->pack_wl); worklist_free(p->unpack_wl); return rc; }
+  p->bound = true;
+  return 0;
+}
+
+extern "C" int rpb200_halo_plan_pack(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->bound) return RPB200_EINVAL;
+  return worklist_launch<true, 0>(p->pack_wl, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+}
+
+extern "C" int rpb200_halo_plan_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->bound) return RPB200_EINVAL;
+  return worklist_launch<false, 0>(p->unpack_wl, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+}
+
+// ---- exchange ---------------------------------------------------------------------------------
+// window layout (identical on every rank because every rank has the same grid):
+//   [0, 256)                  26 arrival flags (uint64), one per receive slot
+//   generation 0, generation 1: receive slot l at recv_off[g][l], nvars * unpack_len[l] doubles
+extern "C" int rpb200_halo_exchange_window(rpb200_halo_plan* p, double* const* vars, void** d_window,
+                                           size_t* bytes, unsigned char ipc_handle[64])
+{
+  if (!p || !vars) return RPB200_EINVAL;
+  if (!p->d_window) {
+    size_t off = 256;
+    for (int g = 0; g < 2; ++g)
+      for (int l = 0; l < NNB; ++l) {
+        p->recv_off[g][l] = off;
+        off += ((size_t)p->nvars * (size_t)p->unpack_len[l] * sizeof(double) + 255) / 256 * 256;
+      }
+    p->window_bytes = off;
+    RPB_CHECK(cudaMalloc(&p->d_window, off));
+    RPB_CHECK(cudaMemset(p->d_window, 0, off));
+    RPB_CHECK(cudaMalloc(&p->d_pack_msgs, sizeof(halo_msg) * NNB));
+    RPB_CHECK(cudaMalloc(&p->d_unpack_msgs, sizeof(halo_msg) * NNB));
+    RPB_CHECK(cudaMalloc(&p->d_msg_done, sizeof(unsigned int) * NNB));
+    RPB_CHECK(cudaMemset(p->d_msg_done, 0, sizeof(unsigned int) * NNB));
+    RPB_CHECK(cudaMalloc(&p->d_error, sizeof(int)));
+    RPB_CHECK(cudaMemset(p->d_error, 0, sizeof(int)));
+    RPB_CHECK(cudaDeviceSynchronize());
+  }
+  p->vars.assign(vars, vars + p->nvars);
+  if (d_window) *d_window = p->d_window;
+  if (bytes) *bytes = p->window_bytes;
+  if (ipc_handle) {
+    cudaIpcMemHandle_t h;
+    RPB_CHECK(cudaIpcGetMemHandle(&h, p->d_window));
+    memcpy(ipc_handle, &h, sizeof(h));
+  }
+  return 0;
+}
+
+static int exchange_finish_connect(rpb200_halo_plan* p)
+{
+  // pack work lists: message l of generation g goes into window[ranks[l]] slot opposite[l]
+  std::vector<rpb200_halo_seg> segs;
+  std::vector<halo_msg> pm(NNB), um(NNB);
+  for (int g = 0; g < 2; ++g) {
+    double* dst[NNB]; double* src[NNB];
+    for (int l = 0; l < NNB; ++l) {
+      const int o = p->opposite[l];
+      if (p->pack_len[l] != p->unpack_len[o]) return RPB200_EINVAL;
+      dst[l] = (double*)((unsigned char*)p->peer_windows[p->ranks[l]] + p->recv_off[g][o]);
+      src[l] = (double*)(p->d_window + p->recv_off[g][l]);
+    }
+    worklist_free(p->xpack_wl[g]); worklist_free(p->xunpack_wl[g]);
+    int rc = plan_segments(p, true, p->vars.data(), dst, segs);
+    if (rc == 0) rc = worklist_build(p->xpack_wl[g], segs.data(), (int)segs.size());
+    if (rc == 0) rc = plan_segments(p, false, p->vars.data(), src, segs);
+    if (rc == 0) rc = worklist_build(p->xunpack_wl[g], segs.data(), (int)segs.size());
+    if (rc != 0) return rc;
+  }
+  for (int l = 0; l < NNB; ++l) {
+    const int o = p->opposite[l];
+    pm[l].remote_flag = (unsigned long long*)p->peer_windows[p->ranks[l]] + o;
+    pm[l].my_flag = nullptr;
+    pm[l].chunks = (unsigned int)(p->nvars * ((p->pack_len[l] + HALO_CHUNK - 1) / HALO_CHUNK));
+    pm[l].pad = 0;
+    um[l].remote_flag = nullptr;
+    um[l].my_flag = (const unsigned long long*)p->d_window + l;
+    um[l].chunks = 0; um[l].pad = 0;
+  }
+  RPB_CHECK(cudaMemcpy(p->d_pack_msgs, pm.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
+  RPB_CHECK(cudaMemcpy(p->d_unpack_msgs, um.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
+  p->connected = true;
+  return 0;
+}
+
+extern "C" int rpb200_halo_exchange_connect(rpb200_halo_plan* p, int nranks, const unsigned char* handles)
+{
+  if (!p || !p->d_window || nranks != p->nranks || !handles) return RPB200_EINVAL;
+  p->peer_windows.assign(nranks, nullptr);
+  p->peer_opened.assign(nranks, false);
+  bool needed[4096] = {false};
+  if (nranks > 4096) return RPB200_EINVAL;
+  for (int l = 0; l < NNB; ++l) needed[p->ranks[l]] = true;
+  for (int r = 0; r < nranks; ++r) {
+    if (r == p->my_rank) { p->peer_windows[r] = p->d_window; continue; }
+    if (!needed[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + (size_t)r * 64, sizeof(h));
+    void* ptr = nullptr;
+    RPB_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_windows[r] = ptr; p->peer_opened[r] = true;
+  }
+  return exchange_finish_connect(p);
+}
+
+extern "C" int rpb200_halo_exchange_connect_ptrs(rpb200_halo_plan* p, int nranks, void* const* d_windows)
+{
+  if (!p || !p->d_window || nranks != p->nranks || !d_windows) return RPB200_EINVAL;
+  p->peer_windows.assign(d_windows, d_windows + nranks);
+  p->peer_opened.assign(nranks, false);
+  p->peer_windows[p->my_rank] = p->d_window;
+  for (int l = 0; l < NNB; ++l) if (!p->peer_windows[p->ranks[l]]) return RPB200_EINVAL;
+  return exchange_finish_connect(p);
+}
+
+extern "C" int rpb200_halo_exchange_pack(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->connected) return RPB200_EINVAL;
+  const unsigned long long epoch = ++p->epoch;
+  return worklist_launch<true, 1>(p->xpack_wl[epoch & 1], p->d_pack_msgs, p->d_msg_done, epoch, p->d_error, rpb_stream(s));
+}
+
+extern "C" int rpb200_halo_exchange_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->connected || p->epoch == 0) return RPB200_EINVAL;
+  const unsigned long long epoch = p->epoch;
+  return worklist_launch<false, 2>(p->xunpack_wl[epoch & 1], p->d_unpack_msgs, p->d_msg_done, epoch, p->d_error, rpb_stream(s));
+}
+
+extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  const int rc = rpb200_halo_exchange_pack(p, s);
+  return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
+}
+
+extern "C" int rpb200_halo_exchange_status(rpb200_halo_plan* p)
+{
+  if (!p || !p->d_error) return RPB200_EINVAL;
+  int e = 0;
+  RPB_CHECK(cudaMemcpy(&e, p->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  return e;
+}

@@ -97,3 +97,50 @@ def ltimes(target=0, nd=64, ng=32, nm=25):   # apps/LTIMES.cpp:23-92
     phi, ell, psi = _seq([("const", nm * ng * nz, 0.0), ("real", nd * nm), ("real", dg * nz)])
     scale = float(np.longdouble(0.001) * (np.longdouble(dflt) / np.longdouble(dg * nz)))
     return dict(nz=nz, nd=nd, ng=ng, nm=nm, phi=phi, ell=ell, psi=psi, scale=scale)
+
+
+def halo_lists(dims, hw):
+    """The 52 index lists of HALO_base::create_lists (comm/HALO_base.cpp:169-291) from the oracle."""
+    L = oracle.lib()
+    d = np.asarray(dims, dtype=np.int64)
+    pack, unpack = [], []
+    for l in range(26):
+        for recv, out in ((0, pack), (1, unpack)):
+            n = L.orc_halo_extent_len(recv, l, hw, d)
+            lst = np.empty(n, dtype=np.int32)
+            L.orc_halo_make_list(recv, l, hw, d, lst)
+            out.append(lst)
+    return pack, unpack
+
+
+def halo_neighbors(rank, pdims):
+    L = oracle.lib()
+    r, st, rt = (np.empty(26, dtype=np.int32) for _ in range(3))
+    L.orc_halo_neighbors(rank, np.asarray(pdims, dtype=np.int32), r, st, rt)
+    return r, st, rt
+
+
+def halo_packing_fused(target=0, hw=1, nvars=3):
+    """setUp of Comm_HALO_PACKING_FUSED (HALO_base.cpp:52-67, HALO_PACKING_FUSED.cpp:63-109): the
+    init counter is bumped by the 52 list allocations and the vars, so pack buffer l is filled
+    with initData at count 52+nvars+l and unpack buffer l at 52+nvars+26+l."""
+    L = oracle.lib()
+    dims = np.zeros(3, dtype=np.int64)
+    L.orc_halo_grid_dims(target or 1000000, dims)
+    pack, unpack = halo_lists(dims, hw)
+    var_size = int(np.prod(dims + 2 * hw))
+    L.orc_reset_init_count()
+    dummy = np.zeros(1, dtype=np.int32)
+    for _ in range(52):
+        L.orc_init_int(dummy, 0)
+    vars_ = []
+    for v in range(nvars):
+        a = np.empty(var_size); L.orc_init_real(a, 0)
+        vars_.append(np.arange(var_size, dtype=np.float64) + v)
+    pack_bufs, unpack_bufs = [], []
+    for l in range(26):
+        a = np.empty(nvars * pack[l].size); L.orc_init_real(a, a.size); pack_bufs.append(a)
+    for l in range(26):
+        a = np.empty(nvars * unpack[l].size); L.orc_init_real(a, a.size); unpack_bufs.append(a)
+    return dict(dims=[int(x) for x in dims], hw=hw, nvars=nvars, var_size=var_size, pack_lists=pack,
+                unpack_lists=unpack, vars=vars_, pack_bufs=pack_bufs, unpack_bufs=unpack_bufs)

@@ -1,0 +1,269 @@
+"""GPU parity: Comm group (HALO_base lists, HALO_PACKING_FUSED, HALO_EXCHANGE_FUSED) through the C ABI
+vs the CPU oracle and the reference's golden checksums.  Everything here is copies and integer index
+work => bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import suite_data as sd
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLD = [c for c in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums.json")))["cases"]
+        if c["kernel"] == "Comm_HALO_PACKING_FUSED"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def dev_list(plan, l, which):
+    """Copy a plan-owned device index list back to the host (through the ABI's own memcpy helper)."""
+    from rajaperf_b200 import cabi
+    nb = plan.neighbors[l]
+    n = nb["pack_len" if which == "pack" else "unpack_len"]
+    src = nb["d_pack_list" if which == "pack" else "d_unpack_list"]
+    host = np.empty(n, dtype=np.int32)
+    cabi.check(cabi.load().rpb200_memcpy_d2h(host.ctypes.data, src, 4 * n, None), "memcpy_d2h")
+    cabi.check(cabi.load().rpb200_device_synchronize(), "device_synchronize")
+    return host
+
+
+@pytest.mark.parametrize("dims,hw", [((5, 5, 5), 1), ((7, 4, 9), 2), ((30, 30, 30), 3), ((100, 100, 100), 1)])
+def test_plan_index_lists_match_oracle(ctx, dims, hw):
+    plan = ctx.halo_plan(dims, hw, 1)
+    pack, unpack = sd.halo_lists(dims, hw)
+    assert plan.var_size == int(np.prod(np.asarray(dims) + 2 * hw))
+    for l in range(26):
+        assert plan.neighbors[l]["pack_len"] == pack[l].size and plan.neighbors[l]["unpack_len"] == unpack[l].size
+        assert np.array_equal(dev_list(plan, l, "pack"), pack[l]), l
+        assert np.array_equal(dev_list(plan, l, "unpack"), unpack[l]), l
+    plan.close()
+
+
+@pytest.mark.parametrize("pdims", [(1, 1, 1), (2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2), (4, 2, 1)])
+def test_plan_rank_grid_matches_oracle(ctx, pdims):
+    P = pdims[0] * pdims[1] * pdims[2]
+    for rank in range(P):
+        plan = ctx.halo_plan((4, 4, 4), 1, 1, rank, pdims)
+        r, st, rt = sd.halo_neighbors(rank, pdims)
+        assert [nb["rank"] for nb in plan.neighbors] == r.tolist()
+        assert [nb["send_tag"] for nb in plan.neighbors] == st.tolist()
+        assert [nb["recv_tag"] for nb in plan.neighbors] == rt.tolist()
+        plan.close()
+
+
+def test_grid_dims_follow_the_reference_truncation():
+    from rajaperf_b200 import cabi
+    L = oracle.lib()
+    for target in (1, 27, 1000, 27000, 999999, 1000000, 1000001, 134217728, 1073741824):
+        d = np.zeros(3, dtype=np.int64)
+        L.orc_halo_grid_dims(target, d)
+        assert cabi.halo_grid_dims(target) == d.tolist()
+
+
+def run_packing_fused(ctx, d, reps):
+    vars_ = [dev(v) for v in d["vars"]]
+    pb = [dev(b) for b in d["pack_bufs"]]
+    ub = [dev(b) for b in d["unpack_bufs"]]
+    plan = ctx.halo_plan(d["dims"], d["hw"], d["nvars"])
+    plan.bind(vars_, pb, ub)
+    for _ in range(reps):
+        plan.pack()
+        plan.unpack()
+    torch.cuda.synchronize()
+    out = [v.cpu().numpy() for v in vars_], [b.cpu().numpy() for b in pb]
+    plan.close()
+    return out
+
+
+def oracle_packing_fused(d, reps):
+    L = oracle.lib()
+    vars_ = [v.copy() for v in d["vars"]]
+    pb = [b.copy() for b in d["pack_bufs"]]
+    nv = d["nvars"]
+    for _ in range(reps):
+        for l in range(26):
+            n = d["pack_lists"][l].size
+            for v in range(nv):
+                L.orc_halo_pack(pb[l][v * n:(v + 1) * n], d["pack_lists"][l], vars_[v], n)
+        for l in range(26):
+            n = d["unpack_lists"][l].size
+            for v in range(nv):
+                L.orc_halo_unpack(vars_[v], d["unpack_lists"][l], d["unpack_bufs"][l][v * n:(v + 1) * n], n)
+    return vars_, pb
+
+
+@pytest.mark.parametrize("case", GOLD, ids=lambda c: f"s{c['size']}-r{c['reps']}-{'_'.join(c['flags'])}")
+def test_halo_packing_fused_checksum_matches_reference_golden(ctx, case):
+    f = dict(zip(case["flags"][0::2], case["flags"][1::2]))
+    d = sd.halo_packing_fused(case["size"], int(f.get("--halo_width", 1)), int(f.get("--halo_num_vars", 3)))
+    vars_, pb = run_packing_fused(ctx, d, case["reps"])
+    ck = sum(oracle.checksum(v) for v in vars_) + sum(oracle.checksum(b) for b in pb)
+    ref = np.longdouble(case["checksum"])
+    assert abs(ck - ref) <= abs(ref) * np.longdouble(4e-19), (ck, ref)
+
+
+@pytest.mark.parametrize("target,hw,nv", [(1, 1, 1), (27, 1, 2), (1000, 3, 1), (50000, 2, 4), (300000, 1, 3)])
+def test_halo_packing_fused_bit_exact_vs_oracle(ctx, target, hw, nv):
+    d = sd.halo_packing_fused(target, hw, nv)
+    vars_, pb = run_packing_fused(ctx, d, 2)
+    rv, rp = oracle_packing_fused(d, 2)
+    for a, b in zip(vars_ + pb, rv + rp):
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+def test_generic_worklist_ragged_unaligned_and_empty_segments(ctx):
+    """The tuple API on its own: ragged lengths (0, 1, 3, chunk-1, chunk, chunk+1, 3 chunks + 5),
+    buffers that are only 8-byte aligned, lists that are only 4-byte aligned, repeated indices."""
+    rng = np.random.default_rng(7)
+    chunk = ctx.halo_chunk()
+    lens = [0, 1, 3, chunk - 1, chunk, chunk + 1, 3 * chunk + 5, 4 * chunk]
+    nvar = 100003
+    var = rng.standard_normal(nvar)
+    d_var = dev(var)
+    big_buf = torch.zeros(sum(lens) + 8 * len(lens) + 8, dtype=torch.float64, device="cuda")
+    big_list = torch.zeros(sum(lens) + 8 * len(lens) + 8, dtype=torch.int32, device="cuda")
+    segs, lists, offs = [], [], []
+    ob = ol = 0
+    for k, n in enumerate(lens):
+        lst = rng.integers(0, nvar, size=n).astype(np.int32)
+        ob += (k % 4)          # 8-byte aligned only for most segments
+        ol += (k % 3)          # 4-byte aligned only
+        big_list[ol:ol + n] = torch.from_numpy(lst).cuda()
+        segs.append((big_buf.data_ptr() + 8 * ob, big_list.data_ptr() + 4 * ol, d_var, n, k % 26))
+        lists.append(lst); offs.append(ob)
+        ob += n; ol += n
+    wl = ctx.halo_worklist(segs)
+    ctx.halo_pack(wl)
+    torch.cuda.synchronize()
+    got = big_buf.cpu().numpy()
+    for lst, o in zip(lists, offs):
+        assert np.array_equal(got[o:o + lst.size].view(np.int64), var[lst].view(np.int64))
+    # unpack into a fresh variable: last writer wins only matters for repeated indices, so use a permutation
+    perm = rng.permutation(nvar).astype(np.int32)
+    d_var2 = torch.zeros(nvar, dtype=torch.float64, device="cuda")
+    segs2, pos = [], 0
+    src = rng.standard_normal(sum(lens))
+    d_src = dev(src)
+    d_perm = dev(perm)
+    for k, n in enumerate(lens):
+        segs2.append((d_src.data_ptr() + 8 * pos, d_perm.data_ptr() + 4 * pos, d_var2, n, 0))
+        pos += n
+    wl2 = ctx.halo_worklist(segs2)
+    ctx.halo_unpack(wl2)
+    torch.cuda.synchronize()
+    ref = np.zeros(nvar)
+    ref[perm[:pos]] = src[:pos]
+    assert np.array_equal(d_var2.cpu().numpy().view(np.int64), ref.view(np.int64))
+    # update() with the same lengths but another variable
+    d_var3 = dev(var * 2.0)
+    wl.update([(b, l, d_var3, n, m) for (b, l, _, n, m) in segs])
+    ctx.halo_pack(wl)
+    torch.cuda.synchronize()
+    got = big_buf.cpu().numpy()
+    for lst, o in zip(lists, offs):
+        assert np.array_equal(got[o:o + lst.size], 2.0 * var[lst])
+    wl.close(); wl2.close()
+
+
+def simulate_exchange(dims, hw, nv, pdims, reps):
+    """P ranks of HALO_EXCHANGE_FUSED on the CPU with the oracle's primitives
+    (HALO_EXCHANGE_FUSED-Seq.cpp:35-116; delivery as in oracle/rpb_oracle.c)."""
+    L = oracle.lib()
+    P = pdims[0] * pdims[1] * pdims[2]
+    pack, unpack = sd.halo_lists(dims, hw)
+    var_size = int(np.prod(np.asarray(dims) + 2 * hw))
+    vars_ = [[np.arange(var_size, dtype=np.float64) + v for v in range(nv)] for _ in range(P)]
+    nbr = [sd.halo_neighbors(r, pdims) for r in range(P)]
+    for _ in range(reps):
+        sent = [[np.concatenate([vars_[r][v][pack[l]] for v in range(nv)]) for l in range(26)] for r in range(P)]
+        for q in range(P):
+            ranks, _, rtags = nbr[q]
+            for l in range(26):
+                buf = sent[ranks[l]][rtags[l]]
+                n = unpack[l].size
+                assert buf.size == nv * n
+                for v in range(nv):
+                    L.orc_halo_unpack(vars_[q][v], unpack[l], np.ascontiguousarray(buf[v * n:(v + 1) * n]), n)
+    return vars_
+
+
+@pytest.mark.parametrize("pdims", [(1, 1, 1), (2, 1, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("dims,hw,nv", [((6, 6, 6), 1, 3), ((20, 20, 20), 2, 2), ((64, 64, 64), 1, 3)])
+def test_halo_exchange_fused_many_ranks_on_one_gpu_bit_exact(ctx, pdims, dims, hw, nv):
+    """All ranks of a px*py*pz grid live in this process and share the GPU; their windows are
+    connected by plain pointers.  Every rank packs (and signals), then every rank waits + unpacks."""
+    P = pdims[0] * pdims[1] * pdims[2]
+    reps = 3
+    plans, dvars, wins = [], [], []
+    for r in range(P):
+        plan = ctx.halo_plan(dims, hw, nv, r, pdims)
+        vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
+        w, nbytes, _ = plan.window(vs, want_handle=False)
+        plans.append(plan); dvars.append(vs); wins.append(w)
+    for plan in plans:
+        plan.connect_ptrs(wins)
+    for _ in range(reps):
+        for plan in plans:
+            plan.exchange_pack()
+        for plan in plans:
+            plan.exchange_unpack()
+    torch.cuda.synchronize()
+    ref = simulate_exchange(dims, hw, nv, pdims, reps)
+    for r in range(P):
+        plans[r].status()
+        for v in range(nv):
+            assert np.array_equal(dvars[r][v].cpu().numpy().view(np.int64), ref[r][v].view(np.int64)), (r, v)
+    for plan in plans:
+        plan.close()
+
+
+@pytest.mark.parametrize("size,reps,hw,nv", [(0, 1, 1, 3), (0, 3, 1, 3), (27000, 2, 2, 5)])
+def test_halo_exchange_fused_suite_checksum_single_rank(ctx, size, reps, hw, nv):
+    """KernelBase flow of Comm_HALO_EXCHANGE_FUSED on one rank (periodic self-exchange) against the
+    oracle's whole-kernel driver (the reference cannot build this kernel without MPI)."""
+    from rajaperf_b200 import cabi
+    dims = cabi.halo_grid_dims(size or 1000000)
+    plan = ctx.halo_plan(dims, hw, nv)
+    vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
+    plan.window(vs, want_handle=False)
+    plan.connect_ptrs([0])
+    for _ in range(reps):
+        plan.exchange()
+    torch.cuda.synchronize()
+    plan.status()
+    ck = sum(oracle.checksum(v.cpu().numpy()) for v in vs)
+    ref = oracle.kat("Comm_HALO_EXCHANGE_FUSED", size, reps, [hw, nv, 1, 1, 1])
+    assert abs(ck - ref) <= abs(ref) * np.longdouble(4e-19), (ck, ref)
+    plan.close()
+
+
+def test_halo_full_size_properties(ctx):
+    """512^3 per GPU (BASELINE config 5): after one exchange every ghost cell equals the periodic
+    image of an owned cell; a second exchange is idempotent; owned cells are never modified."""
+    n, hw, nv = 512, 1, 3
+    plan = ctx.halo_plan((n, n, n), hw, nv)
+    e = n + 2 * hw
+    vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
+    plan.window(vs, want_handle=False)
+    plan.connect_ptrs([0])
+    plan.exchange()
+    torch.cuda.synchronize()
+    plan.status()
+    for v in range(nv):
+        a = vs[v].view(e, e, e)
+        idx = torch.arange(e, device="cuda")
+        src = ((idx - hw) % n) + hw                         # periodic image inside the owned box
+        want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64) + v
+        assert torch.equal(a, want)
+    before = [v.clone() for v in vs]
+    plan.exchange()
+    torch.cuda.synchronize()
+    for a, b in zip(vs, before):
+        assert torch.equal(a, b)
+    plan.close()
