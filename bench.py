@@ -215,20 +215,7 @@ def run_reference_arm(args, rank):
 # ------------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------------
-def rank_grid(P):
-    """The suite's default --mpi_3d_division (RunParams.cpp:1211-1251): prime factors in non-decreasing
-    order, each multiplied into the currently smallest dimension (first one on ties)."""
-    factors, number, f = [], P, 2
-    while f * f <= number:
-        if number % f == 0:
-            factors.append(f); number //= f
-        else:
-            f += 1
-    factors.append(number)
-    dims = [1, 1, 1]
-    for f in factors:
-        dims[dims.index(min(dims))] *= f
-    return dims
+from rajaperf_b200.dist import rank_grid  # noqa: E402  (RunParams.cpp:1211-1251)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -471,10 +458,26 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
     ub = [torch.zeros(nv * nb["unpack_len"], **f64) for nb in plan.neighbors]
     plan.bind(vars_, pb, ub)
 
+    def graph_ms(body, reps):
+        """reps x body() captured into ONE CUDA graph (the rep loop of the suite's runKernel), replayed and
+        timed with CUDA events: removes the ~10 us/launch cost of calling the C ABI from Python."""
+        body(); torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_):
+            for _ in range(reps):
+                body()
+        g_.replay(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g_.replay(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
     def packing():
         plan.pack(); plan.unpack()
-    rec("Comm_HALO_PACKING_FUSED", halo_elems, 40 * halo_elems, time_events(torch, packing, 50, 5),
-        grid=[g, g, g], launches_per_rep=2)
+    rec("Comm_HALO_PACKING_FUSED", halo_elems, 40 * halo_elems, graph_ms(packing, 100),
+        grid=[g, g, g], launches_per_rep=2, timed="100 reps in one CUDA graph")
 
     _, _, handle = plan.window(vars_)
     if world > 1:
@@ -484,27 +487,15 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
         dist.barrier()
     else:
         plan.connect_ptrs([0])
-    reps = 100
-    for _ in range(10):
-        plan.exchange()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        plan.exchange()
-    e1.record()
-    torch.cuda.synchronize()
+    ms = graph_ms(plan.exchange, 100)
     plan.status()
-    ms = e0.elapsed_time(e1) / reps
     if world > 1:
         t = torch.tensor([ms], **f64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-    rec("Comm_HALO_EXCHANGE_FUSED", halo_elems, 56 * halo_elems, ms, grid=[g, g, g], launches_per_rep=2)
+    rec("Comm_HALO_EXCHANGE_FUSED", halo_elems, 56 * halo_elems, ms, grid=[g, g, g], launches_per_rep=2,
+        timed="100 reps in one CUDA graph, max over ranks")
     halo = {"ms_per_rep": ms, "n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": [g, g, g],
             "halo_width": hw, "num_vars": nv, "bytes_sent_per_gpu_per_rep": 8 * halo_elems,
             "transport": "pack kernel stores into the peer's receive window over NVLink (CUDA IPC), "

@@ -4,11 +4,11 @@
 //   reference                                         here
 //   ------------------------------------------------  ----------------------------------------------
 //   (buffer,list,var,len) tuples in pinned HOST        tuples + a chunk->tuple map in DEVICE memory
-//   memory, read by every CTA over PCIe                (one 4-byte and one 32-byte load per CTA)
-//   grid (ceil(avg_len/1024), 78): CTAs of short       one CTA per 2048-element chunk of real work,
-//   tuples idle, CTAs of long ones loop                nothing idle, nothing loops
-//   scalar 4-byte index loads, 8-byte stores           128-bit index loads, 8 gathers in flight per
-//                                                      thread, 256-bit stores
+//   memory, read by every CTA over PCIe                (one 4-byte and one 32-byte load per chunk)
+//   grid (ceil(avg_len/1024), 78): CTAs of short       the work is cut into 2048-element chunks; a grid of
+//   tuples idle, CTAs of long ones loop                4 CTAs per SM takes equal contiguous chunk ranges
+//   1 element per thread per loop trip                 8 independent index loads, then 8 gathers (or
+//                                                      scatters) in flight per thread, all coalesced
 //   cudaStreamSynchronize after pack and after unpack  no host synchronisation at all
 //   MPI_Isend/Irecv through pinned host buffers        pack stores straight into the peer GPU's
 //                                                      receive buffer over NVLink; per-message
@@ -26,27 +26,11 @@ constexpr int HALO_BLOCK = 256;
 constexpr int HALO_CHUNK = 2048;      // elements per CTA: 8 per thread
 constexpr int NNB = RPB200_HALO_NEIGHBORS;
 
-enum { SEG_LIST16 = 1, SEG_BUF32 = 2 };
-
-__device__ __forceinline__ int4 ldg_idx4(const int* p)
-{
-  int4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
 // receive buffers are written by a peer GPU while this kernel may be resident: never through L1
 __device__ __forceinline__ double ld_cg(const double* p)
 {
   double v;
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ dbl4 ld_cg4(const double* p)
-{
-  dbl4 v;
-  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];"
-               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
@@ -69,76 +53,103 @@ struct halo_msg {
 };
 
 // MODE 0: plain;  MODE 1: pack + signal;  MODE 2: wait + unpack
+//
+// Every CTA owns a CONTIGUOUS range of chunks (so it walks the tuples in message order, stays inside
+// a few pages, and in MODE 1 needs ONE system-scope fence for everything it wrote).  Inside a chunk
+// lane t handles elements t, t+256, ...: the index loads, the buffer side and -- for every face whose
+// cells are contiguous -- the variable side are all fully coalesced (a thread owning 4 consecutive
+// elements would turn each of its 4 scatter instructions into 32 partial-sector writes).
 template <bool PACK, int MODE>
 __global__ void __launch_bounds__(HALO_BLOCK)
-halo_kernel(const rpb200_halo_seg* __restrict__ segs, const int* __restrict__ chunk_seg,
-            const long long* __restrict__ seg_first_chunk, const halo_msg* __restrict__ msgs,
-            unsigned int* __restrict__ msg_done, unsigned long long epoch, int* __restrict__ error)
+halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* __restrict__ segs_g1,
+            const int* __restrict__ chunk_seg, const long long* __restrict__ seg_first_chunk, int total_chunks,
+            const halo_msg* __restrict__ msgs, unsigned int* __restrict__ msg_done,
+            unsigned long long* __restrict__ d_epoch, unsigned int* __restrict__ unpack_done,
+            int* __restrict__ error)
 {
-  const int c = blockIdx.x;
-  const int s = __ldg(chunk_seg + c);
-  const rpb200_halo_seg seg = segs[s];
-  const int64_t i0 = ((int64_t)c - __ldg(seg_first_chunk + s)) * HALO_CHUNK;
-  const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+  constexpr int EPT = HALO_CHUNK / HALO_BLOCK;     // 8 elements per thread per chunk
+  // The exchange epoch lives in device memory (so a CUDA graph of many reps replays correctly): the
+  // pack and the unpack of one rep both see *d_epoch + 1; the last unpack CTA to retire commits it.
+  // Its parity selects the receive-buffer generation.
+  unsigned long long epoch = 0;
+  if (MODE != 0) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
+  epoch += 1;
+  const rpb200_halo_seg* __restrict__ segs = (MODE != 0 && (epoch & 1ull)) ? segs_g1 : segs_g0;
+  const int per = (total_chunks + gridDim.x - 1) / gridDim.x;
+  const int c_begin = blockIdx.x * per;
+  const int c_end = min(c_begin + per, total_chunks);
+  int waited_msg = -1;
 
-  if (MODE == 2) {
-    if (threadIdx.x == 0) {
-      const unsigned long long* f = msgs[seg.msg].my_flag;
-      unsigned int spins = 0;
-      while (ld_acquire_sys(f) < epoch) {
-        __nanosleep(40);
-        if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }   // > 1 s: give up loudly
+  for (int c = c_begin; c < c_end; ++c) {
+    const int s = __ldg(chunk_seg + c);
+    const rpb200_halo_seg seg = segs[s];
+    const int64_t i0 = ((int64_t)c - __ldg(seg_first_chunk + s)) * HALO_CHUNK;
+    const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+
+    if (MODE == 2 && seg.msg != waited_msg) {      // first chunk of a message this CTA touches: acquire it
+      if (threadIdx.x == 0) {
+        const unsigned long long* f = msgs[seg.msg].my_flag;
+        unsigned int spins = 0;
+        while (ld_acquire_sys(f) < epoch) {
+          __nanosleep(40);
+          if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }   // > 1 s: give up loudly
+        }
       }
+      __syncthreads();
+      waited_msg = seg.msg;
     }
-    __syncthreads();
-  }
 
-  const int* __restrict__ list = seg.list + i0;
-  double* __restrict__ buf = seg.buffer + i0;
-  double* __restrict__ var = seg.var;
-
-  const bool vec = (seg.flags & (SEG_LIST16 | SEG_BUF32)) == (SEG_LIST16 | SEG_BUF32);
-  int done = 0;
-  if (vec) {
-    // two independent groups of 4 per thread: 8 gathers / scatters in flight
-    const int nvec = cnt >> 2;
-    const int v0 = threadIdx.x, v1 = threadIdx.x + HALO_BLOCK;
-    const bool ok0 = v0 < nvec, ok1 = v1 < nvec;
-    int4 ia = make_int4(0, 0, 0, 0), ib = ia;
-    if (ok0) ia = ldg_idx4(list + 4 * v0);
-    if (ok1) ib = ldg_idx4(list + 4 * v1);
+    const int* __restrict__ list = seg.list + i0;
+    double* __restrict__ buf = seg.buffer + i0;
+    double* __restrict__ var = seg.var;
+    int idx[EPT];
+    double v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const int i = k * HALO_BLOCK + threadIdx.x;
+      idx[k] = (i < cnt) ? __ldg(list + i) : -1;
+    }
     if (PACK) {
-      dbl4 a, b;
-      if (ok0) { a.x = var[ia.x]; a.y = var[ia.y]; a.z = var[ia.z]; a.w = var[ia.w]; }
-      if (ok1) { b.x = var[ib.x]; b.y = var[ib.y]; b.z = var[ib.z]; b.w = var[ib.w]; }
-      if (ok0) stg256(buf + 4 * v0, a);
-      if (ok1) stg256(buf + 4 * v1, b);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
     } else {
-      dbl4 a, b;
-      if (ok0) a = ld_cg4(buf + 4 * v0);
-      if (ok1) b = ld_cg4(buf + 4 * v1);
-      if (ok0) { var[ia.x] = a.x; var[ia.y] = a.y; var[ia.z] = a.z; var[ia.w] = a.w; }
-      if (ok1) { var[ib.x] = b.x; var[ib.y] = b.y; var[ib.z] = b.z; var[ib.w] = b.w; }
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) var[idx[k]] = v[k];
     }
-    done = nvec << 2;
-  }
-  for (int i = done + threadIdx.x; i < cnt; i += HALO_BLOCK) {
-    if (PACK) buf[i] = var[list[i]];
-    else      var[list[i]] = ld_cg(buf + i);
   }
 
-  if (MODE == 1) {
-    // all stores of this CTA -> barrier -> system fence -> count the chunk; whoever completes the
-    // message publishes the epoch to the destination's flag (release at system scope)
+  if (MODE == 1 && c_begin < c_end) {
+    // all stores of this CTA -> barrier -> ONE system fence -> credit every message it touched; whoever
+    // completes a message publishes the epoch to the destination's flag (release at system scope)
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence_system();
-      const halo_msg m = msgs[seg.msg];
-      const unsigned int prev = atomicAdd(msg_done + seg.msg, 1u);
-      if (prev == m.chunks - 1) {
-        msg_done[seg.msg] = 0u;          // re-armed for the next rep (stream-ordered launches)
-        __threadfence_system();
-        st_release_sys(m.remote_flag, epoch);
+      int c = c_begin;
+      while (c < c_end) {
+        const int m = segs[__ldg(chunk_seg + c)].msg;
+        int run = 1;
+        while (c + run < c_end && segs[__ldg(chunk_seg + c + run)].msg == m) ++run;
+        const halo_msg hm = msgs[m];
+        const unsigned int prev = atomicAdd(msg_done + m, (unsigned int)run);
+        if (prev + run == hm.chunks) {
+          msg_done[m] = 0u;              // re-armed for the next rep (stream-ordered launches)
+          st_release_sys(hm.remote_flag, epoch);
+        }
+        c += run;
+      }
+    }
+  }
+  if (MODE == 2) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(unpack_done, 1u);
+      if (prev == gridDim.x - 1) {       // every CTA has read the epoch and finished: commit it
+        *unpack_done = 0u;
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
       }
     }
   }
@@ -164,9 +175,7 @@ int worklist_free(worklist_dev& w)
 
 void classify(rpb200_halo_seg& s)
 {
-  s.flags = 0;
-  if (rpb_aligned(s.list, 16)) s.flags |= SEG_LIST16;
-  if (rpb_aligned(s.buffer, 32)) s.flags |= SEG_BUF32;
+  s.flags = 0;     // reserved (alignment classes are not needed: every access is element-wise coalesced)
 }
 
 int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
@@ -202,13 +211,25 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   return 0;
 }
 
+struct exchange_args {
+  const worklist_dev* other_gen = nullptr;   // generation-1 tuples (same chunk map)
+  const halo_msg* msgs = nullptr;
+  unsigned int* msg_done = nullptr;
+  unsigned long long* d_epoch = nullptr;
+  unsigned int* unpack_done = nullptr;
+  int* error = nullptr;
+};
+
 template <bool PACK, int MODE>
-int worklist_launch(const worklist_dev& w, const halo_msg* msgs, unsigned int* msg_done,
-                    unsigned long long epoch, int* error, cudaStream_t st)
+int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const exchange_args& x, cudaStream_t st)
 {
   if (w.total_chunks == 0) return 0;
-  halo_kernel<PACK, MODE><<<(int)w.total_chunks, HALO_BLOCK, 0, st>>>(w.d_segs, w.d_chunk_seg, w.d_first, msgs,
-                                                                     msg_done, epoch, error);
+  const int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
+  int64_t grid = (int64_t)ctx->sm_count * cps;
+  if (grid > w.total_chunks) grid = w.total_chunks;
+  halo_kernel<PACK, MODE><<<(int)grid, HALO_BLOCK, 0, st>>>(
+      w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)w.total_chunks,
+      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error);
   RPB_LAUNCH_CHECK();
   return 0;
 }
@@ -272,7 +293,8 @@ struct rpb200_halo_plan {
   halo_msg* d_pack_msgs = nullptr; halo_msg* d_unpack_msgs = nullptr;
   unsigned int* d_msg_done = nullptr;
   int* d_error = nullptr;
-  unsigned long long epoch = 0;
+  unsigned long long* d_epoch = nullptr;   // committed exchange epoch (device): reps done so far
+  unsigned int* d_unpack_done = nullptr;
   bool connected = false;
 };
 
@@ -315,13 +337,13 @@ extern "C" void rpb200_halo_worklist_destroy(rpb200_halo_worklist* wl)
 extern "C" int rpb200_halo_pack(rpb200_ctx* ctx, const rpb200_halo_worklist* wl, rpb200_stream_t s)
 {
   if (!ctx || !wl) return RPB200_EINVAL;
-  return worklist_launch<true, 0>(wl->w, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+  return worklist_launch<true, 0>(ctx, RPB_K_HALO_PACKING_FUSED, wl->w, exchange_args(), rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_unpack(rpb200_ctx* ctx, const rpb200_halo_worklist* wl, rpb200_stream_t s)
 {
   if (!ctx || !wl) return RPB200_EINVAL;
-  return worklist_launch<false, 0>(wl->w, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+  return worklist_launch<false, 0>(ctx, RPB_K_HALO_PACKING_FUSED, wl->w, exchange_args(), rpb_stream(s));
 }
 
 // comm/HALO_base.cpp:31-35: the double is truncated when stored into the Index_type dims
@@ -341,6 +363,7 @@ extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
     if (p->peer_opened[r] && p->peer_windows[r]) cudaIpcCloseMemHandle(p->peer_windows[r]);
   cudaFree(p->d_window);
   cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
+  cudaFree(p->d_epoch); cudaFree(p->d_unpack_done);
   delete p;
 }
 
@@ -466,13 +489,13 @@ extern "C" int rpb200_halo_plan_bind(rpb200_halo_plan* p, double* const* vars, d
 extern "C" int rpb200_halo_plan_pack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
   if (!p || !p->bound) return RPB200_EINVAL;
-  return worklist_launch<true, 0>(p->pack_wl, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+  return worklist_launch<true, 0>(p->ctx, RPB_K_HALO_PACKING_FUSED, p->pack_wl, exchange_args(), rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_plan_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
   if (!p || !p->bound) return RPB200_EINVAL;
-  return worklist_launch<false, 0>(p->unpack_wl, nullptr, nullptr, 0, nullptr, rpb_stream(s));
+  return worklist_launch<false, 0>(p->ctx, RPB_K_HALO_PACKING_FUSED, p->unpack_wl, exchange_args(), rpb_stream(s));
 }
 
 // ---- exchange ---------------------------------------------------------------------------------
@@ -499,6 +522,10 @@ extern "C" int rpb200_halo_exchange_window(rpb200_halo_plan* p, double* const* v
     RPB_CHECK(cudaMemset(p->d_msg_done, 0, sizeof(unsigned int) * NNB));
     RPB_CHECK(cudaMalloc(&p->d_error, sizeof(int)));
     RPB_CHECK(cudaMemset(p->d_error, 0, sizeof(int)));
+    RPB_CHECK(cudaMalloc(&p->d_epoch, sizeof(unsigned long long)));
+    RPB_CHECK(cudaMemset(p->d_epoch, 0, sizeof(unsigned long long)));
+    RPB_CHECK(cudaMalloc(&p->d_unpack_done, sizeof(unsigned int)));
+    RPB_CHECK(cudaMemset(p->d_unpack_done, 0, sizeof(unsigned int)));
     RPB_CHECK(cudaDeviceSynchronize());
   }
   p->vars.assign(vars, vars + p->nvars);
@@ -578,18 +605,28 @@ extern "C" int rpb200_halo_exchange_connect_ptrs(rpb200_halo_plan* p, int nranks
   return exchange_finish_connect(p);
 }
 
+static exchange_args plan_xargs(rpb200_halo_plan* p, bool pack)
+{
+  exchange_args x;
+  x.other_gen = pack ? &p->xpack_wl[1] : &p->xunpack_wl[1];
+  x.msgs = pack ? p->d_pack_msgs : p->d_unpack_msgs;
+  x.msg_done = p->d_msg_done;
+  x.d_epoch = p->d_epoch;
+  x.unpack_done = p->d_unpack_done;
+  x.error = p->d_error;
+  return x;
+}
+
 extern "C" int rpb200_halo_exchange_pack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
   if (!p || !p->connected) return RPB200_EINVAL;
-  const unsigned long long epoch = ++p->epoch;
-  return worklist_launch<true, 1>(p->xpack_wl[epoch & 1], p->d_pack_msgs, p->d_msg_done, epoch, p->d_error, rpb_stream(s));
+  return worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xpack_wl[0], plan_xargs(p, true), rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_exchange_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
-  if (!p || !p->connected || p->epoch == 0) return RPB200_EINVAL;
-  const unsigned long long epoch = p->epoch;
-  return worklist_launch<false, 2>(p->xunpack_wl[epoch & 1], p->d_unpack_msgs, p->d_msg_done, epoch, p->d_error, rpb_stream(s));
+  if (!p || !p->connected) return RPB200_EINVAL;
+  return worklist_launch<false, 2>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xunpack_wl[0], plan_xargs(p, false), rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)

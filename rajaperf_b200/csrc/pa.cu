@@ -40,22 +40,47 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
                 int64_t NE)
 {
   constexpr int ND = 4, NQ = 5, SLAB = NQ * NQ;          // 25 values per (element, dz) slab
+  constexpr int BT = (E * SLAB + BLOCK - 1) / BLOCK;     // stage-B tasks per thread
+  static_assert(E * ND <= BLOCK, "one stage-A/C task per thread");
   __shared__ double T[E * ND * SLAB];                    // [task = e*4+dz][25], stride 25 (odd)
 
   const int64_t nbatch = (NE + E - 1) / E;
   for (int64_t batch = blockIdx.x; batch < nbatch; batch += gridDim.x) {
     const int64_t e0 = batch * E;
     const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
+    const int t = threadIdx.x;
+    const bool has_slab = t < cnt * ND;
+
+    // ---- request the whole batch up front: X slab, every D value this thread will need in stage B,
+    //      and the Y slab it will update in stage C (they land while stage A / B compute)
+    const double* xp = X + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
+    double* yp = Y + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
+    dbl4 xv[ND], yo[ND];
+    if (has_slab) {
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) xv[dy] = ldg256_stream(xp + 4 * dy);
+    }
+    double dq[BT][NQ];
+#pragma unroll
+    for (int it = 0; it < BT; ++it) {
+      const int p = t + it * BLOCK;
+      if (p < cnt * SLAB) {
+        const int e = p / SLAB, pen = p - e * SLAB;
+        const double* dp = D + (e0 + e) * 125 + pen;
+#pragma unroll
+        for (int qz = 0; qz < NQ; ++qz) dq[it][qz] = __ldg(dp + qz * SLAB);
+      }
+    }
+    if (has_slab) {
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) yo[dy] = ldg256(yp + 4 * dy);
+    }
 
     // ---- stage A: (e, dz) -> contract x, then y
-    for (int t = threadIdx.x; t < cnt * ND; t += BLOCK) {
-      const double* xp = X + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
+    if (has_slab) {
       double x[ND][ND];
 #pragma unroll
-      for (int dy = 0; dy < ND; ++dy) {
-        const dbl4 v = ldg256_stream(xp + 4 * dy);
-        x[dy][0] = v.x; x[dy][1] = v.y; x[dy][2] = v.z; x[dy][3] = v.w;
-      }
+      for (int dy = 0; dy < ND; ++dy) { x[dy][0] = xv[dy].x; x[dy][1] = xv[dy].y; x[dy][2] = xv[dy].z; x[dy][3] = xv[dy].w; }
       double a[ND][NQ];
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy)
@@ -80,40 +105,36 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     __syncthreads();
 
     // ---- stage B: (e, pencil) -> contract z, scale by D, contract z back
-    for (int p = threadIdx.x; p < cnt * SLAB; p += BLOCK) {
-      const int e = p / SLAB, pen = p - e * SLAB;
-      const double* dp = D + (e0 + e) * 125 + pen;
-      double dq[NQ];
 #pragma unroll
-      for (int qz = 0; qz < NQ; ++qz) dq[qz] = __ldg(dp + qz * SLAB);
-      double* tp = T + e * ND * SLAB + pen;
-      double u[ND];
+    for (int it = 0; it < BT; ++it) {
+      const int p = t + it * BLOCK;
+      if (p < cnt * SLAB) {
+        const int e = p / SLAB, pen = p - e * SLAB;
+        double* tp = T + e * ND * SLAB + pen;
+        double u[ND];
 #pragma unroll
-      for (int dz = 0; dz < ND; ++dz) u[dz] = tp[dz * SLAB];
-      double q[NQ];
+        for (int dz = 0; dz < ND; ++dz) u[dz] = tp[dz * SLAB];
+        double q[NQ];
 #pragma unroll
-      for (int qz = 0; qz < NQ; ++qz) {
-        double s = 0.0;
+        for (int qz = 0; qz < NQ; ++qz) {
+          double s = 0.0;
 #pragma unroll
-        for (int dz = 0; dz < ND; ++dz) s = fma(u[dz], c_mass_B[qz * ND + dz], s);
-        q[qz] = s * dq[qz];
-      }
+          for (int dz = 0; dz < ND; ++dz) s = fma(u[dz], c_mass_B[qz * ND + dz], s);
+          q[qz] = s * dq[it][qz];
+        }
 #pragma unroll
-      for (int dz = 0; dz < ND; ++dz) {
-        double s = 0.0;
+        for (int dz = 0; dz < ND; ++dz) {
+          double s = 0.0;
 #pragma unroll
-        for (int qz = 0; qz < NQ; ++qz) s = fma(q[qz], c_mass_Bt[dz * NQ + qz], s);
-        tp[dz * SLAB] = s;
+          for (int qz = 0; qz < NQ; ++qz) s = fma(q[qz], c_mass_Bt[dz * NQ + qz], s);
+          tp[dz * SLAB] = s;
+        }
       }
     }
     __syncthreads();
 
     // ---- stage C: (e, dz) -> contract y, then x, accumulate into Y
-    for (int t = threadIdx.x; t < cnt * ND; t += BLOCK) {
-      double* yp = Y + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
-      dbl4 yo[ND];
-#pragma unroll
-      for (int dy = 0; dy < ND; ++dy) yo[dy] = ldg256(yp + 4 * dy);
+    if (has_slab) {
       const double* tp = T + t * SLAB;
       double a[ND][NQ];
 #pragma unroll

@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Quick A/B timings on one B200 (run under gpurun): python tools/time_quick.py scan mass halo ..."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rajaperf_b200 import Context  # noqa: E402
+
+which = set(sys.argv[1:]) or {"scan", "pa", "halo", "sort"}
+ctx = Context(0)
+f64 = dict(dtype=torch.float64, device="cuda")
+res = {}
+
+
+def time_ms(fn, reps=20, warm=3, setup=None):
+    for _ in range(warm):
+        if setup: setup()
+        fn()
+    torch.cuda.synchronize()
+    if setup is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    tot = 0.0
+    for _ in range(reps):
+        setup()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / reps
+
+
+def report(name, bytes_, ms, **kw):
+    res[name] = dict(ms=ms, gbs=bytes_ / ms / 1e6, **kw)
+    print(f"{name:48s} {ms:9.4f} ms {bytes_ / ms / 1e6:9.1f} GB/s {kw if kw else ''}", flush=True)
+
+
+if "scan" in which:
+    n = 1 << 27
+    x = torch.rand(n, **f64); y = torch.empty(n, **f64)
+    for tune in [(512, 1, 4), (512, 2, 4), (512, 4, 4), (256, 2, 4), (256, 4, 4), (256, 8, 4), (256, 4, 2), (512, 2, 2), (1024, 1, 2), (128, 4, 4)]:
+        try:
+            ctx.set_tuning("Algorithm_SCAN", *tune)
+            report(f"scan{tune}", 16 * n, time_ms(lambda: ctx.scan_exclusive(x, y)))
+        except Exception as e:
+            print("scan", tune, "failed", e)
+    del x, y
+
+if "pa" in which:
+    NE = 4000000
+    one = lambda m: torch.ones(m, **f64)
+    B, Bt, D, X, Y = one(20), one(20), one(125 * NE), one(64 * NE), one(64 * NE)
+    for cps in (0, 1, 2, 3, 4):
+        ctx.set_tuning("Apps_MASS3DPA", -1, cps, -1)
+        report(f"mass3dpa cps={cps}", 2536 * NE, time_ms(lambda: ctx.mass3dpa(B, Bt, D, X, Y, NE), 10))
+    del D, X, Y
+    B, G, D, X, Y = one(12), one(12), one(384 * NE), one(27 * NE), one(27 * NE)
+    for cps in (0, 2, 4):
+        ctx.set_tuning("Apps_DIFFUSION3DPA", -1, cps, -1)
+        report(f"diffusion3dpa cps={cps}", 3720 * NE, time_ms(lambda: ctx.diffusion3dpa(B, G, D, X, Y, NE), 10))
+    del D
+    D = one(192 * NE)
+    for cps in (0, 2, 4):
+        ctx.set_tuning("Apps_CONVECTION3DPA", -1, cps, -1)
+        report(f"convection3dpa cps={cps}", 2184 * NE, time_ms(lambda: ctx.convection3dpa(B, B, G, D, X, Y, NE), 10))
+    del D, X, Y
+
+if "halo" in which:
+    for g in (512,):
+        nv = 3
+        plan = ctx.halo_plan((g, g, g), 1, nv)
+        vars_ = [torch.arange(plan.var_size, **f64) + v for v in range(nv)]
+        pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
+        ub = [torch.zeros(nv * nb["unpack_len"], **f64) for nb in plan.neighbors]
+        plan.bind(vars_, pb, ub)
+        ne = sum(nb["pack_len"] for nb in plan.neighbors) * nv
+        plan.window(vars_, want_handle=False); plan.connect_ptrs([0])
+        for cps in (2, 4, 8, 16):
+            ctx.set_tuning("Comm_HALO_PACKING_FUSED", -1, cps, -1)
+            ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", -1, cps, -1)
+            report(f"halo{g} pack cps={cps}", 20 * ne, time_ms(plan.pack, 50))
+            report(f"halo{g} unpack cps={cps}", 20 * ne, time_ms(plan.unpack, 50))
+            report(f"halo{g} pack+unpack cps={cps}", 40 * ne, time_ms(lambda: (plan.pack(), plan.unpack()), 50))
+            report(f"halo{g} exchange cps={cps}", 56 * ne, time_ms(plan.exchange, 50))
+        plan.status()
+        plan.close()
+        del vars_, pb, ub
+
+if "sort" in which:
+    n = 1 << 27
+    src = torch.randint(0, 2**31 - 1, (n,), device="cuda").to(torch.float64).div_(2147483647.0)
+    k = torch.empty_like(src); v = torch.empty_like(src)
+    scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
+    ms = time_ms(lambda: ctx.sort_keys(k, scratch), 5, 2, setup=lambda: k.copy_(src))
+    report("sort_keys", 16 * n, ms, mkeys_s=n / ms / 1e3)
+    ms = time_ms(lambda: ctx.sort_pairs(k, v, scratch), 5, 2, setup=lambda: (k.copy_(src), v.copy_(src)))
+    report("sort_pairs", 32 * n, ms, mkeys_s=n / ms / 1e3)
+    ms = time_ms(lambda: torch.sort(src), 5, 2)
+    report("torch.sort (CUB pairs: keys + int64 indices)", 32 * n, ms, mkeys_s=n / ms / 1e3)
+
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(res, open("gpurun_out/time_quick.json", "w"), indent=1)
