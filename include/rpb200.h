@@ -70,6 +70,9 @@ int rpb200_reduce_sum(rpb200_ctx*, const double* x, int64_t n, double init, doub
 /* algorithm/SCAN-Cuda.cpp:34-188 + common/CudaGridScan.hpp: exclusive prefix sum,
  * single pass (decoupled look-back), no per-call memset.                            */
 int rpb200_scan_exclusive(rpb200_ctx*, const double* x, double* y, int64_t n, rpb200_stream_t);
+/* Optional: grow the context's look-back state for n elements now (synchronises), so that later
+ * rpb200_scan_exclusive calls never allocate -- required before capturing them into a CUDA graph.  */
+int rpb200_scan_reserve(rpb200_ctx*, int64_t n);
 /* algorithm/SORT-Cuda.cpp:35-43 (RAJA::sort -> cub::DeviceRadixSort::SortKeys):
  * ascending in-place sort of n doubles (IEEE total order on non-NaN values, -0 < +0).
  * scratch: rpb200_sort_scratch_bytes(n, pairs) bytes of device memory.              */
@@ -178,6 +181,8 @@ int  rpb200_halo_exchange_status(rpb200_halo_plan*);
 int rpb200_ipc_export(void* d_ptr, unsigned char handle[RPB200_IPC_HANDLE_BYTES]);
 int rpb200_ipc_open(const unsigned char handle[RPB200_IPC_HANDLE_BYTES], void** d_ptr_out);
 int rpb200_ipc_close(void* d_ptr);
+/* one process driving several GPUs: let `device` read/write `peer_device` memory through plain pointers */
+int rpb200_enable_peer_access(int device, int peer_device);
 
 /* ---- device memory + timing helpers for C/C++ hosts (the suite harness) ---------
  * Replace allocAndInitData, copyData and deallocData for DataSpace::CudaDevice

@@ -44,6 +44,7 @@ SIGNATURES = {
     "rpb200_stream_dot": (c_int, [_P, _P, _P, c_int64, c_double, _P, c_int, _P]),
     "rpb200_reduce_sum": (c_int, [_P, _P, c_int64, c_double, _P, _P]),
     "rpb200_scan_exclusive": (c_int, [_P, _P, _P, c_int64, _P]),
+    "rpb200_scan_reserve": (c_int, [_P, c_int64]),
     "rpb200_sort_scratch_bytes": (c_size_t, [c_int64, c_int]),
     "rpb200_sort_keys_f64": (c_int, [_P, _P, c_int64, _P, c_size_t, _P]),
     "rpb200_sort_pairs_f64": (c_int, [_P, _P, _P, c_int64, _P, c_size_t, _P]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "rpb200_ipc_export": (c_int, [_P, POINTER(c_ubyte)]),
     "rpb200_ipc_open": (c_int, [POINTER(c_ubyte), POINTER(_P)]),
     "rpb200_ipc_close": (c_int, [_P]),
+    "rpb200_enable_peer_access": (c_int, [c_int, c_int]),
     "rpb200_malloc": (c_int, [POINTER(_P), c_size_t]),
     "rpb200_free": (c_int, [_P]),
     "rpb200_malloc_host": (c_int, [POINTER(_P), c_size_t]),

@@ -167,3 +167,18 @@ extern "C" int rpb200_ipc_open(const unsigned char handle[RPB200_IPC_HANDLE_BYTE
   return 0;
 }
 extern "C" int rpb200_ipc_close(void* d_ptr) { RPB_CHECK(cudaIpcCloseMemHandle(d_ptr)); return 0; }
+
+extern "C" int rpb200_enable_peer_access(int device, int peer_device)
+{
+  if (device == peer_device) return 0;
+  int can = 0;
+  RPB_CHECK(cudaDeviceCanAccessPeer(&can, device, peer_device));
+  if (!can) return (int)cudaErrorPeerAccessUnsupported;
+  int cur = 0;
+  RPB_CHECK(cudaGetDevice(&cur));
+  RPB_CHECK(cudaSetDevice(device));
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  cudaSetDevice(cur);
+  return (int)e;
+}

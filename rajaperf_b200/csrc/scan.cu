@@ -148,6 +148,29 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
 
 }  // namespace
 
+static int scan_grow_state(rpb200_ctx* ctx, size_t need, cudaStream_t st)
+{
+  if (need <= ctx->scan_state_bytes) return 0;
+  // grows only; fresh memory is zeroed once so no stale word can alias a live epoch
+  RPB_CHECK(cudaStreamSynchronize(st));
+  if (ctx->d_scan_state) RPB_CHECK(cudaFree(ctx->d_scan_state));
+  ctx->d_scan_state = nullptr; ctx->scan_state_bytes = 0;
+  size_t cap = need + need / 2 + 4096;
+  RPB_CHECK(cudaMalloc(&ctx->d_scan_state, cap));
+  RPB_CHECK(cudaMemset(ctx->d_scan_state, 0, cap));
+  ctx->scan_state_bytes = cap;
+  ctx->scan_epoch = 0;
+  return 0;
+}
+
+extern "C" int rpb200_scan_reserve(rpb200_ctx* ctx, int64_t n)
+{
+  if (!ctx || n < 0) return RPB200_EINVAL;
+  // the smallest tile any tuning can select (32 threads x 4 doubles) bounds the tile count
+  const size_t tiles = (size_t)((n + 127) / 128);
+  return scan_grow_state(ctx, sizeof(tile_desc) * tiles, nullptr);
+}
+
 extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y, int64_t n,
                                      rpb200_stream_t s)
 {
@@ -165,17 +188,7 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   const unsigned int tiles = (unsigned int)tiles64;
 
   const size_t need = sizeof(tile_desc) * (size_t)tiles;
-  if (need > ctx->scan_state_bytes) {
-    // grows only; fresh memory is zeroed once so no stale word can alias a live epoch
-    RPB_CHECK(cudaStreamSynchronize(st));
-    if (ctx->d_scan_state) RPB_CHECK(cudaFree(ctx->d_scan_state));
-    ctx->d_scan_state = nullptr; ctx->scan_state_bytes = 0;
-    size_t cap = need + need / 2 + 4096;
-    RPB_CHECK(cudaMalloc(&ctx->d_scan_state, cap));
-    RPB_CHECK(cudaMemset(ctx->d_scan_state, 0, cap));
-    ctx->scan_state_bytes = cap;
-    ctx->scan_epoch = 0;
-  }
+  { const int rc = scan_grow_state(ctx, need, st); if (rc != 0) return rc; }
   const unsigned long long epoch = ++ctx->scan_epoch;
 
   int grid = ctx->sm_count * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 4);

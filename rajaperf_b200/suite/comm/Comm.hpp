@@ -1,0 +1,63 @@
+// Comm.hpp -- HALO_base, HALO_PACKING_FUSED, HALO_EXCHANGE_FUSED behind KernelBase
+// (reference: comm/HALO_base.{hpp,cpp}, HALO_PACKING_FUSED.{hpp,cpp}, HALO_EXCHANGE_FUSED.{hpp,cpp}).
+#pragma once
+#include <vector>
+
+#include "../common/KernelBase.hpp"
+
+namespace rajaperf {
+namespace comm {
+
+// Grid dimensions and the per-rank halo plan (26 neighbours, 52 index lists on the device).
+class HALO_base : public KernelBase {
+public:
+  HALO_base(KernelID kid, const RunParams& params);
+  static constexpr int s_num_neighbors = RPB200_HALO_NEIGHBORS;
+protected:
+  Index_type m_grid_dims[3], m_halo_width, m_num_vars, m_var_size = 0;
+  Index_type m_halo_elems = 0;      // sum over neighbours of the pack-list length
+  // allocates the plan of `rank` on `c` and bumps the init counter once per list, as
+  // HALO_base::create_lists does through allocAndInitData (HALO_base.cpp:228-232, 262-266)
+  rpb200_halo_plan* setUp_base(rpb200_ctx* c, int rank, const int* rank_dims);
+};
+
+class HALO_PACKING_FUSED : public HALO_base {
+public:
+  explicit HALO_PACKING_FUSED(const RunParams& params);
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void updateChecksum(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void runB200Variant(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  rpb200_halo_plan* m_plan = nullptr;
+  std::vector<Real_ptr> m_vars, m_pack_buffers, m_unpack_buffers;
+  std::vector<Index_type> m_pack_lens, m_unpack_lens;
+};
+
+// All px*py*pz ranks live in this process; rank r runs on CUDA device first + (r mod ndev).  Every rank
+// owns its vars and its receive window; windows are connected through peer pointers (NVLink P2P when
+// the ranks sit on different GPUs).
+class HALO_EXCHANGE_FUSED : public HALO_base {
+public:
+  explicit HALO_EXCHANGE_FUSED(const RunParams& params);
+  ~HALO_EXCHANGE_FUSED() override;
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void updateChecksum(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void runB200Variant(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  struct Rank {
+    int device = 0;
+    rpb200_ctx* c = nullptr;
+    rpb200_halo_plan* plan = nullptr;
+    std::vector<Real_ptr> vars;
+  };
+  std::vector<Rank> m_ranks;
+  std::vector<rpb200_ctx*> m_dev_ctx;     // one context per device used
+  int m_first_device = 0, m_num_devices = 1;
+};
+
+}  // namespace comm
+}  // namespace rajaperf

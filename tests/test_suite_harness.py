@@ -1,0 +1,120 @@
+"""The C++ suite harness (rajaperf_b200/suite/raja-perf-b200.exe): the reference's driver flags and
+KernelBase life cycle with the Base_B200 variant.  The GPU tests read like the reference's own test
+(test/test-raja-perf-suite.cpp): run the executable in check mode and compare each kernel's checksum
+with Base_Seq -- here the Base_Seq value is the golden checksum printed by the reference binary."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "rajaperf_b200", "suite", "raja-perf-b200.exe")
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_checksums.json")))["cases"]
+
+# parity class per kernel: bit-exact => the 20 printed digits agree to the last place or two
+# of a long double; tolerance class => the suite's own 1e-7 absolute bound (test-raja-perf-suite.cpp:167)
+EXACT = {"Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Algorithm_SORT", "Algorithm_SORTPAIRS",
+         "Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA", "Comm_HALO_PACKING_FUSED"}
+
+
+def run_exe(args, outdir=None, check=True):
+    cmd = [EXE] + args + (["--outdir", str(outdir)] if outdir else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    if check:
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r
+
+
+def read_checksum(outdir, variant="Base_B200"):
+    txt = open(os.path.join(outdir, "RAJAPerf-checksum.txt")).read()
+    m = re.search(rf"^{variant}-\S+\s+(\S+)\s+(\S+)", txt, re.M)
+    assert m, txt
+    return np.longdouble(m.group(1))
+
+
+def test_exe_is_built():
+    assert os.path.exists(EXE), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+
+
+def test_help_print_kernels_and_variants():
+    out = run_exe(["--help"]).stdout
+    for opt in ("--kernels", "--variants", "--size", "--npasses", "--checkrun", "--mpi_3d_division", "--halo_width"):
+        assert opt in out
+    out = run_exe(["-pk"]).stdout
+    for k in ("Stream_TRIAD", "Algorithm_SORTPAIRS", "Apps_LTIMES", "Comm_HALO_EXCHANGE_FUSED"):
+        assert k in out
+    assert "Base_B200" in run_exe(["-pv"]).stdout
+
+
+def test_dryrun_reports_sizes_reps_bytes_like_the_reference():
+    out = run_exe(["--dryrun", "-k", "Stream", "Algorithm_SCAN", "MASS3DPA", "--size", "1000000"]).stdout
+    rows = {l.split()[0]: l.split()[1:] for l in out.splitlines() if re.match(r"^(Stream|Algorithm|Apps)_", l)}
+    # name -> (problem size, reps, its/rep, kernels/rep, bytes/rep, flops/rep): kernels.csv of the reference
+    assert rows["Stream_TRIAD"] == ["1000000", "1000", "1000000", "1", "24000000", "2000000"]
+    assert rows["Stream_COPY"][1] == "1800" and rows["Stream_DOT"][1] == "2000"
+    assert rows["Algorithm_SCAN"] == ["1000000", "100", "1000000", "1", "16000000", "1000000"]
+    assert rows["Apps_MASS3DPA"][0] == "1000000" and int(rows["Apps_MASS3DPA"][4]) == 8000 * 2536 + 320
+    assert int(rows["Apps_MASS3DPA"][5]) == 8000 * 5069
+
+
+def test_bad_input_is_reported_and_nothing_runs():
+    r = run_exe(["-k", "NOT_A_KERNEL"], check=False)
+    assert r.returncode == 1 and "Invalid kernel input" in r.stdout and "will not be run" in r.stdout
+    r = run_exe(["--size", "100", "--sizefact", "2"], check=False)
+    assert r.returncode == 1 and "only set one of" in r.stdout
+    r = run_exe(["-v", "Base_Seq", "--dryrun"], check=True)
+    assert "not available in this build" in r.stdout
+
+
+def _flags(case):
+    return list(case["flags"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD, ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}")
+def test_checkrun_checksum_matches_reference_base_seq(case, tmp_path):
+    args = ["--checkrun", str(case["reps"]), "--disable-warmup", "-k", case["kernel"], "-v", "Base_B200"]
+    if case["size"]:
+        args += ["--size", str(case["size"])]
+    run_exe(args + _flags(case), tmp_path)
+    got, ref = read_checksum(tmp_path), np.longdouble(case["checksum"])
+    if case["kernel"] in EXACT:
+        assert abs(got - ref) <= abs(ref) * np.longdouble(4e-19), (got, ref)
+    else:
+        assert abs(got - ref) < 1e-7, (got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("division", [(1, 1, 1), (2, 1, 1), (2, 2, 2)])
+def test_halo_exchange_fused_rank_grids_match_oracle(division, tmp_path):
+    """No MPI in the reference build here, so the oracle's P-rank restatement is the checker."""
+    args = ["--checkrun", "2", "--disable-warmup", "-k", "HALO_EXCHANGE_FUSED", "--size", "27000", "--halo_width", "2",
+            "--halo_num_vars", "2", "--mpi_3d_division"] + [str(d) for d in division]
+    run_exe(args, tmp_path)
+    got = read_checksum(tmp_path)
+    ref = oracle.kat("Comm_HALO_EXCHANGE_FUSED", 27000, 2, [2, 2] + list(division))
+    assert abs(got - ref) <= abs(ref) * np.longdouble(1e-18), (got, ref)
+
+
+@pytest.mark.gpu
+def test_npasses_accumulate_checksums_and_graph_mode_agrees(tmp_path):
+    a, b, c = tmp_path / "a", tmp_path / "b", tmp_path / "c"
+    base = ["--checkrun", "3", "--disable-warmup", "-k", "Stream", "SCAN", "LTIMES", "HALO_PACKING_FUSED", "HALO_EXCHANGE_FUSED"]
+    run_exe(base, a)
+    run_exe(base + ["--npasses", "2"], b)
+    run_exe(base + ["--graph"], c)
+    ta, tb, tc = (open(os.path.join(d, "RAJAPerf-checksum.txt")).read() for d in (a, b, c))
+    cka = [np.longdouble(x) for x in re.findall(r"^Base_B200-default\s+(\S+)", ta, re.M)]
+    ckb = [np.longdouble(x) for x in re.findall(r"^Base_B200-default\s+(\S+)", tb, re.M)]
+    ckc = [np.longdouble(x) for x in re.findall(r"^Base_B200-default\s+(\S+)", tc, re.M)]
+    assert len(cka) == 9 and len(ckb) == 9 and len(ckc) == 9
+    for x, y, z in zip(cka, ckb, ckc):
+        assert abs(2 * x - y) <= abs(y) * np.longdouble(1e-15)      # checksum += per pass (KernelBase.hpp:528)
+        assert abs(x - z) <= abs(x) * np.longdouble(1e-15)           # same kernels, one graph launch
+    for f in ("RAJAPerf-timing-Minimum.csv", "RAJAPerf-timing-Average.csv", "RAJAPerf-kernels.csv", "RAJAPerf-bandwidth.csv"):
+        assert os.path.getsize(os.path.join(a, f)) > 0
