@@ -108,7 +108,8 @@ Checksum_type calcChecksumHost(const Real_type* ptr, Index_type len, Real_type s
 {
   Checksum_type tchk = 0.0, ckahan = 0.0;
   for (Index_type j = 0; j < len; ++j) {
-    const Checksum_type x = (std::abs(std::sin(Real_type(j + 1.0))) + 0.5) * ptr[j];
+    // the weight is formed in double, the product in long double (DataUtils.cpp:606, :631)
+    const Checksum_type x = (std::abs(std::sin(j + 1.0)) + 0.5) * static_cast<Checksum_type>(ptr[j]);
     const Checksum_type y = x - ckahan;
     volatile Checksum_type t = tchk + y;
     volatile Checksum_type z = t - tchk;

@@ -134,11 +134,12 @@ void KernelBase::runRepLoop()
   const Index_type run_reps = getRunReps();
   if (run_params.useGraph() && m_graph_ok && run_reps > 0) {
     // "capture launch-bound inner loops in CUDA graphs": the whole rep batch becomes one launch
+    (void)ctx();                      // the context (and its scratch) must exist before capture starts
     cudaStream_t cap;
     cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
     cudaGraph_t graph;
     cudaGraphExec_t exec;
-    cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
     for (RepIndex_type irep = 0; irep < run_reps; ++irep) enqueueRep(cap);
     if (cudaStreamEndCapture(cap, &graph) != cudaSuccess || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
       std::fprintf(stderr, "\n%s: CUDA graph capture failed\n", getName().c_str());
