@@ -102,6 +102,31 @@ __device__ __forceinline__ double warp_sum(double v)
   return v;
 }
 
+// ---------------------------------------------------------------------------------
+// mbarrier + bulk-async (TMA) copies: the staging path that does not go through the LSU
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{ asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned int bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity)
+{
+  unsigned int ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared (16-byte aligned, size a multiple of 16); completes tx bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned int bytes, unsigned long long* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 static inline bool rpb_aligned(const void* p, size_t a) { return (((uintptr_t)p) & (a - 1)) == 0; }
 
 static inline cudaStream_t rpb_stream(rpb200_stream_t s) { return (cudaStream_t)s; }

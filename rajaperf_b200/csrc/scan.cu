@@ -148,6 +148,9 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
 
 }  // namespace
 
+int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, void* d_desc, size_t desc_bytes,
+                     unsigned int* d_ticket, unsigned long long epoch, cudaStream_t st, int* handled);   // scan_tma.cu
+
 static int scan_grow_state(rpb200_ctx* ctx, size_t need, cudaStream_t st)
 {
   if (need <= ctx->scan_state_bytes) return 0;
@@ -190,6 +193,14 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   const size_t need = sizeof(tile_desc) * (size_t)tiles;
   { const int rc = scan_grow_state(ctx, need, st); if (rc != 0) return rc; }
   const unsigned long long epoch = ++ctx->scan_epoch;
+
+  // large, aligned problems: the TMA-staged warp-specialised kernel (separate ticket pair: [2], [3])
+  {
+    int handled = 0;
+    const int rc = rpb_scan_tma_try(ctx, x, y, n, ctx->d_scan_state, ctx->scan_state_bytes, ctx->d_scan_ticket + 2, epoch, st, &handled);
+    if (rc != 0) return rc;
+    if (handled) return 0;
+  }
 
   int grid = ctx->sm_count * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 4);
   if ((unsigned int)grid > tiles) grid = (int)tiles;
