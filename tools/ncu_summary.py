@@ -37,6 +37,15 @@ open(sys.argv[2], "w").write("\n".join(out) + "\n")
 if len(sys.argv) > 3:
     m = {"stream_ew_kernel<0, 2>": "Stream_COPY", "stream_ew_kernel<1, 2>": "Stream_MUL", "stream_ew_kernel<2, 2>": "Stream_ADD",
          "stream_ew_kernel<3, 2>": "Stream_TRIAD", "reduce_kernel<2, 2>": "Stream_DOT", "reduce_kernel<1, 8>": "Algorithm_REDUCE_SUM",
-         "scan_kernel<4>": "Algorithm_SCAN"}
+         "scan_kernel<4>": "Algorithm_SCAN", "scan_tma_kernel<1, 0>": "Algorithm_SCAN"}
+    m.update({k: "Apps_MASS3DPA" for k in traffic if k.startswith("mass3dpa_kernel")})
+    m.update({k: "Apps_DIFFUSION3DPA" for k in traffic if k.startswith("diffusion3dpa_kernel")})
+    m.update({k: "Apps_CONVECTION3DPA" for k in traffic if k.startswith("convection3dpa_kernel")})
+    m.update({k: "Apps_LTIMES" for k in traffic if k.startswith("ltimes_dmma")})
     js = {m[k]: {"dram_bytes_per_launch": v[0], "kernel": k} for k, v in traffic.items() if k in m}
-    json.dump(js, open(sys.argv[3], "w"), indent=1)
+    try:                      # merge into an existing file: later captures refresh single kernels
+        old = json.load(open(sys.argv[3]))
+    except Exception:
+        old = {}
+    old.update(js)
+    json.dump(old, open(sys.argv[3], "w"), indent=1)
