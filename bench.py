@@ -194,11 +194,50 @@ def cpu_stream_group(n, steps, warmup, host_arrays=None):
     return gbs, dt / steps * 1e3, threads, "port", sample
 
 
+REF_EXE = os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe")
+
+
+def cpu_stream_group_reference(n, steps, npasses=2):
+    """The UNMODIFIED reference binary (oracle/_ref/raja-perf.exe, built CPU-only from /root/reference by
+    oracle/build_ref.sh in the authoring container; it travels to the GPU box with the snapshot): its own
+    Base_OpenMP Stream kernels, its own timers, all host threads.  Returns None if the binary is absent or fails."""
+    import shutil
+    import tempfile
+    if not os.path.exists(REF_EXE):
+        return None
+    threads = os.cpu_count() or 1
+    out = tempfile.mkdtemp(prefix="rpb_ref_")
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="cores")
+    cmd = [REF_EXE, "--checkrun", str(steps), "-k", "Stream", "-v", "Base_OpenMP", "--size", str(n), "--npasses", str(npasses),
+           "--outdir", out]
+    try:
+        t0 = time.perf_counter()
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, timeout=900)
+        wall = time.perf_counter() - t0
+        secs = {}
+        for line in open(os.path.join(out, "RAJAPerf-timing-Average.csv")):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 2 and f[0] in STREAM_BYTES_PER_ELEM:
+                secs[f[0]] = float(f[1])
+        if set(secs) != set(STREAM_BYTES_PER_ELEM):
+            return None
+    except Exception:
+        return None
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+    dt = sum(secs.values())                      # seconds for `steps` reps of each of the five kernels
+    gbs = STEP_BYTES_PER_ELEM * n * steps / dt / 1e9
+    sample = (f"reference raja-perf.exe -k Stream -v Base_OpenMP --size {n} --checkrun {steps} --npasses {npasses} (mean over "
+              f"passes, the suite's own timers; {dt:.1f} s inside the timers, {wall:.0f} s wall with setUp)")
+    return gbs, dt / steps * 1e3, threads, "reference", sample
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
     n = STREAM_N
-    gbs, ms, threads, kind, sample = cpu_stream_group(n, args.steps, max(args.warmup, 1))
+    ref = cpu_stream_group_reference(n, max(1, min(args.steps, 10)))
+    gbs, ms, threads, kind, sample = ref if ref else cpu_stream_group(n, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -321,7 +360,8 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         n_cpu = STREAM_N
-        gbs, ms, threads, kind, sample = cpu_stream_group(n_cpu, 3, 1)
+        ref = cpu_stream_group_reference(n_cpu, 3, npasses=1)
+        gbs, ms, threads, kind, sample = ref if ref else cpu_stream_group(n_cpu, 3, 1)
         cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "ms_per_step": ms}
 
     if rank == 0:
@@ -423,6 +463,24 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
     ms = time_events(torch, lambda: ctx.sort_pairs(yv, vals, scratch), 5, 2, setup=lambda: (yv.copy_(x), vals.copy_(x)))
     rec("Algorithm_SORTPAIRS", n, 32 * n, ms, mkeys_per_s=n / ms / 1e3, note="32 B/pair is the suite's nominal count")
     del x, yv, vals, scratch
+    torch.cuda.empty_cache()
+
+    # ---- widened rows: INDEXLIST at the Algorithm-group size, GEMM at 4096 x 4096 x 4915 -------
+    x = init_real_dev(torch, n, 0.2, dev) * (torch.randint(0, 2, (n,), device=dev, dtype=torch.float64) * 2 - 1)   # random sign
+    lst = torch.empty(n, dtype=torch.int32, device=dev)
+    ln = torch.zeros(1, dtype=torch.int64, device=dev)
+    ms = time_events(torch, lambda: ctx.indexlist(x, lst, ln), 20, 3)
+    sel = int(ln.item())
+    rec("Basic_INDEXLIST", n, 8 * n + 4 * sel + 16, ms, selected=sel,
+        note="bytes = x read + selected indices written (the suite's nominal count assumes exactly 50 % output)")
+    del x, lst
+    gn = int((16 * 1024 * 1024) ** 0.5 + 2 ** 0.5 - 1)            # --size 16777216 -> ni = nj = 4096, nk = 4915
+    gk = int(1200 / 1000 * gn)
+    A = init_real_dev(torch, gn * gk, 0.2, dev); Bm = init_real_dev(torch, gk * gn, 0.1, dev); C = torch.zeros(gn * gn, **f64)
+    ms = time_events(torch, lambda: ctx.polybench_gemm(A, Bm, C, gn, gn, gk, 0.62, 1.002), 10, 3)
+    rec("Polybench_GEMM", gn * gn, 8 * (2 * gn * gk + gn * gn), ms, dims=[gn, gn, gk], tflops=2.0 * gn * gn * gk / ms / 1e9,
+        bound="fp64 pipe", note="compute-bound: judge by TFLOP/s (2 flop per multiply-add) against the FP64 peak, not GB/s")
+    del A, Bm, C
     torch.cuda.empty_cache()
 
     one = lambda m: torch.ones(m, **f64)

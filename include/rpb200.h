@@ -99,6 +99,24 @@ int rpb200_convection3dpa(rpb200_ctx*, const double* Basis, const double* tBasis
 int rpb200_ltimes(rpb200_ctx*, double* phi, const double* ell, const double* psi,
                   int64_t num_d, int64_t num_g, int64_t num_m, int64_t num_z, rpb200_stream_t);
 
+/* ---- widened rows -----------------------------------------------------
+ * basic/INDEXLIST-Cuda.cpp:33-265 and basic/INDEXLIST_3LOOP-Cuda.cpp:60-128: both define
+ *   list[0..len) = ascending { i in [0,n) : x[i] < 0.0 },  *d_len = len   (INDEXLIST.hpp:17-25,
+ * INDEXLIST_3LOOP.hpp:17-24); one single-pass compaction serves both, without the 3LOOP
+ * `counts` temporary.  list: Int_type (int), d_len: device Index_type (int64).  Entries of
+ * list at and beyond len are left untouched (the reference checksums them too).       */
+int rpb200_indexlist(rpb200_ctx*, const double* x, int* list, int64_t n, int64_t* d_len,
+                     rpb200_stream_t);
+/* Optional: grow the look-back state for n elements now (synchronises); required before
+ * capturing rpb200_indexlist into a CUDA graph.                                        */
+int rpb200_indexlist_reserve(rpb200_ctx*, int64_t n);
+/* polybench/POLYBENCH_GEMM-Cuda.cpp:44-85: C[i][j] = sum_k alpha * A[i][k] * B[k][j], row-major
+ * A (ni x nk), B (nk x nj), C (ni x nj).  `beta` is dead in the reference body
+ * (POLYBENCH_GEMM.hpp:32-39: "C *= beta" is overwritten by "C = dot") and is ignored here too. */
+int rpb200_polybench_gemm(rpb200_ctx*, const double* A, const double* B, double* C,
+                          int64_t ni, int64_t nj, int64_t nk, double alpha, double beta,
+                          rpb200_stream_t);
+
 /* ---- Comm group ------------------------------------------------------------------
  * comm/HALO_PACKING_FUSED-Cuda.cpp:52-197, HALO_EXCHANGE_FUSED-Cuda.cpp:52-206.
  *

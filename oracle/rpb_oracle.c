@@ -963,9 +963,111 @@ long double orc_kat_halo_exchange_fused(int64_t target, int reps, int hw, int nv
 void orc_checksum_out(const double* p, int64_t n, double scale, long double* out)
 { *out = orc_checksum(p, n, scale); }
 
+/* ======================================================================== */
+/* Widened rows: Basic_INDEXLIST(_3LOOP), Polybench_GEMM         */
+/* ======================================================================== */
+
+/* DataUtils.cpp:623-629: the Int_ptr overload of calcChecksum (same Kahan loop) */
+long double orc_checksum_int(const int* p, int64_t n, double scale)
+{
+  long double sum = 0.0L, comp = 0.0L;
+  for (int64_t j = 0; j < n; ++j) {
+    const double w = fabs(sin(j + 1.0)) + 0.5;
+    const long double x = (long double)w * (long double)p[j];
+    const long double y = x - comp;
+    volatile long double t = sum + y;
+    volatile long double z = t - sum;
+    comp = z - y;
+    sum = t;
+  }
+  sum *= scale;
+  return sum;
+}
+
+/* basic/INDEXLIST.hpp:17-25 + INDEXLIST-Seq.cpp:40-52: returns count (m_len) */
+int64_t orc_indexlist(const double* x, int* list, int64_t n)
+{
+  int64_t count = 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (x[i] < 0.0) list[count++] = (int)i;
+  return count;
+}
+
+/* basic/INDEXLIST_3LOOP.hpp:17-24 + INDEXLIST_3LOOP-Seq.cpp:43-65: flags, exclusive scan of
+ * n+1 counts, list[counts[i]] = i where counts[i] != counts[i+1]; returns counts[n]          */
+int64_t orc_indexlist_3loop(const double* x, int* list, int64_t n)
+{
+  int64_t* counts = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+  for (int64_t i = 0; i < n; ++i) counts[i] = (x[i] < 0.0) ? 1 : 0;
+  counts[n] = 0;                       /* the reference scans the uninitialised tail entry; its value is unused */
+  int64_t count = 0;
+  for (int64_t i = 0; i < n + 1; ++i) { const int64_t inc = counts[i]; counts[i] = count; count += inc; }
+  for (int64_t i = 0; i < n; ++i)
+    if (counts[i] != counts[i + 1]) list[counts[i]] = (int)i;
+  const int64_t len = counts[n];
+  free(counts);
+  return len;
+}
+
+/* polybench/POLYBENCH_GEMM.hpp:29-39 + POLYBENCH_GEMM-Seq.cpp:37-47 (k innermost, no FMA on x86-64) */
+void orc_polybench_gemm(const double* A, const double* B, double* C, int64_t ni, int64_t nj, int64_t nk,
+                        double alpha, double beta)
+{
+  for (int64_t i = 0; i < ni; ++i)
+    for (int64_t j = 0; j < nj; ++j) {
+      double dot = 0.0;
+      C[j + i * nj] *= beta;
+      for (int64_t k = 0; k < nk; ++k) dot += alpha * A[k + i * nk] * B[j + k * nj];
+      C[j + i * nj] = dot;
+    }
+}
+
+/* POLYBENCH_GEMM.cpp:24-35: ni = nj = sqrt(target) + sqrt(2) - 1 (truncated), nk = 1.2 * ni (truncated) */
+void orc_polybench_gemm_dims(int64_t target, int64_t* ni, int64_t* nj, int64_t* nk)
+{
+  if (target <= 0) target = 1000 * 1000;
+  *ni = (int64_t)(sqrt((double)target) + sqrt(2.0) - 1);
+  *nj = *ni;
+  *nk = (int64_t)((double)1200 / 1000 * (double)*ni);
+}
+
+static long double kat_indexlist(int64_t target, int reps, int three_loop)   /* basic/INDEXLIST.cpp:21-79 */
+{
+  const int64_t n = tsize(target, 1000000);
+  double* x = dalloc(n);
+  int* list = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  orc_reset_init_count();
+  orc_init_rand_sign(x, n); orc_init_int(list, n);
+  int64_t len = -1;
+  for (int r = 0; r < reps; ++r) len = three_loop ? orc_indexlist_3loop(x, list, n) : orc_indexlist(x, list, n);
+  long double ck = orc_checksum_int(list, n, 1.0);
+  ck += (long double)len;
+  free(x); free(list); return ck;
+}
+long double orc_kat_indexlist(int64_t target, int reps) { return kat_indexlist(target, reps, 0); }
+long double orc_kat_indexlist_3loop(int64_t target, int reps) { return kat_indexlist(target, reps, 1); }
+
+long double orc_kat_polybench_gemm(int64_t target, int reps)    /* polybench/POLYBENCH_GEMM.cpp:21-104 */
+{
+  int64_t ni, nj, nk;
+  orc_polybench_gemm_dims(target, &ni, &nj, &nk);
+  double *A = dalloc(ni * nk), *B = dalloc(nk * nj), *C = dalloc(ni * nj);
+  orc_reset_init_count();
+  orc_init_real(A, ni * nk); orc_init_real(B, nk * nj); orc_init_const(C, ni * nj, 0.0);
+  for (int r = 0; r < reps; ++r) orc_polybench_gemm(A, B, C, ni, nj, nk, 0.62, 1.002);
+  const double scale = (double)(0.001 * ((long double)(1000 * 1000) / (ni * nj)));
+  long double ck = orc_checksum(C, ni * nj, scale);
+  free(A); free(B); free(C); return ck;
+}
+
+
+
 /* ip: ltimes {num_d,num_g,num_m}; halo_packing_fused {halo_width,num_vars};
  * halo_exchange_fused {halo_width,num_vars,px,py,pz}.  Returns 0, or -1 for an
  * unknown kernel name.                                                         */
+void orc_checksum_int_out(const int* p, int64_t n, double scale, long double* out)
+{ *out = orc_checksum_int(p, n, scale); }
+
 int orc_kat(const char* name, int64_t target, int reps, const int* ip, long double* out)
 {
   if      (!strcmp(name, "Stream_COPY"))          *out = orc_kat_stream_copy(target, reps);
@@ -984,6 +1086,11 @@ int orc_kat(const char* name, int64_t target, int reps, const int* ip, long doub
     *out = orc_kat_ltimes(target, reps, ip ? ip[0] : 64, ip ? ip[1] : 32, ip ? ip[2] : 25);
   else if (!strcmp(name, "Comm_HALO_PACKING_FUSED"))
     *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
+  else if (!strcmp(name, "Comm_HALO_PACKING"))    /* same setUp, same result as the fused kernel (HALO_PACKING.cpp:62-110) */
+    *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
+  else if (!strcmp(name, "Basic_INDEXLIST"))       *out = orc_kat_indexlist(target, reps);
+  else if (!strcmp(name, "Basic_INDEXLIST_3LOOP")) *out = orc_kat_indexlist_3loop(target, reps);
+  else if (!strcmp(name, "Polybench_GEMM"))        *out = orc_kat_polybench_gemm(target, reps);
   else if (!strcmp(name, "Comm_HALO_EXCHANGE_FUSED")) {
     const int one[3] = {1, 1, 1};
     *out = orc_kat_halo_exchange_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3,

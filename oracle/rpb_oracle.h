@@ -74,6 +74,16 @@ void    orc_halo_neighbors(int rank, const int pdims[3], int ranks[ORC_HALO_NEIG
 void    orc_halo_pack(double* buffer, const int* list, const double* var, int64_t len);
 void    orc_halo_unpack(double* var, const int* list, const double* buffer, int64_t len);
 
+/* ---- widened rows ----------------------------------------------- */
+long double orc_checksum_int(const int* p, int64_t n, double scale);             /* DataUtils.cpp:623-629 */
+int64_t orc_indexlist(const double* x, int* list, int64_t n);                     /* basic/INDEXLIST-Seq.cpp:40-52 */
+int64_t orc_indexlist_3loop(const double* x, int* list, int64_t n);               /* basic/INDEXLIST_3LOOP-Seq.cpp:43-65 */
+void    orc_polybench_gemm(const double* A, const double* B, double* C, int64_t ni, int64_t nj, int64_t nk,
+                           double alpha, double beta);                            /* polybench/POLYBENCH_GEMM-Seq.cpp:37-47 */
+void    orc_polybench_gemm_dims(int64_t target, int64_t* ni, int64_t* nj, int64_t* nk);  /* POLYBENCH_GEMM.cpp:24-35 */
+long double orc_kat_indexlist(int64_t target_size, int reps);
+long double orc_kat_indexlist_3loop(int64_t target_size, int reps);
+long double orc_kat_polybench_gemm(int64_t target_size, int reps);
 /* ---- whole-kernel known-answer drivers: setUp -> reps -> checksum ---------- */
 /* target_size = --size value (<=0: default size); reps = --checkrun N.        */
 long double orc_kat_stream_copy(int64_t target_size, int reps);
@@ -98,6 +108,7 @@ long double orc_kat_halo_exchange_fused(int64_t target_size, int reps, int halo_
                                         long double* per_rank);
 
 /* pointer-out forms for ctypes (a returned long double is narrowed to double) */
+void orc_checksum_int_out(const int* p, int64_t n, double scale, long double* out);
 void orc_checksum_out(const double* p, int64_t n, double scale, long double* out);
 int  orc_kat(const char* kernel_full_name, int64_t target_size, int reps,
              const int* iparams, long double* out);

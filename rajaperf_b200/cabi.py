@@ -52,6 +52,9 @@ SIGNATURES = {
     "rpb200_diffusion3dpa": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "rpb200_convection3dpa": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "rpb200_ltimes": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P]),
+    "rpb200_indexlist": (c_int, [_P, _P, _P, c_int64, _P, _P]),
+    "rpb200_indexlist_reserve": (c_int, [_P, c_int64]),
+    "rpb200_polybench_gemm": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_double, _P]),
     "rpb200_halo_chunk": (c_int, []),
     "rpb200_halo_worklist_create": (c_int, [_P, _P, c_int, POINTER(_P)]),
     "rpb200_halo_worklist_update": (c_int, [_P, _P, c_int, _P]),
@@ -228,6 +231,16 @@ class Context:
     def ltimes(self, phi, ell, psi, num_d, num_g, num_m, num_z):
         check(self.lib.rpb200_ltimes(self.h, _ptr(phi), _ptr(ell), _ptr(psi), num_d, num_g, num_m,
                                      num_z, _stream()), "ltimes")
+
+    # ---- widened rows -----------------------------------------------------
+    def indexlist(self, x, list_, d_len, n=None):
+        """list_: int32 tensor (>= n entries), d_len: int64 tensor of 1 element (device)."""
+        n = x.numel() if n is None else n
+        check(self.lib.rpb200_indexlist(self.h, _ptr(x), _ptr(list_), n, _ptr(d_len), _stream()), "indexlist")
+
+    def polybench_gemm(self, A, B, C, ni, nj, nk, alpha, beta=0.0):
+        check(self.lib.rpb200_polybench_gemm(self.h, _ptr(A), _ptr(B), _ptr(C), ni, nj, nk, alpha, beta,
+                                             _stream()), "polybench_gemm")
 
     # ---- Comm ----------------------------------------------------------------------------
     def halo_chunk(self) -> int:

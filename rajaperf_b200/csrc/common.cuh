@@ -31,6 +31,7 @@ enum rpb_kernel_id {
   RPB_K_REDUCE_SUM, RPB_K_SCAN, RPB_K_SORT, RPB_K_SORTPAIRS,
   RPB_K_MASS3DPA, RPB_K_DIFFUSION3DPA, RPB_K_CONVECTION3DPA, RPB_K_LTIMES,
   RPB_K_HALO_PACKING_FUSED, RPB_K_HALO_EXCHANGE_FUSED,
+  RPB_K_INDEXLIST, RPB_K_POLYBENCH_GEMM,
   RPB_K_COUNT
 };
 
@@ -48,6 +49,10 @@ struct rpb200_ctx {
   unsigned int* d_scan_ticket;   // dynamic tile counter, reset by the last tile
   // diffusion: effective basis tables (48 doubles) built per call by a 1-CTA prologue
   double*       d_basis_tables;
+  // indexlist: 8-byte look-back descriptors, epoch-tagged like the scan's
+  void*         d_ilist_state;
+  size_t        ilist_state_bytes;
+  unsigned int  ilist_epoch;
 };
 
 #define RPB_MAX_PARTIALS 8192

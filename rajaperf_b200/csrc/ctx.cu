@@ -8,7 +8,8 @@ static const char* const k_kernel_names[RPB_K_COUNT] = {
   "Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT",
   "Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS",
   "Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA", "Apps_LTIMES",
-  "Comm_HALO_PACKING_FUSED", "Comm_HALO_EXCHANGE_FUSED"
+  "Comm_HALO_PACKING_FUSED", "Comm_HALO_EXCHANGE_FUSED",
+  "Basic_INDEXLIST", "Polybench_GEMM"
 };
 
 // Built-in defaults; see profiles/ for the sweeps that picked them.
@@ -25,6 +26,11 @@ static void default_tunings(rpb200_ctx* c)
   c->tune[RPB_K_MASS3DPA]       = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_DIFFUSION3DPA]  = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_CONVECTION3DPA] = rpb_tuning{128, 0, 1};
+  c->tune[RPB_K_INDEXLIST]      = rpb_tuning{512, 4, 4};
+  // halo kernels: block_size 128 = chunks dealt round-robin, unroll 1 = no L2 eviction hints
+  // (profiles/r01_halo_variants.md: 112 -> 101 us pack+unpack, 119 -> 113 us exchange at 512^3)
+  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{128, 8, 1};
+  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{128, 8, 1};
 }
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }
@@ -72,6 +78,7 @@ extern "C" void rpb200_destroy(rpb200_ctx* c)
   cudaFree(c->d_scan_ticket);
   cudaFree(c->d_scan_state);
   cudaFree(c->d_basis_tables);
+  cudaFree(c->d_ilist_state);
   free(c);
 }
 

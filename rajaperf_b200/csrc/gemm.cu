@@ -1,0 +1,189 @@
+// gemm.cu -- Polybench_GEMM: C = alpha * A * B in FP64 on the tensor path (DMMA) for sm_100a.
+//
+// Replaces polybench/POLYBENCH_GEMM-Cuda.cpp:44-85 (one thread per C entry, a k loop of scalar
+// DFMAs reading A and B straight from global memory: 16 B of L1/L2 traffic per FMA).
+// The reference body (POLYBENCH_GEMM.hpp:29-39) is
+//     dot = 0; C[i][j] *= beta; for k: dot += alpha * A[i][k] * B[k][j]; C[i][j] = dot;
+// i.e. the beta scaling is overwritten and the result is alpha * (A B): `beta` is accepted for
+// interface fidelity and has no effect, exactly as in the reference.
+// This is the one genuinely dense FP64 contraction on the path (north_star), so it runs on
+// mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind):
+//   * CTA tile BM x BN x GK (GK = 16 or 32), 3-stage cp.async ring (zero-filled at the ragged edges), A kept
+//     [m][k] and B [k][n] exactly as they lie in global memory (no transposes);
+//   * padded leading dimensions (GK+4 and BN+4 doubles) make every fragment load -- one LDS.64 per
+//     lane per 8x4 / 4x8 fragment -- bank-conflict-free;
+//   * each warp owns a WM x WN block of C: (WM/8)(WN/8) DMMAs per (WM/8 + WN/8) fragment loads;
+//   * alpha is applied once in the epilogue (alpha * sum instead of sum of alpha * a * b: the same
+//     value to ~1 ulp, inside the suite's checksum tolerance, test/test-raja-perf-suite.cpp:167).
+#include "common.cuh"
+
+namespace {
+
+constexpr int GSTAGES = 3;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gsrc, int src_bytes)
+{
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// VEC = doubles per cp.async (2 when every row start is 16-byte aligned, else 1)
+template <int BM, int BN, int WM, int WN, int GK, int VEC>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+gemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
+                 int ni, int nj, int nk, double alpha)
+{
+  constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
+  constexpr int LDA = GK + 4, LDB = BN + 4;      // doubles; both = 4 mod 16: conflict-free fragment loads
+  constexpr int MF = WM / 8, NF = WN / 8;
+  constexpr int A_STAGE = BM * LDA, B_STAGE = GK * LDB;
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + GSTAGES * A_STAGE;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm0 = (warp / (BN / WN)) * WM, wn0 = (warp % (BN / WN)) * WN;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const int ktiles = (nk + GK - 1) / GK;
+
+  auto load_stage = [&](int kt, int stage) {
+    const int k0 = kt * GK;
+    double* a_s = sA + stage * A_STAGE;
+    double* b_s = sB + stage * B_STAGE;
+    constexpr int A_CH = BM * (GK / VEC);       // copies per A tile: row r, k chunk c
+    for (int q = threadIdx.x; q < A_CH; q += THREADS) {
+      const int r = q / (GK / VEC), c = (q % (GK / VEC)) * VEC;
+      const int gi = i0 + r, gk = k0 + c;
+      int nb = 0;
+      if (gi < ni && gk < nk) nb = (nk - gk >= VEC ? VEC : nk - gk) * 8;
+      const double* src = nb ? A + (int64_t)gi * nk + gk : A;
+      cp_async_zfill<VEC * 8>(a_s + r * LDA + c, src, nb);
+    }
+    constexpr int B_CH = GK * (BN / VEC);       // row k, column chunk c
+    for (int q = threadIdx.x; q < B_CH; q += THREADS) {
+      const int r = q / (BN / VEC), c = (q % (BN / VEC)) * VEC;
+      const int gk = k0 + r, gj = j0 + c;
+      int nb = 0;
+      if (gk < nk && gj < nj) nb = (nj - gj >= VEC ? VEC : nj - gj) * 8;
+      const double* src = nb ? B + (int64_t)gk * nj + gj : B;
+      cp_async_zfill<VEC * 8>(b_s + r * LDB + c, src, nb);
+    }
+  };
+
+  double acc[MF][NF][2];
+#pragma unroll
+  for (int m = 0; m < MF; ++m)
+#pragma unroll
+    for (int n = 0; n < NF; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < ktiles) load_stage(s, s);
+    cp_async_commit();
+  }
+
+  const int fr = lane >> 2, fk = lane & 3;       // fragment row (A) / column (B), and k
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();                              // tile kt has landed; tile kt-1's buffer is free
+    {
+      const int nxt = kt + GSTAGES - 1;
+      if (nxt < ktiles) load_stage(nxt, nxt % GSTAGES);
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % GSTAGES) * A_STAGE + (wm0 + fr) * LDA + fk;
+    const double* b_s = sB + (kt % GSTAGES) * B_STAGE + fk * LDB + wn0 + fr;
+#pragma unroll
+    for (int kk = 0; kk < GK / 4; ++kk) {
+      double a[MF], b[NF];
+#pragma unroll
+      for (int m = 0; m < MF; ++m) a[m] = a_s[m * 8 * LDA + kk * 4];
+#pragma unroll
+      for (int n = 0; n < NF; ++n) b[n] = b_s[kk * 4 * LDB + n * 8];
+#pragma unroll
+      for (int m = 0; m < MF; ++m)
+#pragma unroll
+        for (int n = 0; n < NF; ++n) dmma(acc[m][n][0], acc[m][n][1], a[m], b[n]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: C fragment (row lane/4, columns 2*(lane%4) + {0,1})
+  const bool pair_ok = (nj % 2 == 0) && ((reinterpret_cast<unsigned long long>(C) & 15ull) == 0ull);
+#pragma unroll
+  for (int m = 0; m < MF; ++m) {
+    const int gi = i0 + wm0 + m * 8 + fr;
+    if (gi >= ni) continue;
+#pragma unroll
+    for (int n = 0; n < NF; ++n) {
+      const int gj = j0 + wn0 + n * 8 + 2 * fk;
+      double* dst = C + (int64_t)gi * nj + gj;
+      const double c0 = alpha * acc[m][n][0], c1 = alpha * acc[m][n][1];
+      if (pair_ok && gj + 1 < nj) {
+        *reinterpret_cast<double2*>(dst) = make_double2(c0, c1);
+      } else {
+        if (gj < nj) dst[0] = c0;
+        if (gj + 1 < nj) dst[1] = c1;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN, int GK, int VEC>
+int gemm_launch(const double* A, const double* B, double* C, int ni, int nj, int nk, double alpha, cudaStream_t st)
+{
+  constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
+  constexpr size_t smem = sizeof(double) * GSTAGES * (BM * (GK + 4) + GK * (BN + 4));
+  static bool attr_done = false;
+  if (!attr_done) {
+    RPB_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((nj + BN - 1) / BN, (ni + BM - 1) / BM);
+  gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC><<<grid, THREADS, smem, st>>>(A, B, C, ni, nj, nk, alpha);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int rpb200_polybench_gemm(rpb200_ctx* ctx, const double* A, const double* B, double* C,
+                                     int64_t ni, int64_t nj, int64_t nk, double alpha, double beta,
+                                     rpb200_stream_t s)
+{
+  (void)beta;     // dead in the reference body as well (POLYBENCH_GEMM.hpp:32-39)
+  if (!ctx || ni < 0 || nj < 0 || nk < 0) return RPB200_EINVAL;
+  if (ni == 0 || nj == 0) return 0;
+  if (!C || (nk > 0 && (!A || !B))) return RPB200_EINVAL;
+  if (ni > 0x7fffffffll || nj > 0x7fffffffll || nk > 0x7fffffffll) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  const bool vec = (nk % 2 == 0) && (nj % 2 == 0) && rpb_aligned(A, 16) && rpb_aligned(B, 16);
+  // tuning field `block_size` picks the tiling: 64 = 64x64 (4 warps of 32x32), 96 = 128x64 (8 warps of 32x32),
+  // 128 = 128x128 (8 warps of 64x32), 160 = 128x128 (16 warps of 32x32); anything else = automatic
+  const int64_t big_tiles = ((ni + 127) / 128) * ((nj + 127) / 128);
+  int tile = ctx->tune[RPB_K_POLYBENCH_GEMM].block_size;
+  if (tile != 64 && tile != 96 && tile != 128 && tile != 160) tile = (big_tiles >= 2 * (int64_t)ctx->sm_count ? 160 : 64);
+  const int i = (int)ni, j = (int)nj, k = (int)nk;
+  const bool k32 = ctx->tune[RPB_K_POLYBENCH_GEMM].unroll == 8;       // tuning field `unroll`: 8 = 32-deep stages, else 16
+#define RPB_GEMM(BM, BN, WM, WN)                                                                                         \
+  (k32 ? (vec ? gemm_launch<BM, BN, WM, WN, 32, 2>(A, B, C, i, j, k, alpha, st) : gemm_launch<BM, BN, WM, WN, 32, 1>(A, B, C, i, j, k, alpha, st)) \
+       : (vec ? gemm_launch<BM, BN, WM, WN, 16, 2>(A, B, C, i, j, k, alpha, st) : gemm_launch<BM, BN, WM, WN, 16, 1>(A, B, C, i, j, k, alpha, st)))
+  switch (tile) {
+    case 160: return RPB_GEMM(128, 128, 32, 32);
+    case 128: return RPB_GEMM(128, 128, 64, 32);
+    case 96:  return RPB_GEMM(128, 64, 32, 32);
+    default:  return RPB_GEMM(64, 64, 32, 32);
+  }
+#undef RPB_GEMM
+}

@@ -44,6 +44,46 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// L2 eviction priorities.  A face whose cells are strided in the variable (every list with an x
+// offset: stride nx+2h) touches ONE 8-byte cell per 32-byte sector, and the ghost cell the unpack
+// writes shares that sector with the owned cell the pack reads.  Those sectors (2 x (ny+2h)(nz+2h) x
+// 32 B per variable: 51 MB for 3 variables at 512^3) fit the 126 MB L2, so they are kept with
+// evict_last while everything that streams (contiguous faces, buffers, lists) goes evict_first:
+// from the second rep on the strided faces are L2 hits and the partial-sector ghost writes never
+// become DRAM read-modify-writes.
+// (scalar ld/st take the priority as a createpolicy operand: the .L2::evict_* qualifiers are only
+// accepted on 256-bit accesses for sm_100)
+__device__ __forceinline__ unsigned long long policy_keep()
+{
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long policy_once()
+{
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double ld_hint(const double* p, unsigned long long pol)
+{
+  double v;
+  asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_hint(double* p, double v, unsigned long long pol)
+{
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" :: "l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ int ld_hint_i32(const int* p, unsigned long long pol)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
+constexpr int SEG_STRIDED = 1;       // rpb200_halo_seg.flags bit 0 (set by the library)
+
 // per-message signalling state of an exchange (device)
 struct halo_msg {
   unsigned long long* remote_flag;   // pack: flag of the receive slot in the DESTINATION window
@@ -59,7 +99,7 @@ struct halo_msg {
 // lane t handles elements t, t+256, ...: the index loads, the buffer side and -- for every face whose
 // cells are contiguous -- the variable side are all fully coalesced (a thread owning 4 consecutive
 // elements would turn each of its 4 scatter instructions into 32 partial-sector writes).
-template <bool PACK, int MODE>
+template <bool PACK, int MODE, bool HINT, bool STRIDED>
 __global__ void __launch_bounds__(HALO_BLOCK)
 halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* __restrict__ segs_g1,
             const int* __restrict__ chunk_seg, const long long* __restrict__ seg_first_chunk, int total_chunks,
@@ -76,11 +116,13 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   epoch += 1;
   const rpb200_halo_seg* __restrict__ segs = (MODE != 0 && (epoch & 1ull)) ? segs_g1 : segs_g0;
   const int per = (total_chunks + gridDim.x - 1) / gridDim.x;
-  const int c_begin = blockIdx.x * per;
-  const int c_end = min(c_begin + per, total_chunks);
+  const int c_begin = STRIDED ? (int)blockIdx.x : blockIdx.x * per;
+  const int c_end = STRIDED ? total_chunks : min(c_begin + per, total_chunks);
+  const int c_step = STRIDED ? (int)gridDim.x : 1;
   int waited_msg = -1;
+  const unsigned long long pol_keep = HINT ? policy_keep() : 0ull, pol_once = HINT ? policy_once() : 0ull;
 
-  for (int c = c_begin; c < c_end; ++c) {
+  for (int c = c_begin; c < c_end; c += c_step) {
     const int s = __ldg(chunk_seg + c);
     const rpb200_halo_seg seg = segs[s];
     const int64_t i0 = ((int64_t)c - __ldg(seg_first_chunk + s)) * HALO_CHUNK;
@@ -107,22 +149,50 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       const int i = k * HALO_BLOCK + threadIdx.x;
-      idx[k] = (i < cnt) ? __ldg(list + i) : -1;
+      idx[k] = (i < cnt) ? (HINT ? ld_hint_i32(list + i, pol_once) : __ldg(list + i)) : -1;
     }
+    const bool keep = HINT && (seg.flags & SEG_STRIDED);      // uniform over the chunk
     if (PACK) {
+      if (keep) {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_hint(var + idx[k], pol_keep);
+      } else if (HINT) {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_hint(var + idx[k], pol_once);
+      } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
+      }
+      // MODE 1: the buffer is the peer's receive slot, read back by its unpack right away: default policy
+      if (HINT && MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) st_hint(buf + k * HALO_BLOCK + threadIdx.x, v[k], pol_once);
+      } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+      }
     } else {
+      if (HINT && MODE == 0) {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_hint(buf + k * HALO_BLOCK + threadIdx.x, pol_once);
+      } else {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) var[idx[k]] = v[k];
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+      }
+      if (keep) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) st_hint(var + idx[k], v[k], pol_keep);
+      } else if (HINT) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) st_hint(var + idx[k], v[k], pol_once);
+      } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) var[idx[k]] = v[k];
+      }
     }
   }
 
-  if (MODE == 1 && c_begin < c_end) {
+  if (MODE == 1 && c_begin < c_end) {   // (STRIDED: blockIdx.x < total_chunks always holds, the grid is clamped)
     // all stores of this CTA -> barrier -> ONE system fence -> credit every message it touched; whoever
     // completes a message publishes the epoch to the destination's flag (release at system scope)
     __syncthreads();
@@ -132,14 +202,14 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
       while (c < c_end) {
         const int m = segs[__ldg(chunk_seg + c)].msg;
         int run = 1;
-        while (c + run < c_end && segs[__ldg(chunk_seg + c + run)].msg == m) ++run;
+        while (c + run * c_step < c_end && segs[__ldg(chunk_seg + c + run * c_step)].msg == m) ++run;
         const halo_msg hm = msgs[m];
         const unsigned int prev = atomicAdd(msg_done + m, (unsigned int)run);
         if (prev + run == hm.chunks) {
           msg_done[m] = 0u;              // re-armed for the next rep (stream-ordered launches)
           st_release_sys(hm.remote_flag, epoch);
         }
-        c += run;
+        c += run * c_step;
       }
     }
   }
@@ -163,6 +233,7 @@ struct worklist_dev {
   int nsegs = 0;
   int64_t total_chunks = 0;
   std::vector<int64_t> lens;
+  std::vector<int> flags;
 };
 
 int worklist_free(worklist_dev& w)
@@ -173,9 +244,17 @@ int worklist_free(worklist_dev& w)
   return 0;
 }
 
-void classify(rpb200_halo_seg& s)
+// flags bit 0: the segment's cells are strided in the variable (first two list entries not adjacent).
+// Setup-time only (one 8-byte D2H copy per tuple); a performance hint, never a correctness input.
+int classify(rpb200_halo_seg& s)
 {
-  s.flags = 0;     // reserved (alignment classes are not needed: every access is element-wise coalesced)
+  s.flags = 0;
+  if (s.len >= 2) {
+    int two[2];
+    RPB_CHECK(cudaMemcpy(two, s.list, sizeof(two), cudaMemcpyDeviceToHost));
+    if (two[1] - two[0] != 1) s.flags |= SEG_STRIDED;
+  }
+  return 0;
 }
 
 int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
@@ -189,7 +268,8 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   int64_t chunks = 0;
   for (int s = 0; s < nsegs; ++s) {
     if (segs[s].len < 0 || (segs[s].len > 0 && (!segs[s].buffer || !segs[s].list || !segs[s].var))) return RPB200_EINVAL;
-    classify(segs[s]);
+    { const int rc = classify(segs[s]); if (rc != 0) return rc; }
+    w.flags.push_back(segs[s].flags);
     w.lens[s] = segs[s].len;
     first[s] = chunks;
     const int64_t nc = (segs[s].len + HALO_CHUNK - 1) / HALO_CHUNK;
@@ -227,9 +307,19 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
   const int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
   int64_t grid = (int64_t)ctx->sm_count * cps;
   if (grid > w.total_chunks) grid = w.total_chunks;
-  halo_kernel<PACK, MODE><<<(int)grid, HALO_BLOCK, 0, st>>>(
-      w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)w.total_chunks,
-      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error);
+  // tuning field `unroll` of the two halo kernels: 1 = no L2 eviction-priority hints, else hints on;
+  // tuning field `block_size`: 128 = chunks dealt round-robin (c = b, b + grid, ...) instead of in
+  // contiguous ranges, so the slow strided faces are spread over every CTA
+  const bool hint = ctx->tune[kid].unroll != 1, strided = ctx->tune[kid].block_size == 128;
+#define RPB_HALO_LAUNCH(H, S)                                                                                  \
+  halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
+      w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)w.total_chunks,   \
+      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error)
+  if (hint && strided) RPB_HALO_LAUNCH(true, true);
+  else if (hint) RPB_HALO_LAUNCH(true, false);
+  else if (strided) RPB_HALO_LAUNCH(false, true);
+  else RPB_HALO_LAUNCH(false, false);
+#undef RPB_HALO_LAUNCH
   RPB_LAUNCH_CHECK();
   return 0;
 }
@@ -320,7 +410,7 @@ extern "C" int rpb200_halo_worklist_update(rpb200_halo_worklist* wl, const rpb20
   for (int i = 0; i < nsegs; ++i) {
     if (h_segs[i].len != wl->w.lens[i]) return RPB200_EINVAL;    // the chunk map depends on the lengths
     wl->w.h_stage[i] = h_segs[i];
-    classify(wl->w.h_stage[i]);
+    wl->w.h_stage[i].flags = wl->w.flags[i];      // same lengths => same geometry class as at create()
   }
   if (nsegs > 0)
     RPB_CHECK(cudaMemcpyAsync(wl->w.d_segs, wl->w.h_stage, sizeof(rpb200_halo_seg) * nsegs, cudaMemcpyHostToDevice, rpb_stream(s)));

@@ -18,8 +18,8 @@
 // All hand-offs are mbarriers (no block-wide barrier in the steady state).  Traffic stays algorithmic:
 // 8 B read + 8 B written per element.
 #include "common.cuh"
+#include "tma_stream.cuh"
 
-#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -48,12 +48,6 @@ __device__ __forceinline__ void desc_load(const tile_desc* p, unsigned long long
   v = __longlong_as_double(bits);
 }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar)
-{
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-               :: "r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-
 struct scan_smem {
   alignas(1024) double tile[ST_STAGES][ST_TILE];          // 3 x 64 KiB, 128-byte-swizzled rows
   unsigned long long full[ST_STAGES];                     // TMA landed (tx bytes)
@@ -64,18 +58,6 @@ struct scan_smem {
   unsigned int tile_id[ST_STAGES];
   unsigned int arrived[2];                                // compute warps done with A(k): the last one publishes
 };
-
-// one compute thread: its row of 16 doubles out of the swizzled stage
-__device__ __forceinline__ void load_row(double (&v)[ST_IPT], const double* stage, int row)
-{
-  const char* base = reinterpret_cast<const char*>(stage) + row * 128;
-  const int sw = row & 7;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const double2 q = *reinterpret_cast<const double2*>(base + ((c ^ sw) << 4));
-    v[2 * c] = q.x; v[2 * c + 1] = q.y;
-  }
-}
 
 template <int LB, int BACKOFF>
 __global__ void __launch_bounds__(ST_THREADS, 1)
@@ -109,8 +91,8 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
         const long long row0 = (long long)t * ST_ROWS;
         const bool second = row0 + ST_BOX_ROWS < rows;
         mbar_arrive_expect_tx(&S.full[st], (second ? 2u : 1u) * ST_BOX_ROWS * 128u);
-        tma_load_2d(&S.tile[st][0], &x_map, 0, (int)row0, &S.full[st]);
-        if (second) tma_load_2d(&S.tile[st][ST_BOX_ROWS * ST_IPT], &x_map, 0, (int)(row0 + ST_BOX_ROWS), &S.full[st]);
+        rpb_tma::tma_load_2d(&S.tile[st][0], &x_map, 0, (int)row0, &S.full[st]);
+        if (second) rpb_tma::tma_load_2d(&S.tile[st][ST_BOX_ROWS * ST_IPT], &x_map, 0, (int)(row0 + ST_BOX_ROWS), &S.full[st]);
       } else {
         S.tile_id[st] = ST_INVALID;      // every CTA draws exactly one terminating ticket
         mbar_arrive(&S.full[st]);
@@ -221,7 +203,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
     mbar_wait(&S.full[st], (k / ST_STAGES) & 1);
     t = S.tile_id[st];
     if (t == ST_INVALID) return;
-    load_row(r, &S.tile[st][0], row);
+    rpb_tma::load_row16(r, &S.tile[st][0], row);
     if ((long long)t * ST_ROWS + row >= rows) {          // rows past the end of the array (zero-filled or stale)
 #pragma unroll
       for (int i = 0; i < ST_IPT; ++i) r[i] = 0.0;
@@ -286,24 +268,6 @@ __global__ void scan_tail_kernel(const double* __restrict__ x, double* __restric
   for (int i = 0; i < count; ++i) { y[first + i] = run; run += x[first + i]; }
 }
 
-typedef CUresult (*encode_fn_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-encode_fn_t get_encode()
-{
-  static encode_fn_t fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<encode_fn_t>(p);
-  }
-  return fn;
-}
-
 }  // namespace
 
 // Returns 1 if the call was handled here, 0 if the caller should use the register-staged kernel, < 0 / cudaError on failure.
@@ -317,7 +281,7 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
   const int64_t rows = n / ST_IPT;
   if (rows < (int64_t)ST_ROWS * ctx->sm_count * 2) return 0;          // small problems: the simpler kernel
   if (!rpb_aligned(x, 16) || !rpb_aligned(y, 32) || rows > 0x7fffffffll) return 0;
-  encode_fn_t encode = get_encode();
+  rpb_tma::encode_fn_t encode = rpb_tma::get_encode();
   if (!encode) return 0;
   const int64_t tiles = (rows + ST_ROWS - 1) / ST_ROWS;
   if (sizeof(tile_desc) * (size_t)tiles > desc_bytes) return 0;

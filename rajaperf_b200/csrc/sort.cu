@@ -16,6 +16,8 @@
 //   * caller-provided scratch, no allocation, no host synchronisation; stable (pairs well-defined).
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int RADIX_BITS = 8;
@@ -147,14 +149,22 @@ __device__ __forceinline__ void st_desc(unsigned long long* p, unsigned long lon
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// digit of a pass: the shift is a multiple of 8, so the byte lives in one 32-bit half of the key
+__device__ __forceinline__ unsigned int key_digit(unsigned long long k, int shift)
+{
+  const unsigned int w = (shift & 32) ? (unsigned int)(k >> 32) : (unsigned int)k;
+  return (w >> (shift & 31)) & (RADIX - 1);
+}
+
 template <bool PAIRS, bool FIRST, bool LAST>
-__global__ void __launch_bounds__(SORT_BLOCK)
+__global__ void __launch_bounds__(SORT_BLOCK, 2)
 sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                      const unsigned long long* __restrict__ vals_in, unsigned long long* __restrict__ vals_out,
                      int64_t n, int shift, const unsigned long long* __restrict__ g_base /*[RADIX]*/,
                      unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket,
                      unsigned int num_tiles, unsigned int parity)
 {
+  using pos_t = typename std::conditional<PAIRS, unsigned short, int>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);            // [TILE]
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_keys + SORT_TILE);               // [WARPS][RADIX]
@@ -175,18 +185,25 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
 
   // ---- load: warp w owns the contiguous chunk [w*32*IPT, (w+1)*32*IPT); round r, lane l
   unsigned long long key[SORT_IPT];
-  unsigned long long val[PAIRS ? SORT_IPT : 1];
   const int chunk = warp * 32 * SORT_IPT + lane;
+  const bool full = (valid == SORT_TILE);                     // every tile but the last: no bounds tests
+  if (full) {
 #pragma unroll
-  for (int r = 0; r < SORT_IPT; ++r) {
-    const int p = chunk + r * 32;
-    unsigned long long k = 0xffffffffffffffffull;           // padding sorts last, never written
-    if (p < valid) {
-      k = keys_in[tile_base + p];
-      if (FIRST) k = key_encode(k);
+    for (int r = 0; r < SORT_IPT; ++r) {
+      unsigned long long k = keys_in[tile_base + chunk + r * 32];
+      key[r] = FIRST ? key_encode(k) : k;
     }
-    key[r] = k;
-    if (PAIRS) val[r] = (p < valid) ? vals_in[tile_base + p] : 0ull;
+  } else {
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+      const int p = chunk + r * 32;
+      unsigned long long k = 0xffffffffffffffffull;           // padding sorts last, never written
+      if (p < valid) {
+        k = keys_in[tile_base + p];
+        if (FIRST) k = key_encode(k);
+      }
+      key[r] = k;
+    }
   }
 
   // ---- rank inside the warp chunk (stable): match-any on the digit
@@ -194,7 +211,7 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   unsigned int* my_cnt = s_cnt + warp * RADIX;
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
-    const unsigned int d = (unsigned int)(key[r] >> shift) & (RADIX - 1);
+    const unsigned int d = key_digit(key[r], shift);
     const unsigned int peers = match_digit(d);
     const int leader = __ffs(peers) - 1;
     unsigned int before = 0;
@@ -251,13 +268,25 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   __syncthreads();
 
   // ---- reorder by digit in shared memory
-  int pos[SORT_IPT];
+  pos_t pos[SORT_IPT];
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
-    const unsigned int d = (unsigned int)(key[r] >> shift) & (RADIX - 1);
-    pos[r] = (int)(s_bin_start[d] + my_cnt[d] + rank[r]);
+    const unsigned int d = key_digit(key[r], shift);
+    pos[r] = (pos_t)(s_bin_start[d] + my_cnt[d] + rank[r]);
     s_keys[pos[r]] = key[r];
     if (PAIRS) s_digit[pos[r]] = (unsigned char)d;
+  }
+  // pairs: the values are requested only now, when the key registers are dead (the kernel stays at
+  // 64 registers = 2 CTAs per SM); their latency hides behind the key write-out
+  unsigned long long val[PAIRS ? SORT_IPT : 1];
+  if (PAIRS) {
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+      const int p = chunk + r * 32;
+      val[r] = 0ull;
+      if (p < valid)
+        asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(val[r]) : "l"(vals_in + tile_base + p));
+    }
   }
   __syncthreads();
 
@@ -265,9 +294,9 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
     const int p = threadIdx.x + r * SORT_BLOCK;
-    if (p < valid) {
+    if (full || p < valid) {
       unsigned long long k = s_keys[p];
-      const unsigned int d = (unsigned int)(k >> shift) & (RADIX - 1);
+      const unsigned int d = key_digit(k, shift);
       if (LAST) k = key_decode(k);
       keys_out[p + s_delta[d]] = k;
     }
@@ -280,7 +309,7 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
       const int p = threadIdx.x + r * SORT_BLOCK;
-      if (p < valid) vals_out[p + s_delta[s_digit[p]]] = s_keys[p];
+      if (full || p < valid) vals_out[p + s_delta[s_digit[p]]] = s_keys[p];
     }
   }
 }

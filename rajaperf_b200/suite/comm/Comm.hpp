@@ -23,16 +23,31 @@ protected:
 
 class HALO_PACKING_FUSED : public HALO_base {
 public:
-  explicit HALO_PACKING_FUSED(const RunParams& params);
+  explicit HALO_PACKING_FUSED(const RunParams& params) : HALO_PACKING_FUSED(rajaperf::Comm_HALO_PACKING_FUSED, params) {}
   void setUp(VariantID vid, size_t tune_idx) override;
   void updateChecksum(VariantID vid, size_t tune_idx) override;
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
-private:
+protected:
+  HALO_PACKING_FUSED(KernelID kid, const RunParams& params);
   rpb200_halo_plan* m_plan = nullptr;
   std::vector<Real_ptr> m_vars, m_pack_buffers, m_unpack_buffers;
   std::vector<Index_type> m_pack_lens, m_unpack_lens;
+};
+
+// The unfused kernel (widened row; reference comm/HALO_PACKING.{hpp,cpp}, -Cuda.cpp:26-47): same
+// setUp, same result, but one launch per (neighbour, variable) -- 78 packs + 78 unpacks per rep -- so the
+// report shows what the fusion buys.  Each launch is a one-tuple work list; the rep batch replays from a
+// CUDA graph like every other kernel.
+class HALO_PACKING : public HALO_PACKING_FUSED {
+public:
+  explicit HALO_PACKING(const RunParams& params);
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  std::vector<rpb200_halo_worklist*> m_pack_wl, m_unpack_wl;     // [neighbour * num_vars + var]
 };
 
 // All px*py*pz ranks live in this process; rank r runs on CUDA device first + (r mod ndev).  Every rank

@@ -6,7 +6,7 @@
 namespace rajaperf {
 namespace comm {
 
-HALO_PACKING_FUSED::HALO_PACKING_FUSED(const RunParams& params) : HALO_base(rajaperf::Comm_HALO_PACKING_FUSED, params)
+HALO_PACKING_FUSED::HALO_PACKING_FUSED(KernelID kid, const RunParams& params) : HALO_base(kid, params)
 {
   setDefaultReps(200);
   setItsPerRep(m_num_vars * m_halo_elems * 2);

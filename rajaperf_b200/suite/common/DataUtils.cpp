@@ -94,6 +94,28 @@ void allocAndInitDataRandSign(Real_ptr& d_ptr, Index_type len)
   });
 }
 
+void allocAndInitData(Int_ptr& d_ptr, Index_type len)        // DataUtils.cpp:477-497
+{
+  void* p = nullptr;
+  checkAbi(rpb200_malloc(&p, sizeof(Int_type) * (Size_type)(len > 0 ? len : 1)), "rpb200_malloc");
+  d_ptr = static_cast<Int_ptr>(p);
+  std::vector<Int_type> h((Size_type)len);
+  std::srand(4793);
+  Real_type signfact = 0.0;
+  for (Index_type i = 0; i < len; ++i) {
+    signfact = Real_type(std::rand()) / RAND_MAX;
+    h[i] = (signfact < 0.5 ? -1 : 1);
+  }
+  if (len > 0) {
+    signfact = Real_type(std::rand()) / RAND_MAX;
+    h[(Size_type)(len * signfact)] = -58;
+    signfact = Real_type(std::rand()) / RAND_MAX;
+    h[(Size_type)(len * signfact)] = 19;
+  }
+  copyToDevice(d_ptr, h.data(), sizeof(Int_type) * (Size_type)len);
+  detail::incDataInitCount();
+}
+
 void initData(Real_type& d)
 {
   const Real_type factor = parityFactor();
@@ -110,6 +132,23 @@ Checksum_type calcChecksumHost(const Real_type* ptr, Index_type len, Real_type s
   for (Index_type j = 0; j < len; ++j) {
     // the weight is formed in double, the product in long double (DataUtils.cpp:606, :631)
     const Checksum_type x = (std::abs(std::sin(j + 1.0)) + 0.5) * static_cast<Checksum_type>(ptr[j]);
+    const Checksum_type y = x - ckahan;
+    volatile Checksum_type t = tchk + y;
+    volatile Checksum_type z = t - tchk;
+    ckahan = z - y;
+    tchk = t;
+  }
+  tchk *= scale_factor;
+  return tchk;
+}
+
+Checksum_type calcChecksum(const Int_type* d_ptr, Index_type len, Real_type scale_factor)
+{
+  std::vector<Int_type> h((Size_type)len);
+  copyToHost(h.data(), d_ptr, sizeof(Int_type) * (Size_type)len);
+  Checksum_type tchk = 0.0, ckahan = 0.0;
+  for (Index_type j = 0; j < len; ++j) {
+    const Checksum_type x = (std::abs(std::sin(j + 1.0)) + 0.5) * static_cast<Checksum_type>(h[j]);
     const Checksum_type y = x - ckahan;
     volatile Checksum_type t = tchk + y;
     volatile Checksum_type z = t - tchk;

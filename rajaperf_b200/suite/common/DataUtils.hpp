@@ -21,6 +21,7 @@ void allocAndInitData(Real_ptr& d_ptr, Index_type len);                       //
 void allocAndInitDataConst(Real_ptr& d_ptr, Index_type len, Real_type val);   // initDataConst:  DataUtils.cpp:518-525
 void allocAndInitDataRandValue(Real_ptr& d_ptr, Index_type len);              // initDataRandValue: :560-569
 void allocAndInitDataRandSign(Real_ptr& d_ptr, Index_type len);               // initDataRandSign:  :542-555
+void allocAndInitData(Int_ptr& d_ptr, Index_type len);                        // initData(Int_ptr): :477-497
 void initData(Real_type& d);                                                  // scalar: :589-595
 void deallocData(Real_ptr& d_ptr);
 void deallocData(Int_ptr& d_ptr);
@@ -30,6 +31,7 @@ void copyToHost(void* h_dst, const void* d_src, Size_type bytes);
 
 // checksum of a DEVICE array (copied back first) / of a host array
 Checksum_type calcChecksum(const Real_type* d_ptr, Index_type len, Real_type scale_factor = 1.0);
+Checksum_type calcChecksum(const Int_type* d_ptr, Index_type len, Real_type scale_factor = 1.0);   // :623-629
 Checksum_type calcChecksumHost(const Real_type* h_ptr, Index_type len, Real_type scale_factor = 1.0);
 
 void checkAbi(int err, const char* what);   // aborts with the rpb200 error string (the cudaErrchk analogue)

@@ -15,13 +15,15 @@ namespace rajaperf {
 class KernelBase;
 class RunParams;
 
-enum GroupID { Stream = 0, Apps, Algorithm, Comm, NumGroups };
+enum GroupID { Basic = 0, Polybench, Stream, Apps, Algorithm, Comm, NumGroups };   // reference order (RAJAPerfSuite.hpp:47-63)
 
 enum KernelID {
-  Stream_ADD = 0, Stream_COPY, Stream_DOT, Stream_MUL, Stream_TRIAD,
+  Basic_INDEXLIST = 0, Basic_INDEXLIST_3LOOP,          // widened rows
+  Polybench_GEMM,
+  Stream_ADD, Stream_COPY, Stream_DOT, Stream_MUL, Stream_TRIAD,
   Apps_CONVECTION3DPA, Apps_DIFFUSION3DPA, Apps_LTIMES, Apps_MASS3DPA,
   Algorithm_SCAN, Algorithm_SORT, Algorithm_SORTPAIRS, Algorithm_REDUCE_SUM,
-  Comm_HALO_PACKING_FUSED, Comm_HALO_EXCHANGE_FUSED,
+  Comm_HALO_PACKING, Comm_HALO_PACKING_FUSED, Comm_HALO_EXCHANGE_FUSED,
   NumKernels
 };
 

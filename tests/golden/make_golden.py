@@ -5,7 +5,7 @@ Usage (in the authoring container, where /root/reference exists):
     python tests/golden/make_golden.py [--exe oracle/_ref/raja-perf.exe]
 
 The binary is the reference's own raja-perf.exe built CPU-only from /root/reference
-(oracle/build_ref.sh).  Every case runs
+(oracle/build_ref.sh: the reference's own CMake build, CPU-only, out of tree).  Every case runs
     raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [kernel flags]
 and the Base_Seq checksum printed in RAJAPerf-checksum.txt is recorded verbatim (20 digits).
 Output: tests/golden/ref_checksums.json.  The GPU box never runs this script.
@@ -32,6 +32,12 @@ CASES += [("Apps_LTIMES", 0, 1, []), ("Apps_LTIMES", 0, 3, []), ("Apps_LTIMES", 
 CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, []), ("Comm_HALO_PACKING_FUSED", 0, 3, []),
           ("Comm_HALO_PACKING_FUSED", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
           ("Comm_HALO_PACKING_FUSED", 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1"])]
+# widened rows
+for k in ["Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP"]:
+    CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 1, 1, []), (k, 1000, 2, []), (k, 123457, 2, [])]
+CASES += [("Polybench_GEMM", 0, 1, []), ("Polybench_GEMM", 0, 2, []), ("Polybench_GEMM", 1, 1, []),
+          ("Polybench_GEMM", 10000, 2, []), ("Polybench_GEMM", 54321, 1, [])]
+CASES += [("Comm_HALO_PACKING", 0, 1, []), ("Comm_HALO_PACKING", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"])]
 
 
 def run_case(exe, kernel, size, reps, extra, workdir):

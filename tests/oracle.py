@@ -55,6 +55,11 @@ def lib():
         "orc_halo_neighbors": (None, [c_int, _I, _I, _I, _I]),
         "orc_halo_pack": (None, [_D, _I, _D, c_int64]),
         "orc_halo_unpack": (None, [_D, _I, _D, c_int64]),
+        "orc_checksum_int_out": (None, [_I, c_int64, c_double, c_void_p]),
+        "orc_indexlist": (c_int64, [_D, _I, c_int64]),
+        "orc_indexlist_3loop": (c_int64, [_D, _I, c_int64]),
+        "orc_polybench_gemm": (None, [_D, _D, _D, c_int64, c_int64, c_int64, c_double, c_double]),
+        "orc_polybench_gemm_dims": (None, [c_int64, _L, _L, _L]),
         "orc_kat": (c_int, [c_char_p, c_int64, c_int, c_void_p, c_void_p]),
         "orc_omp_threads": (c_int, []),
         "orc_stream_copy_omp": (None, [_D, _D, c_int64]),
@@ -77,6 +82,14 @@ def checksum(arr: np.ndarray, scale: float = 1.0) -> np.longdouble:
     a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
     out = np.zeros(1, dtype=np.longdouble)
     lib().orc_checksum_out(a, a.size, scale, out.ctypes.data_as(c_void_p))
+    return out[0]
+
+
+def checksum_int(arr: np.ndarray, scale: float = 1.0) -> np.longdouble:
+    """The Int_ptr overload (DataUtils.cpp:623-629)."""
+    a = np.ascontiguousarray(arr, dtype=np.int32).reshape(-1)
+    out = np.zeros(1, dtype=np.longdouble)
+    lib().orc_checksum_int_out(a, a.size, scale, out.ctypes.data_as(c_void_p))
     return out[0]
 
 

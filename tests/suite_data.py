@@ -60,6 +60,24 @@ def scan(n):          # algorithm/SCAN.cpp:68-71
     return dict(x=x, y=y)
 
 
+def indexlist(n):     # basic/INDEXLIST.cpp:62-67 (and INDEXLIST_3LOOP.cpp: same setUp)
+    L = oracle.lib()
+    L.orc_reset_init_count()
+    x = np.empty(n); L.orc_init_rand_sign(x, n)
+    lst = np.empty(max(n, 1), dtype=np.int32); L.orc_init_int(lst, n)
+    return dict(x=x, list=lst[:n] if n else lst[:0])
+
+
+def polybench_gemm(target=0):   # polybench/POLYBENCH_GEMM.cpp:21-89
+    L = oracle.lib()
+    ni, nj, nk = (np.zeros(1, dtype=np.int64) for _ in range(3))
+    L.orc_polybench_gemm_dims(target, ni, nj, nk)
+    ni, nj, nk = int(ni[0]), int(nj[0]), int(nk[0])
+    A, B, C = _seq([("real", ni * nk), ("real", nk * nj), ("const", ni * nj, 0.0)])
+    scale = float(np.longdouble(0.001) * (np.longdouble(1000 * 1000) / np.longdouble(ni * nj)))
+    return dict(A=A, B=B, C=C, ni=ni, nj=nj, nk=nk, alpha=0.62, beta=1.002, scale=scale)
+
+
 def triad_scale(n):   # stream/TRIAD.cpp:36-38 (long double, narrowed to double at the call)
     return float(np.longdouble(0.001) * (np.longdouble(1000000) / np.longdouble(n)))
 

@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rajaperf_b200 import Context  # noqa: E402
 
-which = set(sys.argv[1:]) or {"stream", "scan", "sort", "pa", "ltimes", "halo"}
+which = set(sys.argv[1:]) or {"stream", "scan", "sort", "pa", "ltimes", "halo", "gemm", "indexlist"}
 ctx = Context(0)
 f64 = dict(dtype=torch.float64, device="cuda")
 
@@ -68,4 +68,15 @@ if "halo" in which:
     plan.exchange()
     torch.cuda.synchronize()
     plan.status()
+if "gemm" in which:
+    ni = nj = 4096; nk = 4915
+    A = torch.rand(ni * nk, **f64); B = torch.rand(nk * nj, **f64); C = torch.empty(ni * nj, **f64)
+    ctx.set_tuning("Polybench_GEMM", 96, -1, 4)
+    ctx.polybench_gemm(A, B, C, ni, nj, nk, 0.62)
+    torch.cuda.synchronize()
+if "indexlist" in which:
+    n = 1 << 27
+    x = torch.randn(n, **f64); lst = torch.empty(n, dtype=torch.int32, device="cuda"); ln = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.indexlist(x, lst, ln)
+    torch.cuda.synchronize()
 print("prof_kernels done")

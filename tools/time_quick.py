@@ -83,13 +83,15 @@ if "halo" in which:
         plan.bind(vars_, pb, ub)
         ne = sum(nb["pack_len"] for nb in plan.neighbors) * nv
         plan.window(vars_, want_handle=False); plan.connect_ptrs([0])
-        for cps in (2, 4, 8, 16):
-            ctx.set_tuning("Comm_HALO_PACKING_FUSED", -1, cps, -1)
-            ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", -1, cps, -1)
-            report(f"halo{g} pack cps={cps}", 20 * ne, time_ms(plan.pack, 50))
-            report(f"halo{g} unpack cps={cps}", 20 * ne, time_ms(plan.unpack, 50))
-            report(f"halo{g} pack+unpack cps={cps}", 40 * ne, time_ms(lambda: (plan.pack(), plan.unpack()), 50))
-            report(f"halo{g} exchange cps={cps}", 56 * ne, time_ms(plan.exchange, 50))
+        for hint, blk in ((4, 256), (4, 128), (1, 128)):   # `unroll` 1 = no L2 hints; `block_size` 128 = round-robin chunks
+          for cps in (4, 8):
+            ctx.set_tuning("Comm_HALO_PACKING_FUSED", blk, cps, hint)
+            ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, hint)
+            tag = f"cps={cps} hint={int(hint != 1)} rr={int(blk == 128)}"
+            report(f"halo{g} pack {tag}", 20 * ne, time_ms(plan.pack, 50))
+            report(f"halo{g} unpack {tag}", 20 * ne, time_ms(plan.unpack, 50))
+            report(f"halo{g} pack+unpack {tag}", 40 * ne, time_ms(lambda: (plan.pack(), plan.unpack()), 50))
+            report(f"halo{g} exchange {tag}", 56 * ne, time_ms(plan.exchange, 50))
         plan.status()
         plan.close()
         del vars_, pb, ub
@@ -105,6 +107,29 @@ if "sort" in which:
     report("sort_pairs", 32 * n, ms, mkeys_s=n / ms / 1e3)
     ms = time_ms(lambda: torch.sort(src), 5, 2)
     report("torch.sort (CUB pairs: keys + int64 indices)", 32 * n, ms, mkeys_s=n / ms / 1e3)
+
+if "indexlist" in which:
+    n = 1 << 27
+    x = torch.randn(n, **f64); lst = torch.empty(n, dtype=torch.int32, device="cuda")
+    ln = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for cps in (2, 3, 4):
+        ctx.set_tuning("Basic_INDEXLIST", -1, cps, -1)
+        ms = time_ms(lambda: ctx.indexlist(x, lst, ln))
+        report(f"indexlist cps={cps}", 8 * n + 4 * int(ln.item()), ms)
+    del x, lst
+
+if "gemm" in which:
+    for ni, cfgs in ((1000, ((64, 4), (64, 8), (96, 4))), (4096, ((64, 4), (64, 8), (96, 4), (96, 8), (128, 8), (160, 8))), (8192, ((96, 4), (96, 8), (160, 8)))):
+        nj, nk = ni, int(1.2 * ni)
+        A = torch.rand(ni * nk, **f64); B = torch.rand(nk * nj, **f64); C = torch.empty(ni * nj, **f64)
+        for t, u in cfgs:
+            ctx.set_tuning("Polybench_GEMM", t, -1, u)
+            ms = time_ms(lambda: ctx.polybench_gemm(A, B, C, ni, nj, nk, 0.62), 10)
+            report(f"gemm {ni}x{nj}x{nk} tile={t} gk={16 if u != 8 else 32}", 8 * (ni * nk + nk * nj + ni * nj), ms, tflops=2.0 * ni * nj * nk / ms / 1e9)
+        ms = time_ms(lambda: torch.mm(A.view(ni, nk), B.view(nk, nj), out=C.view(ni, nj)), 10)
+        report(f"gemm {ni} cuBLAS dgemm (incumbent)", 8 * (ni * nk + nk * nj + ni * nj), ms, tflops=2.0 * ni * nj * nk / ms / 1e9)
+        ctx.set_tuning("Polybench_GEMM", 256, -1, 4)
+        del A, B, C
 
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/time_quick.json", "w"), indent=1)
