@@ -8,7 +8,7 @@
 // interface fidelity and has no effect, exactly as in the reference.
 // This is the one genuinely dense FP64 contraction on the path (north_star), so it runs on
 // mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind):
-//   * CTA tile BM x BN x GK (GK = 16 or 32), 3-stage cp.async ring (zero-filled at the ragged edges), A kept
+//   * CTA tile 128x64x16 (8 warps, 2 CTAs/SM) for large C, 64x64x16 (4 warps, 4 CTAs/SM) otherwise; 3-stage cp.async ring (zero-filled at the ragged edges), A kept
 //     [m][k] and B [k][n] exactly as they lie in global memory (no transposes);
 //   * padded leading dimensions (GK+4 and BN+4 doubles) make every fragment load -- one LDS.64 per
 //     lane per 8x4 / 4x8 fragment -- bank-conflict-free;
@@ -57,27 +57,35 @@ gemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
   const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
   const int ktiles = (nk + GK - 1) / GK;
 
+  // Every thread issues the same A_N + B_N copies for every k tile.  Copy q of a thread is copy 0 shifted by
+  // q * A_RSTEP rows of A (q * B_KSTEP rows of B), same column: one base pointer per operand is computed ONCE;
+  // per tile only the k bound moves.
+  constexpr int A_CPR = GK / VEC, B_CPR = BN / VEC;              // copies per row
+  static_assert(THREADS % A_CPR == 0 && THREADS % B_CPR == 0, "a thread's copies share their column");
+  static_assert((BM * A_CPR) % THREADS == 0 && (GK * B_CPR) % THREADS == 0, "copies divide evenly over the CTA");
+  constexpr int A_N = BM * A_CPR / THREADS, B_N = GK * B_CPR / THREADS;
+  constexpr int A_RSTEP = THREADS / A_CPR, B_KSTEP = THREADS / B_CPR;
+  const int a_r = threadIdx.x / A_CPR, a_c = (threadIdx.x % A_CPR) * VEC;
+  const int b_r = threadIdx.x / B_CPR, b_c = (threadIdx.x % B_CPR) * VEC;
+  const double* a_src = A + (int64_t)(i0 + a_r) * nk + a_c;      // dereferenced only when in range
+  const double* b_src = B + (int64_t)b_r * nj + j0 + b_c;
+  const int64_t a_step = (int64_t)A_RSTEP * nk, b_step = (int64_t)B_KSTEP * nj;
+  const int b_w = j0 + b_c < nj ? (nj - j0 - b_c >= VEC ? VEC : nj - j0 - b_c) * 8 : 0;     // valid bytes (column bound)
   auto load_stage = [&](int kt, int stage) {
     const int k0 = kt * GK;
-    double* a_s = sA + stage * A_STAGE;
-    double* b_s = sB + stage * B_STAGE;
-    constexpr int A_CH = BM * (GK / VEC);       // copies per A tile: row r, k chunk c
-    for (int q = threadIdx.x; q < A_CH; q += THREADS) {
-      const int r = q / (GK / VEC), c = (q % (GK / VEC)) * VEC;
-      const int gi = i0 + r, gk = k0 + c;
-      int nb = 0;
-      if (gi < ni && gk < nk) nb = (nk - gk >= VEC ? VEC : nk - gk) * 8;
-      const double* src = nb ? A + (int64_t)gi * nk + gk : A;
-      cp_async_zfill<VEC * 8>(a_s + r * LDA + c, src, nb);
+    double* a_s = sA + stage * A_STAGE + a_r * LDA + a_c;
+    double* b_s = sB + stage * B_STAGE + b_r * LDB + b_c;
+    const int ka = nk - k0 - a_c;                                  // doubles left in the row from this copy's column
+    const int a_w = ka >= VEC ? VEC * 8 : (ka > 0 ? ka * 8 : 0);
+#pragma unroll
+    for (int q = 0; q < A_N; ++q) {
+      const int nb = (i0 + a_r + q * A_RSTEP < ni) ? a_w : 0;
+      cp_async_zfill<VEC * 8>(a_s + q * A_RSTEP * LDA, nb ? a_src + q * a_step + k0 : A, nb);
     }
-    constexpr int B_CH = GK * (BN / VEC);       // row k, column chunk c
-    for (int q = threadIdx.x; q < B_CH; q += THREADS) {
-      const int r = q / (BN / VEC), c = (q % (BN / VEC)) * VEC;
-      const int gk = k0 + r, gj = j0 + c;
-      int nb = 0;
-      if (gk < nk && gj < nj) nb = (nj - gj >= VEC ? VEC : nj - gj) * 8;
-      const double* src = nb ? B + (int64_t)gk * nj + gj : B;
-      cp_async_zfill<VEC * 8>(b_s + r * LDB + c, src, nb);
+#pragma unroll
+    for (int q = 0; q < B_N; ++q) {
+      const int nb = (k0 + b_r + q * B_KSTEP < nk) ? b_w : 0;
+      cp_async_zfill<VEC * 8>(b_s + q * B_KSTEP * LDB, nb ? b_src + q * b_step + (int64_t)k0 * nj : B, nb);
     }
   };
 
@@ -173,7 +181,7 @@ extern "C" int rpb200_polybench_gemm(rpb200_ctx* ctx, const double* A, const dou
   // 128 = 128x128 (8 warps of 64x32), 160 = 128x128 (16 warps of 32x32); anything else = automatic
   const int64_t big_tiles = ((ni + 127) / 128) * ((nj + 127) / 128);
   int tile = ctx->tune[RPB_K_POLYBENCH_GEMM].block_size;
-  if (tile != 64 && tile != 96 && tile != 128 && tile != 160) tile = (big_tiles >= 2 * (int64_t)ctx->sm_count ? 160 : 64);
+  if (tile != 64 && tile != 96 && tile != 128 && tile != 160) tile = (big_tiles >= 8 * (int64_t)ctx->sm_count ? 96 : 64);   // profiles/r01_widened.md
   const int i = (int)ni, j = (int)nj, k = (int)nk;
   const bool k32 = ctx->tune[RPB_K_POLYBENCH_GEMM].unroll == 8;       // tuning field `unroll`: 8 = 32-deep stages, else 16
 #define RPB_GEMM(BM, BN, WM, WN)                                                                                         \

@@ -225,6 +225,108 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   }
 }
 
+// HALO_EXCHANGE_FUSED as ONE launch: every CTA first packs its share of the chunks (storing into the peers'
+// windows and crediting / releasing the messages it completes), then turns to its share of the unpack chunks,
+// acquiring each message's flag the first time it touches it.  The grid is sized to be fully co-resident, and the
+// pack phase never waits, so every rank's flags are eventually released: no deadlock.  Compared with the
+// pack-launch + unpack-launch pair this overlaps the tail of the (NVLink-bound) packing with the first unpacks
+// and removes one launch.  Pack reads owned cells, unpack writes ghost cells: the two phases never alias.
+struct halo_side {
+  const rpb200_halo_seg* segs_g0; const rpb200_halo_seg* segs_g1;
+  const int* chunk_seg; const long long* seg_first_chunk; int total_chunks;
+};
+
+__global__ void __launch_bounds__(HALO_BLOCK)
+halo_exchange_kernel(halo_side P, halo_side U, const halo_msg* __restrict__ pmsgs, const halo_msg* __restrict__ umsgs,
+                     unsigned int* __restrict__ msg_done, unsigned long long* __restrict__ d_epoch,
+                     unsigned int* __restrict__ unpack_done, int* __restrict__ error)
+{
+  constexpr int EPT = HALO_CHUNK / HALO_BLOCK;
+  unsigned long long epoch = 0;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
+  epoch += 1;
+  const bool odd = (epoch & 1ull) != 0;
+  const rpb200_halo_seg* __restrict__ psegs = odd ? P.segs_g1 : P.segs_g0;
+  const rpb200_halo_seg* __restrict__ usegs = odd ? U.segs_g1 : U.segs_g0;
+  const int step = (int)gridDim.x;
+
+  // ---- phase 1: pack + signal
+  for (int c = blockIdx.x; c < P.total_chunks; c += step) {
+    const int s = __ldg(P.chunk_seg + c);
+    const rpb200_halo_seg seg = psegs[s];
+    const int64_t i0 = ((int64_t)c - __ldg(P.seg_first_chunk + s)) * HALO_CHUNK;
+    const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+    const int* __restrict__ list = seg.list + i0;
+    double* __restrict__ buf = seg.buffer + i0;
+    const double* __restrict__ var = seg.var;
+    int idx[EPT]; double v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; idx[k] = (i < cnt) ? __ldg(list + i) : -1; }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+  }
+  if ((int)blockIdx.x < P.total_chunks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      int c = blockIdx.x;
+      while (c < P.total_chunks) {
+        const int m = psegs[__ldg(P.chunk_seg + c)].msg;
+        int run = 1;
+        while (c + run * step < P.total_chunks && psegs[__ldg(P.chunk_seg + c + run * step)].msg == m) ++run;
+        const halo_msg hm = pmsgs[m];
+        const unsigned int prev = atomicAdd(msg_done + m, (unsigned int)run);
+        if (prev + run == hm.chunks) {
+          msg_done[m] = 0u;
+          st_release_sys(hm.remote_flag, epoch);
+        }
+        c += run * step;
+      }
+    }
+  }
+
+  // ---- phase 2: wait + unpack
+  int waited_msg = -1;
+  for (int c = blockIdx.x; c < U.total_chunks; c += step) {
+    const int s = __ldg(U.chunk_seg + c);
+    const rpb200_halo_seg seg = usegs[s];
+    const int64_t i0 = ((int64_t)c - __ldg(U.seg_first_chunk + s)) * HALO_CHUNK;
+    const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+    if (seg.msg != waited_msg) {
+      if (threadIdx.x == 0) {
+        const unsigned long long* f = umsgs[seg.msg].my_flag;
+        unsigned int spins = 0;
+        while (ld_acquire_sys(f) < epoch) {
+          __nanosleep(40);
+          if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }
+        }
+      }
+      __syncthreads();
+      waited_msg = seg.msg;
+    }
+    const int* __restrict__ list = seg.list + i0;
+    const double* __restrict__ buf = seg.buffer + i0;
+    double* __restrict__ var = seg.var;
+    int idx[EPT]; double v[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; idx[k] = (i < cnt) ? __ldg(list + i) : -1; }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) var[idx[k]] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(unpack_done, 1u);
+    if (prev == gridDim.x - 1) {         // every CTA has read the epoch and finished: commit it
+      *unpack_done = 0u;
+      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
+    }
+  }
+}
+
 struct worklist_dev {
   rpb200_halo_seg* d_segs = nullptr;
   int* d_chunk_seg = nullptr;
@@ -307,10 +409,10 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
   const int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
   int64_t grid = (int64_t)ctx->sm_count * cps;
   if (grid > w.total_chunks) grid = w.total_chunks;
-  // tuning field `unroll` of the two halo kernels: 1 = no L2 eviction-priority hints, else hints on;
+  // tuning field `unroll` of the two halo kernels: 4 = L2 eviction-priority hints on, else off;
   // tuning field `block_size`: 128 = chunks dealt round-robin (c = b, b + grid, ...) instead of in
   // contiguous ranges, so the slow strided faces are spread over every CTA
-  const bool hint = ctx->tune[kid].unroll != 1, strided = ctx->tune[kid].block_size == 128;
+  const bool hint = ctx->tune[kid].unroll == 4, strided = ctx->tune[kid].block_size == 128;
 #define RPB_HALO_LAUNCH(H, S)                                                                                  \
   halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
       w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)w.total_chunks,   \
@@ -721,8 +823,30 @@ extern "C" int rpb200_halo_exchange_unpack(rpb200_halo_plan* p, rpb200_stream_t 
 
 extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
 {
-  const int rc = rpb200_halo_exchange_pack(p, s);
-  return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
+  if (!p || !p->connected) return RPB200_EINVAL;
+  const rpb_tuning& t = p->ctx->tune[RPB_K_HALO_EXCHANGE_FUSED];
+  if (t.unroll == 2 || t.unroll == 4) {   // tuning field `unroll`: 2 / 4 = the two-launch form (pack + signal, then wait + unpack) without / with L2 hints
+    const int rc = rpb200_halo_exchange_pack(p, s);
+    return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
+  }
+  static int resident = 0;      // CTAs of the fused kernel that fit one SM: the grid must be fully co-resident
+  if (!resident) {
+    RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_exchange_kernel, HALO_BLOCK, 0));
+    if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
+  }
+  int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 4;
+  if (cps > resident) cps = resident;
+  const worklist_dev& pw = p->xpack_wl[0]; const worklist_dev& uw = p->xunpack_wl[0];
+  int64_t grid = (int64_t)p->ctx->sm_count * cps;
+  const int64_t most = pw.total_chunks > uw.total_chunks ? pw.total_chunks : uw.total_chunks;
+  if (grid > most) grid = most;
+  if (grid < 1) return 0;
+  halo_side P{pw.d_segs, p->xpack_wl[1].d_segs, pw.d_chunk_seg, pw.d_first, (int)pw.total_chunks};
+  halo_side U{uw.d_segs, p->xunpack_wl[1].d_segs, uw.d_chunk_seg, uw.d_first, (int)uw.total_chunks};
+  halo_exchange_kernel<<<(int)grid, HALO_BLOCK, 0, rpb_stream(s)>>>(P, U, p->d_pack_msgs, p->d_unpack_msgs, p->d_msg_done,
+                                                                    p->d_epoch, p->d_unpack_done, p->d_error);
+  RPB_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int rpb200_halo_exchange_status(rpb200_halo_plan* p)

@@ -24,6 +24,7 @@ constexpr int IL_TILE = IL_BLOCK * IL_IPT;     // 8192 elements = 64 KB of x per
 
 // descriptor: [63:34] epoch (30 bits)  [33:32] status  [31:0] count
 constexpr unsigned long long IL_PARTIAL = 1ull, IL_INCLUSIVE = 2ull;
+constexpr size_t IL_DESC_BYTES = 128;          // state per tile: the TMA path keeps one descriptor per 128-byte line
 
 __device__ __forceinline__ unsigned long long il_ld(const unsigned long long* p)
 {
@@ -169,7 +170,7 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
 extern "C" int rpb200_indexlist_reserve(rpb200_ctx* ctx, int64_t n)
 {
   if (!ctx || n < 0) return RPB200_EINVAL;
-  return il_grow_state(ctx, sizeof(unsigned long long) * (size_t)((n + IL_TILE - 1) / IL_TILE + 1), nullptr);
+  return il_grow_state(ctx, IL_DESC_BYTES * (size_t)((n + IL_TILE - 1) / IL_TILE + 1), nullptr);
 }
 
 extern "C" int rpb200_indexlist(rpb200_ctx* ctx, const double* x, int* list, int64_t n, int64_t* d_len,
@@ -180,7 +181,7 @@ extern "C" int rpb200_indexlist(rpb200_ctx* ctx, const double* x, int* list, int
   cudaStream_t st = rpb_stream(s);
   if (n == 0) { RPB_CHECK(cudaMemsetAsync(d_len, 0, sizeof(int64_t), st)); return 0; }
   const unsigned int tiles = (unsigned int)((n + IL_TILE - 1) / IL_TILE);
-  { const int rc = il_grow_state(ctx, sizeof(unsigned long long) * ((size_t)tiles + 1), st); if (rc != 0) return rc; }
+  { const int rc = il_grow_state(ctx, IL_DESC_BYTES * ((size_t)tiles + 1), st); if (rc != 0) return rc; }
   if (++ctx->ilist_epoch >= 0x3fffffffu) {             // 30-bit tag about to wrap: start over from clean state
     RPB_CHECK(cudaMemsetAsync(ctx->d_ilist_state, 0, ctx->ilist_state_bytes, st));
     ctx->ilist_epoch = 1;

@@ -55,10 +55,13 @@ struct il_smem {
   unsigned int arrived[2];
 };
 
+// IT_LBW = descriptors per lane per look-back round; dstride = distance between descriptors in 8-byte words
+// (16 = one descriptor per 128-byte line, so the polls of a round spread over 32 L2 slices instead of 2 lines)
+template <int IT_LBW>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict__ list, long long rows,
                      unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long tag,
-                     unsigned int num_tiles)
+                     unsigned int num_tiles, int dstride, unsigned int backoff_ns, int num_lb)
 {
   extern __shared__ unsigned char smem_raw[];
   il_smem& S = *reinterpret_cast<il_smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -103,8 +106,10 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
     // ---------------------------------------------------------------- look-back warps: tiles k = slot, slot + 2, ...
     // (they never touch the stage ring: the compute warps hand them the tile number with agg_ready, and
     //  cannot run two sequence numbers ahead of a look-back warp, so the barrier phases cannot alias)
-    const int slot = warp - IT_WARPS - 1;
-    for (int k = slot;; k += 2) {
+    // num_lb == 1: warp 17 alone takes every tile (experiment switch, RPB200_IL_NLB)
+    if (num_lb == 1 && warp != IT_WARPS + 1) return;
+    for (int k = warp - IT_WARPS - 1;; k += num_lb) {
+      const int slot = k & 1;
       mbar_wait(&S.agg_ready[slot], (k >> 1) & 1);
       const unsigned int tile = S.lb_tile[slot];
       if (tile == IT_INVALID) break;
@@ -119,23 +124,41 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
 
       unsigned int prefix = 0;
       if (tile != 0) {                  // the aggregate was already published by the last compute warp of A(k)
+        // At full HBM speed ~56 tiles finish per microsecond across the GPU, more than one 32-descriptor round
+        // trip can cover: every lane keeps IT_LBW independent descriptor loads in flight (128 tiles per round).
         long long look = (long long)tile - 1;
         for (;;) {
-          const long long idx = look - lane;
-          unsigned long long w = tag | (IT_INCLUSIVE << 32);
-          if (idx >= 0) {
-            do { w = it_ld(desc + idx); } while ((w >> 34) != (tag >> 34) || ((w >> 32) & 3ull) == 0ull);
-          }
-          const unsigned int incl = __ballot_sync(0xffffffffu, ((w >> 32) & 3ull) == IT_INCLUSIVE);
-          const int first = __ffs(incl) - 1;
-          unsigned int c = (first < 0 || lane <= first) ? (unsigned int)w : 0u;
+          unsigned long long w[IT_LBW];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-          prefix += c;
-          if (first >= 0) break;
-          look -= 32;
+          for (int j = 0; j < IT_LBW; ++j) {
+            const long long idx = look - 32 * j - lane;
+            w[j] = tag | (IT_INCLUSIVE << 32);                 // before tile 0: an inclusive prefix of 0
+            if (idx >= 0) w[j] = it_ld(desc + idx * dstride);
+          }
+          bool found = false;
+#pragma unroll
+          for (int j = 0; j < IT_LBW; ++j) {
+            if (!found) {                                       // warp-uniform
+              const long long idx = look - 32 * j - lane;
+              if (idx >= 0) {
+                while ((w[j] >> 34) != (tag >> 34) || ((w[j] >> 32) & 3ull) == 0ull) {
+                  if (backoff_ns) __nanosleep(backoff_ns);
+                  w[j] = it_ld(desc + idx * dstride);
+                }
+              }
+              const unsigned int incl = __ballot_sync(0xffffffffu, ((w[j] >> 32) & 3ull) == IT_INCLUSIVE);
+              const int first = __ffs(incl) - 1;
+              unsigned int c = (first < 0 || lane <= first) ? (unsigned int)w[j] : 0u;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+              prefix += c;
+              found = first >= 0;
+            }
+          }
+          if (found) break;
+          look -= 32 * IT_LBW;
         }
-        if (lane == 0) it_st(desc + tile, tag | (IT_INCLUSIVE << 32) | (unsigned long long)(prefix + tile_total));
+        if (lane == 0) it_st(desc + (long long)tile * dstride, tag | (IT_INCLUSIVE << 32) | (unsigned long long)(prefix + tile_total));
       }
       if (lane < IT_WARPS) S.woff[slot][lane] = prefix + (winc - wt);
       __syncwarp();
@@ -186,7 +209,7 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
       for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
       if (lane == 0) {
         S.arrived[slot] = 0u;
-        it_st(desc + t, tag | ((t == 0 ? IT_INCLUSIVE : IT_PARTIAL) << 32) | (unsigned long long)tot);
+        it_st(desc + (long long)t * dstride, tag | ((t == 0 ? IT_INCLUSIVE : IT_PARTIAL) << 32) | (unsigned long long)tot);
       }
       __syncwarp();
     }
@@ -245,21 +268,36 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
   if (rows < (int64_t)IT_ROWS * ctx->sm_count * 2) return 0;
   if (!rpb_aligned(x, 16) || rows > 0x7fffffffll) return 0;
   const int64_t tiles = (rows + IT_ROWS - 1) / IT_ROWS;
-  if (sizeof(unsigned long long) * (size_t)tiles > desc_bytes) return 0;
+  static int lbw = -1, dstride = -1, backoff = 0, nlb = 2;
+  if (lbw < 0) {
+    const char* e = getenv("RPB200_IL_LBW"); lbw = e ? atoi(e) : 1;
+    e = getenv("RPB200_IL_DSTRIDE"); dstride = e ? atoi(e) : 16;
+    e = getenv("RPB200_IL_BACKOFF"); backoff = e ? atoi(e) : 0;
+    e = getenv("RPB200_IL_NLB"); nlb = (e && atoi(e) == 1) ? 1 : 2;
+    if (lbw != 1 && lbw != 2 && lbw != 4) lbw = 1;
+    if (dstride < 1) dstride = 1;
+  }
+  int ds = dstride;
+  while (ds > 1 && sizeof(unsigned long long) * (size_t)tiles * ds > desc_bytes) ds >>= 1;     // denser if the state is small
+  if (sizeof(unsigned long long) * (size_t)tiles * ds > desc_bytes) return 0;
   CUtensorMap map;
   if (!rpb_tma::make_row_map(&map, x, rows, IT_BOX_ROWS)) return 0;
 
   const size_t smem = sizeof(il_smem) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   int grid = ctx->sm_count;
   if (grid > tiles) grid = (int)tiles;
-  indexlist_tma_kernel<<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles);
+  if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
+  else if (lbw == 2) indexlist_tma_kernel<2><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
+  else indexlist_tma_kernel<1><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
   RPB_LAUNCH_CHECK();
-  indexlist_tail_kernel<<<1, 32, 0, st>>>(x, list, (long long)rows * IT_IPT, (int)(n - rows * IT_IPT), d_desc + (tiles - 1), d_len);
+  indexlist_tail_kernel<<<1, 32, 0, st>>>(x, list, (long long)rows * IT_IPT, (int)(n - rows * IT_IPT), d_desc + (tiles - 1) * ds, d_len);
   RPB_LAUNCH_CHECK();
   *handled = 1;
   return 0;

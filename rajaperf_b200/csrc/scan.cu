@@ -190,7 +190,9 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   if (tiles64 > 0x7ffffff0ll) return RPB200_EINVAL;
   const unsigned int tiles = (unsigned int)tiles64;
 
-  const size_t need = sizeof(tile_desc) * (size_t)tiles;
+  // the TMA path spreads its descriptors one per 128-byte line (8192-element tiles)
+  size_t need = sizeof(tile_desc) * (size_t)tiles;
+  { const size_t spread = 128 * (size_t)((n + 8191) / 8192 + 1); if (spread > need) need = spread; }
   { const int rc = scan_grow_state(ctx, need, st); if (rc != 0) return rc; }
   const unsigned long long epoch = ++ctx->scan_epoch;
 

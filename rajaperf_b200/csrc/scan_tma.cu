@@ -63,8 +63,10 @@ template <int LB, int BACKOFF>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ y, long long rows,
                 tile_desc* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long epoch,
-                unsigned int num_tiles, unsigned long long* __restrict__ dbg)
+                unsigned int num_tiles, unsigned long long* __restrict__ dbg, int dstride)
 {
+  // dstride: distance between tile descriptors in 16-byte units (2 = one per 32-byte sector: the polls
+  // of a look-back round spread over more L2 lines/slices; 5860 -> 6146 GB/s at 2^27, profiles/r01_widened.md)
   // dbg (optional, RPB200_SCAN_DEBUG=1): per CTA {tiles, clk waiting for TMA, clk waiting for agg_ready,
   // clk in look-back, look-back rounds, descriptor polls, total clk}
   unsigned long long d_tiles = 0, d_full = 0, d_agg = 0, d_lb = 0, d_rounds = 0, d_polls = 0;
@@ -143,7 +145,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
           for (int j = 0; j < LB; ++j) {
             const long long idx = look - 32 * j - lane;
             word[j] = (epoch << 2) | ST_INCLUSIVE; val[j] = 0.0;
-            if (idx >= 0) desc_load(desc + idx, word[j], val[j]);
+            if (idx >= 0) desc_load(desc + idx * dstride, word[j], val[j]);
           }
           bool found = false;
 #pragma unroll
@@ -154,7 +156,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
                 while ((word[j] >> 2) != epoch || (word[j] & 3ull) == 0ull) {
                   d_polls++;
                   if (BACKOFF > 0) __nanosleep(BACKOFF);
-                  desc_load(desc + idx, word[j], val[j]);
+                  desc_load(desc + idx * dstride, word[j], val[j]);
                 }
               }
               const unsigned int incl_mask = __ballot_sync(0xffffffffu, (word[j] & 3ull) == ST_INCLUSIVE);
@@ -168,7 +170,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
           if (found) break;
           look -= 32 * LB;
         }
-        if (lane == 0) desc_store(desc + tile, (epoch << 2) | ST_INCLUSIVE, prefix + tile_total);
+        if (lane == 0) desc_store(desc + (long long)tile * dstride, (epoch << 2) | ST_INCLUSIVE, prefix + tile_total);
       }
       d_lb += clock64() - t2;
       if (lane < ST_WARPS) S.woff[slot][lane] = prefix + (winc - wt);
@@ -229,7 +231,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
       const double tot = warp_sum(lane < ST_WARPS ? S.wtot[slot][lane] : 0.0);
       if (lane == 0) {
         S.arrived[slot] = 0u;
-        desc_store(desc + t, (epoch << 2) | (t == 0 ? ST_INCLUSIVE : ST_PARTIAL), tot);
+        desc_store(desc + (long long)t * dstride, (epoch << 2) | (t == 0 ? ST_INCLUSIVE : ST_PARTIAL), tot);
       }
       __syncwarp();
     }
@@ -284,7 +286,11 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
   rpb_tma::encode_fn_t encode = rpb_tma::get_encode();
   if (!encode) return 0;
   const int64_t tiles = (rows + ST_ROWS - 1) / ST_ROWS;
-  if (sizeof(tile_desc) * (size_t)tiles > desc_bytes) return 0;
+  static int dstride = -1;
+  if (dstride < 0) { const char* e = getenv("RPB200_SCAN_DSTRIDE"); dstride = e ? atoi(e) : 2; if (dstride < 1) dstride = 1; }
+  int ds = dstride;
+  while (ds > 1 && sizeof(tile_desc) * (size_t)tiles * ds > desc_bytes) ds >>= 1;      // denser if the state is small
+  if (sizeof(tile_desc) * (size_t)tiles * ds > desc_bytes) return 0;
 
   CUtensorMap map;
   const cuuint64_t dims[2] = {(cuuint64_t)ST_IPT, (cuuint64_t)rows};
@@ -310,7 +316,7 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
   do {                                                                                                                 \
     RPB_CHECK(cudaFuncSetAttribute(scan_tma_kernel<LB, BO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
     scan_tma_kernel<LB, BO><<<grid, ST_THREADS, smem, st>>>(map, y, (long long)rows, (tile_desc*)d_desc, d_ticket, epoch, \
-                                                           (unsigned int)tiles, dbg);                                 \
+                                                           (unsigned int)tiles, dbg, ds);                                 \
   } while (0)
   ST_LAUNCH(1, 0);
   RPB_LAUNCH_CHECK();
@@ -328,7 +334,7 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
   }
   const int rem = (int)(n - rows * ST_IPT);
   if (rem > 0) {
-    scan_tail_kernel<<<1, 32, 0, st>>>(x, y, (long long)rows * ST_IPT, rem, (const tile_desc*)d_desc + (tiles - 1));
+    scan_tail_kernel<<<1, 32, 0, st>>>(x, y, (long long)rows * ST_IPT, rem, (const tile_desc*)d_desc + (tiles - 1) * ds);
     RPB_LAUNCH_CHECK();
   }
   *handled = 1;

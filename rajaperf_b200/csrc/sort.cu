@@ -80,9 +80,33 @@ inline sort_scratch_layout make_layout(int64_t n, int pairs)
 // ----------------------------------------------------------------------------------------------
 // histogram of all 8 digits in one read of the keys
 // ----------------------------------------------------------------------------------------------
+// one key into the 8 shared-memory histograms.  The top byte (sign + high exponent bits) of similar-magnitude keys
+// usually hits one bin for the whole warp: it is counted with one atomic per warp instead of a 32-way conflict.
+__device__ __forceinline__ void hist_one(unsigned int (*s_hist)[RADIX], unsigned long long k, bool ok, int lane)
+{
+  const unsigned int lo = (unsigned int)k, hi = (unsigned int)(k >> 32);
+  if (ok) {
+    atomicAdd(&s_hist[0][lo & 0xffu], 1u);
+    atomicAdd(&s_hist[1][(lo >> 8) & 0xffu], 1u);
+    atomicAdd(&s_hist[2][(lo >> 16) & 0xffu], 1u);
+    atomicAdd(&s_hist[3][lo >> 24], 1u);
+    atomicAdd(&s_hist[4][hi & 0xffu], 1u);
+    atomicAdd(&s_hist[5][(hi >> 8) & 0xffu], 1u);
+    atomicAdd(&s_hist[6][(hi >> 16) & 0xffu], 1u);
+  }
+  const unsigned int d7 = hi >> 24;                        // sign + high exponent bits
+  const unsigned int d7_0 = __shfl_sync(0xffffffffu, d7, 0);
+  if (__all_sync(0xffffffffu, ok && d7 == d7_0)) {
+    if (lane == 0) atomicAdd(&s_hist[7][d7], 32u);
+  } else if (ok) {
+    atomicAdd(&s_hist[7][d7], 1u);
+  }
+}
+
+// 256-bit loads, two independent vectors per thread per trip (the kernel is a pure stream of the keys)
 __global__ void __launch_bounds__(512)
 sort_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n,
-                 unsigned long long* __restrict__ g_hist)
+                 unsigned long long* __restrict__ g_hist, int vector_ok)
 {
   __shared__ unsigned int s_hist[NUM_PASSES][RADIX];
   for (int i = threadIdx.x; i < NUM_PASSES * RADIX; i += blockDim.x) (&s_hist[0][0])[i] = 0u;
@@ -90,23 +114,27 @@ sort_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n,
 
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const int64_t n_round = (n + 31) & ~31ll;          // whole warps iterate together
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const bool ok = i < n;
-    const unsigned long long k = ok ? key_encode(keys[i]) : 0ull;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nv = vector_ok ? n / 4 : 0;                // whole 4-key vectors
+  const int64_t nv_round = (nv + 31) & ~31ll;              // whole warps iterate together
+  for (int64_t v = gtid; v < nv_round; v += 2 * stride) {
+    const int64_t v1 = v + stride;
+    const bool ok0 = v < nv, ok1 = v1 < nv;
+    dbl4 q0, q1;
+    if (ok0) q0 = ldg256_stream(reinterpret_cast<const double*>(keys) + 4 * v);
+    if (ok1) q1 = ldg256_stream(reinterpret_cast<const double*>(keys) + 4 * v1);
+    const double e0[4] = {q0.x, q0.y, q0.z, q0.w}, e1[4] = {q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-    for (int p = 0; p < NUM_PASSES; ++p) {
-      const unsigned int d = (unsigned int)(k >> (p * RADIX_BITS)) & (RADIX - 1);
-      if (p >= 5) {
-        // exponent bytes of similar-magnitude keys: usually the whole warp hits one bin
-        const unsigned int d0 = __shfl_sync(0xffffffffu, d, 0);
-        if (__all_sync(0xffffffffu, ok && d == d0)) {
-          if (lane == 0) atomicAdd(&s_hist[p][d], 32u);
-          continue;
-        }
-      }
-      if (ok) atomicAdd(&s_hist[p][d], 1u);
+    for (int j = 0; j < 4; ++j) hist_one(s_hist, ok0 ? key_encode((unsigned long long)__double_as_longlong(e0[j])) : 0ull, ok0, lane);
+    if (v1 < nv_round) {                                    // warp-uniform
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hist_one(s_hist, ok1 ? key_encode((unsigned long long)__double_as_longlong(e1[j])) : 0ull, ok1, lane);
     }
+  }
+  const int64_t r0 = 4 * nv, nr_round = (n - r0 + 31) & ~31ll;     // scalar remainder (everything if unaligned)
+  for (int64_t i = gtid; i < nr_round; i += stride) {
+    const bool ok = r0 + i < n;
+    hist_one(s_hist, ok ? key_encode(keys[r0 + i]) : 0ull, ok, lane);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < NUM_PASSES * RADIX; i += blockDim.x) {
@@ -342,7 +370,7 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
     int grid = ctx->sm_count * 4;
     int64_t need = (n + 511) / 512;
     if (need < grid) grid = (int)need;
-    sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist);
+    sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist, rpb_aligned(keys, 32) ? 1 : 0);
     RPB_LAUNCH_CHECK();
     sort_hist_scan_kernel<<<NUM_PASSES, RADIX, 0, st>>>(hist);
     RPB_LAUNCH_CHECK();

@@ -83,15 +83,25 @@ if "halo" in which:
         plan.bind(vars_, pb, ub)
         ne = sum(nb["pack_len"] for nb in plan.neighbors) * nv
         plan.window(vars_, want_handle=False); plan.connect_ptrs([0])
-        for hint, blk in ((4, 256), (4, 128), (1, 128)):   # `unroll` 1 = no L2 hints; `block_size` 128 = round-robin chunks
+        def graph_ms(body, reps=100):
+            body(); torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                for _ in range(reps):
+                    body()
+            g_.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g_.replay(); e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        # `unroll`: 1 = no L2 hints, 2 = exchange as two launches (no hints), 4 = hints; `block_size` 128 = round-robin chunks
+        for hint, blk in ((1, 256), (4, 256), (1, 128), (4, 128)):
           for cps in (4, 8):
             ctx.set_tuning("Comm_HALO_PACKING_FUSED", blk, cps, hint)
-            ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, hint)
-            tag = f"cps={cps} hint={int(hint != 1)} rr={int(blk == 128)}"
-            report(f"halo{g} pack {tag}", 20 * ne, time_ms(plan.pack, 50))
-            report(f"halo{g} unpack {tag}", 20 * ne, time_ms(plan.unpack, 50))
-            report(f"halo{g} pack+unpack {tag}", 40 * ne, time_ms(lambda: (plan.pack(), plan.unpack()), 50))
-            report(f"halo{g} exchange {tag}", 56 * ne, time_ms(plan.exchange, 50))
+            tag = f"cps={cps} hint={int(hint == 4)} rr={int(blk == 128)}"
+            report(f"halo{g} pack+unpack [graph] {tag}", 40 * ne, graph_ms(lambda: (plan.pack(), plan.unpack())))
+            for xu in ((1, 2) if hint == 1 else (4,)):      # exchange: 1 = one fused launch, 2 / 4 = two launches without / with hints
+                ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
+                report(f"halo{g} exchange [graph] {tag} launches={1 if xu == 1 else 2}", 56 * ne, graph_ms(plan.exchange))
         plan.status()
         plan.close()
         del vars_, pb, ub
