@@ -465,6 +465,13 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
     del x, yv, vals, scratch
     torch.cuda.empty_cache()
 
+    # ---- the suite's own calibration streams ------------------------------------------------
+    x = torch.zeros(STREAM_N, **f64); yv = torch.empty(STREAM_N, **f64)
+    rec("Algorithm_MEMCPY", STREAM_N, 16 * STREAM_N, time_events(torch, lambda: ctx.stream_copy(yv, x), 20, 3))
+    rec("Algorithm_MEMSET", STREAM_N, 8 * STREAM_N, time_events(torch, lambda: ctx.memset_f64(yv, 0.0), 20, 3), note="write-only stream")
+    del x, yv
+    torch.cuda.empty_cache()
+
     # ---- widened rows: INDEXLIST at the Algorithm-group size, GEMM at 4096 x 4096 x 4915 -------
     x = init_real_dev(torch, n, 0.2, dev) * (torch.randint(0, 2, (n,), device=dev, dtype=torch.float64) * 2 - 1)   # random sign
     lst = torch.empty(n, dtype=torch.int32, device=dev)

@@ -113,6 +113,9 @@ int rpb200_indexlist_reserve(rpb200_ctx*, int64_t n);
 /* polybench/POLYBENCH_GEMM-Cuda.cpp:44-85: C[i][j] = sum_k alpha * A[i][k] * B[k][j], row-major
  * A (ni x nk), B (nk x nj), C (ni x nj).  `beta` is dead in the reference body
  * (POLYBENCH_GEMM.hpp:32-39: "C *= beta" is overwritten by "C = dot") and is ignored here too. */
+/* algorithm/MEMSET-Cuda.cpp:27-76: x[i] = val, the write-only calibration stream; Algorithm_MEMCPY
+ * (MEMCPY-Cuda.cpp:27-76, y[i] = x[i]) is rpb200_stream_copy.                              */
+int rpb200_memset_f64(rpb200_ctx*, double* x, double val, int64_t n, rpb200_stream_t);
 int rpb200_polybench_gemm(rpb200_ctx*, const double* A, const double* B, double* C,
                           int64_t ni, int64_t nj, int64_t nk, double alpha, double beta,
                           rpb200_stream_t);

@@ -1031,6 +1031,29 @@ void orc_polybench_gemm_dims(int64_t target, int64_t* ni, int64_t* nj, int64_t* 
   *nk = (int64_t)((double)1200 / 1000 * (double)*ni);
 }
 
+/* algorithm/MEMCPY.cpp:59-68 + MEMCPY.hpp:27-28, algorithm/MEMSET.cpp:59-68 + MEMSET.hpp:27-28 */
+long double orc_kat_memcpy(int64_t target, int reps)
+{
+  const int64_t n = tsize(target, 1000000);
+  double *x = dalloc(n), *y = dalloc(n);
+  orc_reset_init_count();
+  orc_init_const(x, n, 0.0); orc_init_const(y, n, -1.234567e89);
+  for (int r = 0; r < reps; ++r) for (int64_t i = 0; i < n; ++i) y[i] = x[i];
+  long double ck = orc_checksum(y, n, 1.0);
+  free(x); free(y); return ck;
+}
+long double orc_kat_memset(int64_t target, int reps)
+{
+  const int64_t n = tsize(target, 1000000);
+  double* x = dalloc(n);
+  orc_reset_init_count();
+  orc_init_const(x, n, -1.234567e89);
+  const double val = 0.0;
+  for (int r = 0; r < reps; ++r) for (int64_t i = 0; i < n; ++i) x[i] = val;
+  long double ck = orc_checksum(x, n, 1.0);
+  free(x); return ck;
+}
+
 static long double kat_indexlist(int64_t target, int reps, int three_loop)   /* basic/INDEXLIST.cpp:21-79 */
 {
   const int64_t n = tsize(target, 1000000);
@@ -1088,6 +1111,8 @@ int orc_kat(const char* name, int64_t target, int reps, const int* ip, long doub
     *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
   else if (!strcmp(name, "Comm_HALO_PACKING"))    /* same setUp, same result as the fused kernel (HALO_PACKING.cpp:62-110) */
     *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
+  else if (!strcmp(name, "Algorithm_MEMCPY"))      *out = orc_kat_memcpy(target, reps);
+  else if (!strcmp(name, "Algorithm_MEMSET"))      *out = orc_kat_memset(target, reps);
   else if (!strcmp(name, "Basic_INDEXLIST"))       *out = orc_kat_indexlist(target, reps);
   else if (!strcmp(name, "Basic_INDEXLIST_3LOOP")) *out = orc_kat_indexlist_3loop(target, reps);
   else if (!strcmp(name, "Polybench_GEMM"))        *out = orc_kat_polybench_gemm(target, reps);

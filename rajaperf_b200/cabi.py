@@ -54,6 +54,7 @@ SIGNATURES = {
     "rpb200_ltimes": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int64, _P]),
     "rpb200_indexlist": (c_int, [_P, _P, _P, c_int64, _P, _P]),
     "rpb200_indexlist_reserve": (c_int, [_P, c_int64]),
+    "rpb200_memset_f64": (c_int, [_P, _P, c_double, c_int64, _P]),
     "rpb200_polybench_gemm": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, c_double, c_double, _P]),
     "rpb200_halo_chunk": (c_int, []),
     "rpb200_halo_worklist_create": (c_int, [_P, _P, c_int, POINTER(_P)]),
@@ -237,6 +238,10 @@ class Context:
         """list_: int32 tensor (>= n entries), d_len: int64 tensor of 1 element (device)."""
         n = x.numel() if n is None else n
         check(self.lib.rpb200_indexlist(self.h, _ptr(x), _ptr(list_), n, _ptr(d_len), _stream()), "indexlist")
+
+    def memset_f64(self, x, val, n=None):
+        n = x.numel() if n is None else n
+        check(self.lib.rpb200_memset_f64(self.h, _ptr(x), val, n, _stream()), "memset_f64")
 
     def polybench_gemm(self, A, B, C, ni, nj, nk, alpha, beta=0.0):
         check(self.lib.rpb200_polybench_gemm(self.h, _ptr(A), _ptr(B), _ptr(C), ni, nj, nk, alpha, beta,

@@ -27,10 +27,12 @@ static void default_tunings(rpb200_ctx* c)
   c->tune[RPB_K_DIFFUSION3DPA]  = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_CONVECTION3DPA] = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_INDEXLIST]      = rpb_tuning{512, 4, 4};
-  // halo kernels: block_size 128 = chunks dealt round-robin; unroll 4 = L2 eviction hints (off); exchange: unroll 1 =
-  // ONE fused launch per rep, 2 / 4 = pack launch + unpack launch (profiles/r01_halo_variants.md)
-  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{128, 8, 1};
-  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{128, 4, 1};
+  // halo kernels: block_size 256 = contiguous chunk ranges (128 = round-robin); unroll 4 = L2 eviction hints;
+  // exchange: unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch.  The alternatives win on
+  // some B200s and lose on others (SM enumeration differs per chip); these are the settings that never lose
+  // (profiles/r01_halo_variants.md)
+  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{256, 8, 1};
+  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{256, 4, 2};     // 4 CTAs/SM: 119 / 117 / 120 / 137 us at 1 / 2 / 4 / 8 GPUs
 }
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }

@@ -134,6 +134,38 @@ extern "C" int rpb200_stream_triad(rpb200_ctx* ctx, double* a, const double* b, 
                                    double alpha, int64_t n, rpb200_stream_t s)
 { return launch_ew<OP_TRIAD>(ctx, RPB_K_TRIAD, a, b, c, alpha, n, s); }
 
+// Algorithm_MEMSET (algorithm/MEMSET-Cuda.cpp:27-76, MEMSET.hpp:27-28): x[i] = val -- a write-only stream, the
+// in-suite ceiling for store bandwidth.  Algorithm_MEMCPY is rpb200_stream_copy.
+__global__ void __launch_bounds__(512)
+stream_set_kernel(double* __restrict__ out, double val, int64_t n, int64_t head)
+{
+  // `head` scalars bring the pointer to a 32-byte boundary; then whole vectors; then the tail
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+  if (gtid < head) out[gtid] = val;
+  double* __restrict__ body = out + head;
+  const int64_t nvec = (n - head) >> 2;
+  dbl4 v; v.x = v.y = v.z = v.w = val;
+  for (int64_t i = gtid; i < nvec; i += stride) stg256_stream(body + (i << 2), v);
+  const int64_t e = head + (nvec << 2) + gtid;
+  if (e < n) out[e] = val;
+}
+
+extern "C" int rpb200_memset_f64(rpb200_ctx* ctx, double* x, double val, int64_t n, rpb200_stream_t s)
+{
+  if (!ctx || n < 0 || (n > 0 && !x)) return RPB200_EINVAL;
+  if (n == 0) return 0;
+  if (!rpb_aligned(x, 8)) return RPB200_EINVAL;
+  int64_t head = (int64_t)((32 - ((uintptr_t)x & 31)) & 31) / 8;
+  if (head > n) head = n;
+  int64_t blocks = ((n >> 2) + 511) / 512;
+  const int64_t cap = (int64_t)ctx->sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  stream_set_kernel<<<(int)blocks, 512, 0, rpb_stream(s)>>>(x, val, n, head);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
 // =====================================================================================
 // Reductions: DOT (two inputs) and REDUCE_SUM (one input)
 // =====================================================================================

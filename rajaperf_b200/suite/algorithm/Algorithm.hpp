@@ -62,5 +62,31 @@ private:
   Index_type m_rep = 0;
 };
 
+// Calibration streams (widened rows; reference algorithm/MEMCPY.{hpp,cpp}, MEMSET.{hpp,cpp}).
+class MEMCPY : public KernelBase {         // y[i] = x[i]
+public:
+  explicit MEMCPY(const RunParams& params);
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void updateChecksum(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void runB200Variant(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  Real_ptr m_x = nullptr, m_y = nullptr;
+};
+
+class MEMSET : public KernelBase {         // x[i] = val
+public:
+  explicit MEMSET(const RunParams& params);
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void updateChecksum(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void runB200Variant(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  Real_ptr m_x = nullptr;
+  Real_type m_val = 0.0;
+};
+
 }  // namespace algorithm
 }  // namespace rajaperf

@@ -18,7 +18,7 @@ static const std::string KernelNames[] = {
   "Polybench_GEMM",
   "Stream_ADD", "Stream_COPY", "Stream_DOT", "Stream_MUL", "Stream_TRIAD",
   "Apps_CONVECTION3DPA", "Apps_DIFFUSION3DPA", "Apps_LTIMES", "Apps_MASS3DPA",
-  "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS", "Algorithm_REDUCE_SUM",
+  "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS", "Algorithm_REDUCE_SUM", "Algorithm_MEMSET", "Algorithm_MEMCPY",
   "Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED", "Comm_HALO_EXCHANGE_FUSED",
   "Unknown Kernel"
 };
@@ -38,7 +38,7 @@ GroupID getKernelGroup(KernelID kid)
   if (kid <= Polybench_GEMM) return Polybench;
   if (kid <= Stream_TRIAD) return Stream;
   if (kid <= Apps_MASS3DPA) return Apps;
-  if (kid <= Algorithm_REDUCE_SUM) return Algorithm;
+  if (kid <= Algorithm_MEMCPY) return Algorithm;
   return Comm;
 }
 const std::string& getVariantName(VariantID vid) { return VariantNames[vid]; }
@@ -64,6 +64,8 @@ KernelBase* getKernelObject(KernelID kid, const RunParams& p)
     case Algorithm_SORT: return new algorithm::SORT(p);
     case Algorithm_SORTPAIRS: return new algorithm::SORTPAIRS(p);
     case Algorithm_REDUCE_SUM: return new algorithm::REDUCE_SUM(p);
+    case Algorithm_MEMSET: return new algorithm::MEMSET(p);
+    case Algorithm_MEMCPY: return new algorithm::MEMCPY(p);
     case Comm_HALO_PACKING: return new comm::HALO_PACKING(p);
     case Comm_HALO_PACKING_FUSED: return new comm::HALO_PACKING_FUSED(p);
     case Comm_HALO_EXCHANGE_FUSED: return new comm::HALO_EXCHANGE_FUSED(p);

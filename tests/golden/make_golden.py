@@ -37,6 +37,8 @@ for k in ["Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP"]:
     CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 1, 1, []), (k, 1000, 2, []), (k, 123457, 2, [])]
 CASES += [("Polybench_GEMM", 0, 1, []), ("Polybench_GEMM", 0, 2, []), ("Polybench_GEMM", 1, 1, []),
           ("Polybench_GEMM", 10000, 2, []), ("Polybench_GEMM", 54321, 1, [])]
+for k in ["Algorithm_MEMCPY", "Algorithm_MEMSET"]:      # calibration streams: the checksum is 0 iff every element was written
+    CASES += [(k, 0, 1, []), (k, 1, 1, []), (k, 123457, 2, [])]
 CASES += [("Comm_HALO_PACKING", 0, 1, []), ("Comm_HALO_PACKING", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"])]
 
 

@@ -20,7 +20,7 @@ GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_checksums.json"
 # of a long double; tolerance class => the suite's own 1e-7 absolute bound (test-raja-perf-suite.cpp:167)
 EXACT = {"Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Algorithm_SORT", "Algorithm_SORTPAIRS",
          "Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA", "Comm_HALO_PACKING_FUSED",
-         "Comm_HALO_PACKING", "Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP"}
+         "Comm_HALO_PACKING", "Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP", "Algorithm_MEMCPY", "Algorithm_MEMSET"}
 
 
 def run_exe(args, outdir=None, check=True):

@@ -84,6 +84,32 @@ def test_indexlist_full_size_properties(ctx):
     assert bool((sel[1:] > sel[:-1]).all()) and bool((x[sel] < 0).all())
 
 
+# ------------------------------------------------------------------------------------- MEMSET / MEMCPY
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1000, 123457, (1 << 22) + 3])
+@pytest.mark.parametrize("offset", [0, 1, 3])
+def test_memset_writes_exactly_the_range(ctx, n, offset):
+    """x[i] = val on [offset, offset + n) of a sentinel-filled array: every element inside, nothing outside (unaligned heads)."""
+    buf = torch.full((n + 8,), -1.234567e89, dtype=torch.float64, device="cuda")
+    ctx.memset_f64(buf[offset:offset + n], 0.25, n)
+    got = buf.cpu().numpy()
+    assert np.all(got[offset:offset + n] == 0.25) and np.all(got[:offset] == -1.234567e89) and np.all(got[offset + n:] == -1.234567e89)
+
+
+@pytest.mark.parametrize("kernel", ["Algorithm_MEMSET", "Algorithm_MEMCPY"])
+@pytest.mark.parametrize("size,reps", [(0, 1), (1, 1), (123457, 2)])
+def test_calibration_streams_match_reference_golden(ctx, kernel, size, reps):
+    n = size or 1000000
+    y = torch.full((n,), -1.234567e89, dtype=torch.float64, device="cuda")         # MEMCPY.cpp:59-63, MEMSET.cpp:59-63
+    x = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for _ in range(reps):
+        if kernel == "Algorithm_MEMSET":
+            ctx.memset_f64(y, 0.0)
+        else:
+            ctx.stream_copy(y, x)
+    got = oracle.checksum(y.cpu().numpy())
+    assert got == np.longdouble(GOLD[(kernel, size, reps)]) == 0      # 0 iff every sentinel was overwritten
+
+
 # ------------------------------------------------------------------------------------- POLYBENCH_GEMM
 @pytest.mark.parametrize("ni,nj,nk", [(1, 1, 1), (3, 5, 7), (8, 8, 4), (64, 64, 16), (65, 63, 17), (100, 100, 120),
                                       (129, 257, 33), (200, 130, 0), (333, 334, 401)])
