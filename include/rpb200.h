@@ -191,6 +191,20 @@ int  rpb200_halo_exchange_connect_ptrs(rpb200_halo_plan*, int nranks, void* cons
 /* one rep = pack_signal then wait_unpack (or exchange() for both); all stream-ordered      */
 int  rpb200_halo_exchange_pack(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_exchange_unpack(rpb200_halo_plan*, rpb200_stream_t);
+/* The unfused HALO_EXCHANGE (comm/HALO_EXCHANGE-Cuda.cpp:26-123, HALO_EXCHANGE-Seq.cpp:34-116): one launch per
+ * (neighbour l, variable v) tuple instead of one per rep.  Message l is released to its receiver by whichever pack
+ * launch completes its last chunk; `commit` != 0 marks the LAST unpack launch of the rep (it advances the epoch).   */
+int  rpb200_halo_exchange_pack_seg(rpb200_halo_plan*, int l, int v, rpb200_stream_t);
+int  rpb200_halo_exchange_unpack_seg(rpb200_halo_plan*, int l, int v, int commit, rpb200_stream_t);
+/* HALO_SENDRECV (comm/HALO_SENDRECV.cpp:21-123, HALO_SENDRECV-Seq.cpp:34-52): transport only.  Message l is the caller's
+ * send_buffers[l] (num_vars * pack_len[l] doubles, device); rpb200_halo_sendrecv puts every message into the receive slot
+ * of its destination (the slot whose recv_tag is l) over NVLink, signals it, and waits for this rank's 26 messages:
+ * MPI_Irecv x26 / MPI_Isend x26 / MPI_Waitall x2 as one put kernel + one wait kernel, no host synchronisation.
+ * bind() after rpb200_halo_exchange_connect*.  rpb200_halo_recv_buffer returns where message l of the last completed rep
+ * lies in this rank's window (it synchronises; the location alternates between two generations).                  */
+int  rpb200_halo_sendrecv_bind(rpb200_halo_plan*, double* const* d_send_buffers);
+int  rpb200_halo_sendrecv(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_recv_buffer(rpb200_halo_plan*, int l, const double** d_ptr, int64_t* len);
 int  rpb200_halo_exchange(rpb200_halo_plan*, rpb200_stream_t);
 /* 0, or RPB200_ETIMEDOUT if an unpack CTA gave up waiting for a flag (synchronises)        */
 int  rpb200_halo_exchange_status(rpb200_halo_plan*);

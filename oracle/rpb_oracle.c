@@ -1031,6 +1031,36 @@ void orc_polybench_gemm_dims(int64_t target, int64_t* ni, int64_t* nj, int64_t* 
   *nk = (int64_t)((double)1200 / 1000 * (double)*ni);
 }
 
+/* comm/HALO_SENDRECV.cpp:62-105 (setUp, checksum) + HALO_SENDRECV-Seq.cpp:34-52: transport only.  Receive buffer l is
+ * filled by the message its neighbour sent with tag recv_tags[l]; every rank holds identical send buffers, so for any
+ * rank grid recv[l] = send[recv_tags[l]] and the rank average equals one rank's checksum.                          */
+long double orc_kat_halo_sendrecv(int64_t target, int reps, int hw, int nvars, const int pd[3])
+{
+  int64_t dims[3];
+  orc_halo_grid_dims(target > 0 ? target : 1000000, dims);
+  int ranks[ORC_HALO_NEIGHBORS], stags[ORC_HALO_NEIGHBORS], rtags[ORC_HALO_NEIGHBORS];
+  orc_halo_neighbors(0, pd, ranks, stags, rtags);
+  orc_reset_init_count();
+  int64_t plen[ORC_HALO_NEIGHBORS], ulen[ORC_HALO_NEIGHBORS];
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) {              /* setUp_base: 52 list allocations bump the counter */
+    plen[l] = orc_halo_extent_len(0, l, hw, dims);
+    ulen[l] = orc_halo_extent_len(1, l, hw, dims);
+    int* tmp = (int*)malloc(sizeof(int) * (size_t)(plen[l] > ulen[l] ? plen[l] : ulen[l]));
+    orc_init_int(tmp, plen[l]); orc_init_int(tmp, ulen[l]);
+    free(tmp);
+  }
+  double *send[ORC_HALO_NEIGHBORS], *recv[ORC_HALO_NEIGHBORS];
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) { send[l] = dalloc(nvars * plen[l]); orc_init_real(send[l], nvars * plen[l]); }
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) { recv[l] = dalloc(nvars * ulen[l]); orc_init_real(recv[l], nvars * ulen[l]); }
+  for (int r = 0; r < reps; ++r)
+    for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l)
+      memcpy(recv[l], send[rtags[l]], sizeof(double) * (size_t)(nvars * ulen[l]));     /* plen[rtags[l]] == ulen[l] */
+  long double ck = 0.0L;
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) ck += orc_checksum(recv[l], nvars * ulen[l], 1.0);
+  for (int l = 0; l < ORC_HALO_NEIGHBORS; ++l) { free(send[l]); free(recv[l]); }
+  return ck;
+}
+
 /* algorithm/MEMCPY.cpp:59-68 + MEMCPY.hpp:27-28, algorithm/MEMSET.cpp:59-68 + MEMSET.hpp:27-28 */
 long double orc_kat_memcpy(int64_t target, int reps)
 {
@@ -1111,12 +1141,16 @@ int orc_kat(const char* name, int64_t target, int reps, const int* ip, long doub
     *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
   else if (!strcmp(name, "Comm_HALO_PACKING"))    /* same setUp, same result as the fused kernel (HALO_PACKING.cpp:62-110) */
     *out = orc_kat_halo_packing_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3);
+  else if (!strcmp(name, "Comm_HALO_SENDRECV")) {
+    const int one[3] = {1, 1, 1};
+    *out = orc_kat_halo_sendrecv(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3, ip ? ip + 2 : one);
+  }
   else if (!strcmp(name, "Algorithm_MEMCPY"))      *out = orc_kat_memcpy(target, reps);
   else if (!strcmp(name, "Algorithm_MEMSET"))      *out = orc_kat_memset(target, reps);
   else if (!strcmp(name, "Basic_INDEXLIST"))       *out = orc_kat_indexlist(target, reps);
   else if (!strcmp(name, "Basic_INDEXLIST_3LOOP")) *out = orc_kat_indexlist_3loop(target, reps);
   else if (!strcmp(name, "Polybench_GEMM"))        *out = orc_kat_polybench_gemm(target, reps);
-  else if (!strcmp(name, "Comm_HALO_EXCHANGE_FUSED")) {
+  else if (!strcmp(name, "Comm_HALO_EXCHANGE_FUSED") || !strcmp(name, "Comm_HALO_EXCHANGE")) {   /* same data flow (HALO_EXCHANGE-Seq.cpp:34-116) */
     const int one[3] = {1, 1, 1};
     *out = orc_kat_halo_exchange_fused(target, reps, ip ? ip[0] : 1, ip ? ip[1] : 3,
                                        ip ? ip + 2 : one, NULL);

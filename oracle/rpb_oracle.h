@@ -81,6 +81,7 @@ int64_t orc_indexlist_3loop(const double* x, int* list, int64_t n);             
 void    orc_polybench_gemm(const double* A, const double* B, double* C, int64_t ni, int64_t nj, int64_t nk,
                            double alpha, double beta);                            /* polybench/POLYBENCH_GEMM-Seq.cpp:37-47 */
 void    orc_polybench_gemm_dims(int64_t target, int64_t* ni, int64_t* nj, int64_t* nk);  /* POLYBENCH_GEMM.cpp:24-35 */
+long double orc_kat_halo_sendrecv(int64_t target_size, int reps, int halo_width, int num_vars, const int pdims[3]);
 long double orc_kat_memcpy(int64_t target_size, int reps);
 long double orc_kat_memset(int64_t target_size, int reps);
 long double orc_kat_indexlist(int64_t target_size, int reps);

@@ -76,6 +76,11 @@ SIGNATURES = {
     "rpb200_halo_exchange_connect_ptrs": (c_int, [_P, c_int, POINTER(_P)]),
     "rpb200_halo_exchange_pack": (c_int, [_P, _P]),
     "rpb200_halo_exchange_unpack": (c_int, [_P, _P]),
+    "rpb200_halo_exchange_pack_seg": (c_int, [_P, c_int, c_int, _P]),
+    "rpb200_halo_exchange_unpack_seg": (c_int, [_P, c_int, c_int, c_int, _P]),
+    "rpb200_halo_sendrecv_bind": (c_int, [_P, POINTER(_P)]),
+    "rpb200_halo_sendrecv": (c_int, [_P, _P]),
+    "rpb200_halo_recv_buffer": (c_int, [_P, c_int, POINTER(_P), POINTER(c_int64)]),
     "rpb200_halo_exchange": (c_int, [_P, _P]),
     "rpb200_halo_exchange_status": (c_int, [_P]),
     "rpb200_ipc_export": (c_int, [_P, POINTER(c_ubyte)]),
@@ -353,11 +358,12 @@ class HaloPlan:
         check(self.lib.rpb200_halo_plan_unpack(self.h, _stream()), "halo_plan_unpack")
 
     def window(self, vars_, want_handle=True):
-        """Allocate this rank's receive window; returns (device pointer, bytes, ipc handle bytes)."""
+        """Allocate this rank's receive window; returns (device pointer, bytes, ipc handle bytes).
+        vars_ = None: a transport-only window (HALO_SENDRECV)."""
         self._keep_x = vars_
         w, nb = c_void_p(), c_size_t()
         hbuf = (c_ubyte * 64)()
-        check(self.lib.rpb200_halo_exchange_window(self.h, self._ptr_array(vars_), ctypes.byref(w), ctypes.byref(nb),
+        check(self.lib.rpb200_halo_exchange_window(self.h, self._ptr_array(vars_) if vars_ is not None else None, ctypes.byref(w), ctypes.byref(nb),
                                                    hbuf if want_handle else None), "halo_exchange_window")
         return w.value, nb.value, bytes(hbuf)
 
@@ -379,6 +385,30 @@ class HaloPlan:
 
     def exchange(self):
         check(self.lib.rpb200_halo_exchange(self.h, _stream()), "halo_exchange")
+
+    def sendrecv_bind(self, send_buffers):
+        self._keep_send = send_buffers
+        check(self.lib.rpb200_halo_sendrecv_bind(self.h, self._ptr_array(send_buffers)), "halo_sendrecv_bind")
+
+    def sendrecv(self):
+        check(self.lib.rpb200_halo_sendrecv(self.h, _stream()), "halo_sendrecv")
+
+    def recv_buffer(self, l):
+        """(device pointer, length in doubles) of message l of the last completed rep."""
+        p, n = c_void_p(), c_int64()
+        check(self.lib.rpb200_halo_recv_buffer(self.h, l, ctypes.byref(p), ctypes.byref(n)), "halo_recv_buffer")
+        return p.value, n.value
+
+    def exchange_unfused(self, num_vars):
+        """The unfused HALO_EXCHANGE: one pack launch and one unpack launch per (neighbour, variable)."""
+        st = _stream()
+        for l in range(26):
+            for v in range(num_vars):
+                check(self.lib.rpb200_halo_exchange_pack_seg(self.h, l, v, st), "halo_exchange_pack_seg")
+        for l in range(26):
+            for v in range(num_vars):
+                last = 1 if (l == 25 and v == num_vars - 1) else 0
+                check(self.lib.rpb200_halo_exchange_unpack_seg(self.h, l, v, last, st), "halo_exchange_unpack_seg")
 
     def status(self):
         check(self.lib.rpb200_halo_exchange_status(self.h), "halo_exchange_status")

@@ -83,6 +83,7 @@ __device__ __forceinline__ int ld_hint_i32(const int* p, unsigned long long pol)
 }
 
 constexpr int SEG_STRIDED = 1;       // rpb200_halo_seg.flags bit 0 (set by the library)
+constexpr int SEG_IDENTITY = 2;      // bit 1: no index list, element i of the segment is var[i] (HALO_SENDRECV puts)
 
 // per-message signalling state of an exchange (device)
 struct halo_msg {
@@ -105,8 +106,10 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
             const int* __restrict__ chunk_seg, const long long* __restrict__ seg_first_chunk, int total_chunks,
             const halo_msg* __restrict__ msgs, unsigned int* __restrict__ msg_done,
             unsigned long long* __restrict__ d_epoch, unsigned int* __restrict__ unpack_done,
-            int* __restrict__ error)
+            int* __restrict__ error, int chunk_lo, int commit)
 {
+  // The launch covers chunks [chunk_lo, total_chunks) of the work list (the whole list for the fused kernels, one
+  // (neighbour, variable) tuple for the unfused HALO_EXCHANGE); `commit` = this is the last unpack launch of the rep.
   constexpr int EPT = HALO_CHUNK / HALO_BLOCK;     // 8 elements per thread per chunk
   // The exchange epoch lives in device memory (so a CUDA graph of many reps replays correctly): the
   // pack and the unpack of one rep both see *d_epoch + 1; the last unpack CTA to retire commits it.
@@ -115,8 +118,8 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   if (MODE != 0) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
   epoch += 1;
   const rpb200_halo_seg* __restrict__ segs = (MODE != 0 && (epoch & 1ull)) ? segs_g1 : segs_g0;
-  const int per = (total_chunks + gridDim.x - 1) / gridDim.x;
-  const int c_begin = STRIDED ? (int)blockIdx.x : blockIdx.x * per;
+  const int per = (total_chunks - chunk_lo + gridDim.x - 1) / gridDim.x;
+  const int c_begin = chunk_lo + (STRIDED ? (int)blockIdx.x : blockIdx.x * per);
   const int c_end = STRIDED ? total_chunks : min(c_begin + per, total_chunks);
   const int c_step = STRIDED ? (int)gridDim.x : 1;
   int waited_msg = -1;
@@ -149,7 +152,7 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       const int i = k * HALO_BLOCK + threadIdx.x;
-      idx[k] = (i < cnt) ? (HINT ? ld_hint_i32(list + i, pol_once) : __ldg(list + i)) : -1;
+      idx[k] = (i < cnt) ? ((seg.flags & SEG_IDENTITY) ? (int)(i0 + i) : (HINT ? ld_hint_i32(list + i, pol_once) : __ldg(list + i))) : -1;
     }
     const bool keep = HINT && (seg.flags & SEG_STRIDED);      // uniform over the chunk
     if (PACK) {
@@ -213,7 +216,7 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
       }
     }
   }
-  if (MODE == 2) {
+  if (MODE == 2 && commit) {
     __syncthreads();
     if (threadIdx.x == 0) {
       const unsigned int prev = atomicAdd(unpack_done, 1u);
@@ -327,6 +330,24 @@ halo_exchange_kernel(halo_side P, halo_side U, const halo_msg* __restrict__ pmsg
   }
 }
 
+// HALO_SENDRECV's receive side: wait for the 26 messages of this rep, then commit the epoch
+__global__ void halo_wait_kernel(const halo_msg* __restrict__ umsgs, unsigned long long* __restrict__ d_epoch, int* __restrict__ error)
+{
+  unsigned long long epoch = 0;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
+  epoch += 1;
+  if (threadIdx.x < NNB) {
+    const unsigned long long* f = umsgs[threadIdx.x].my_flag;
+    unsigned int spins = 0;
+    while (ld_acquire_sys(f) < epoch) {
+      __nanosleep(40);
+      if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }
+    }
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
+}
+
 struct worklist_dev {
   rpb200_halo_seg* d_segs = nullptr;
   int* d_chunk_seg = nullptr;
@@ -336,6 +357,7 @@ struct worklist_dev {
   int64_t total_chunks = 0;
   std::vector<int64_t> lens;
   std::vector<int> flags;
+  std::vector<long long> first;     // host copy: first chunk of every tuple
 };
 
 int worklist_free(worklist_dev& w)
@@ -350,6 +372,7 @@ int worklist_free(worklist_dev& w)
 // Setup-time only (one 8-byte D2H copy per tuple); a performance hint, never a correctness input.
 int classify(rpb200_halo_seg& s)
 {
+  if (s.flags & SEG_IDENTITY) { s.flags = SEG_IDENTITY; return 0; }      // set by the library only
   s.flags = 0;
   if (s.len >= 2) {
     int two[2];
@@ -369,7 +392,7 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   w.lens.resize(nsegs);
   int64_t chunks = 0;
   for (int s = 0; s < nsegs; ++s) {
-    if (segs[s].len < 0 || (segs[s].len > 0 && (!segs[s].buffer || !segs[s].list || !segs[s].var))) return RPB200_EINVAL;
+    if (segs[s].len < 0 || (segs[s].len > 0 && (!segs[s].buffer || !segs[s].var || (!segs[s].list && !(segs[s].flags & SEG_IDENTITY))))) return RPB200_EINVAL;
     { const int rc = classify(segs[s]); if (rc != 0) return rc; }
     w.flags.push_back(segs[s].flags);
     w.lens[s] = segs[s].len;
@@ -380,6 +403,7 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   }
   if (chunks > 0x7fffffffll) return RPB200_EINVAL;
   w.total_chunks = chunks;
+  w.first = first;
   const size_t nb = sizeof(rpb200_halo_seg) * (size_t)(nsegs > 0 ? nsegs : 1);
   RPB_CHECK(cudaMalloc(&w.d_segs, nb));
   RPB_CHECK(cudaMallocHost(&w.h_stage, nb));
@@ -402,21 +426,31 @@ struct exchange_args {
   int* error = nullptr;
 };
 
+// seg_lo < 0: the whole work list; else only the tuples [seg_lo, seg_hi)
 template <bool PACK, int MODE>
-int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const exchange_args& x, cudaStream_t st)
+int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const exchange_args& x, cudaStream_t st,
+                    int seg_lo = -1, int seg_hi = -1, int commit = 1)
 {
   if (w.total_chunks == 0) return 0;
+  int64_t chunk_lo = 0, chunk_hi = w.total_chunks;
+  if (seg_lo >= 0) {
+    if (seg_hi > w.nsegs || seg_lo >= seg_hi) return RPB200_EINVAL;
+    chunk_lo = w.first[seg_lo];
+    chunk_hi = seg_hi < w.nsegs ? w.first[seg_hi] : w.total_chunks;
+    if (chunk_hi == chunk_lo && !(MODE == 2 && commit)) return 0;        // empty tuples: nothing to launch
+  }
   const int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
   int64_t grid = (int64_t)ctx->sm_count * cps;
-  if (grid > w.total_chunks) grid = w.total_chunks;
+  if (grid > chunk_hi - chunk_lo) grid = chunk_hi - chunk_lo;
+  if (grid < 1) grid = 1;
   // tuning field `unroll` of the two halo kernels: 4 = L2 eviction-priority hints on, else off;
   // tuning field `block_size`: 128 = chunks dealt round-robin (c = b, b + grid, ...) instead of in
   // contiguous ranges, so the slow strided faces are spread over every CTA
   const bool hint = ctx->tune[kid].unroll == 4, strided = ctx->tune[kid].block_size == 128;
 #define RPB_HALO_LAUNCH(H, S)                                                                                  \
   halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
-      w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)w.total_chunks,   \
-      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error)
+      w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)chunk_hi,         \
+      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error, (int)chunk_lo, commit)
   if (hint && strided) RPB_HALO_LAUNCH(true, true);
   else if (hint) RPB_HALO_LAUNCH(true, false);
   else if (strided) RPB_HALO_LAUNCH(false, true);
@@ -482,7 +516,9 @@ struct rpb200_halo_plan {
   size_t recv_off[2][NNB];                 // byte offsets of receive slot l, generation g, in ANY rank's window
   std::vector<void*> peer_windows; std::vector<bool> peer_opened;
   worklist_dev xpack_wl[2], xunpack_wl[2];
-  halo_msg* d_pack_msgs = nullptr; halo_msg* d_unpack_msgs = nullptr;
+  worklist_dev xsend_wl[2];                // HALO_SENDRECV: identity puts of the caller's send buffers
+  bool send_bound = false;
+  halo_msg* d_pack_msgs = nullptr; halo_msg* d_unpack_msgs = nullptr; halo_msg* d_send_msgs = nullptr;
   unsigned int* d_msg_done = nullptr;
   int* d_error = nullptr;
   unsigned long long* d_epoch = nullptr;   // committed exchange epoch (device): reps done so far
@@ -499,7 +535,9 @@ extern "C" int rpb200_halo_worklist_create(rpb200_ctx* ctx, const rpb200_halo_se
   *out = nullptr;
   rpb200_halo_worklist* wl = new (std::nothrow) rpb200_halo_worklist();
   if (!wl) return (int)cudaErrorMemoryAllocation;
-  const int rc = worklist_build(wl->w, h_segs, nsegs);
+  std::vector<rpb200_halo_seg> clean(h_segs ? h_segs : nullptr, h_segs ? h_segs + (nsegs > 0 ? nsegs : 0) : nullptr);
+  for (rpb200_halo_seg& c : clean) c.flags = 0;                 // "filled by the library; pass 0"
+  const int rc = worklist_build(wl->w, clean.data(), nsegs);
   if (rc != 0) { worklist_free(wl->w); delete wl; return rc; }
   *out = wl;
   return 0;
@@ -550,11 +588,11 @@ extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
   if (!p) return;
   cudaFree(p->d_lists);
   worklist_free(p->pack_wl); worklist_free(p->unpack_wl);
-  for (int g = 0; g < 2; ++g) { worklist_free(p->xpack_wl[g]); worklist_free(p->xunpack_wl[g]); }
+  for (int g = 0; g < 2; ++g) { worklist_free(p->xpack_wl[g]); worklist_free(p->xunpack_wl[g]); worklist_free(p->xsend_wl[g]); }
   for (size_t r = 0; r < p->peer_windows.size(); ++r)
     if (p->peer_opened[r] && p->peer_windows[r]) cudaIpcCloseMemHandle(p->peer_windows[r]);
   cudaFree(p->d_window);
-  cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
+  cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_send_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
   cudaFree(p->d_epoch); cudaFree(p->d_unpack_done);
   delete p;
 }
@@ -697,7 +735,7 @@ extern "C" int rpb200_halo_plan_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
 extern "C" int rpb200_halo_exchange_window(rpb200_halo_plan* p, double* const* vars, void** d_window,
                                            size_t* bytes, unsigned char ipc_handle[64])
 {
-  if (!p || !vars) return RPB200_EINVAL;
+  if (!p) return RPB200_EINVAL;          // vars == NULL: a transport-only window (HALO_SENDRECV), no pack/unpack work lists
   if (!p->d_window) {
     size_t off = 256;
     for (int g = 0; g < 2; ++g)
@@ -720,7 +758,7 @@ extern "C" int rpb200_halo_exchange_window(rpb200_halo_plan* p, double* const* v
     RPB_CHECK(cudaMemset(p->d_unpack_done, 0, sizeof(unsigned int)));
     RPB_CHECK(cudaDeviceSynchronize());
   }
-  p->vars.assign(vars, vars + p->nvars);
+  if (vars) p->vars.assign(vars, vars + p->nvars); else p->vars.clear();
   if (d_window) *d_window = p->d_window;
   if (bytes) *bytes = p->window_bytes;
   if (ipc_handle) {
@@ -745,6 +783,7 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
       src[l] = (double*)(p->d_window + p->recv_off[g][l]);
     }
     worklist_free(p->xpack_wl[g]); worklist_free(p->xunpack_wl[g]);
+    if (p->vars.empty()) continue;               // transport-only window
     int rc = plan_segments(p, true, p->vars.data(), dst, segs);
     if (rc == 0) rc = worklist_build(p->xpack_wl[g], segs.data(), (int)segs.size());
     if (rc == 0) rc = plan_segments(p, false, p->vars.data(), src, segs);
@@ -811,19 +850,37 @@ static exchange_args plan_xargs(rpb200_halo_plan* p, bool pack)
 
 extern "C" int rpb200_halo_exchange_pack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
-  if (!p || !p->connected) return RPB200_EINVAL;
+  if (!p || !p->connected || p->vars.empty()) return RPB200_EINVAL;
   return worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xpack_wl[0], plan_xargs(p, true), rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_exchange_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
 {
-  if (!p || !p->connected) return RPB200_EINVAL;
+  if (!p || !p->connected || p->vars.empty()) return RPB200_EINVAL;
   return worklist_launch<false, 2>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xunpack_wl[0], plan_xargs(p, false), rpb_stream(s));
+}
+
+// The unfused HALO_EXCHANGE (comm/HALO_EXCHANGE-Cuda.cpp:26-123): one launch per (neighbour, variable) tuple.
+// The message flag is released by whichever launch completes the message's last chunk (the credit counters
+// persist across launches); `commit` marks the last unpack launch of the rep, which advances the epoch.
+extern "C" int rpb200_halo_exchange_pack_seg(rpb200_halo_plan* p, int l, int v, rpb200_stream_t s)
+{
+  if (!p || !p->connected || p->vars.empty() || l < 0 || l >= NNB || v < 0 || v >= p->nvars) return RPB200_EINVAL;
+  const int seg = l * p->nvars + v;
+  return worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xpack_wl[0], plan_xargs(p, true), rpb_stream(s), seg, seg + 1, 0);
+}
+
+extern "C" int rpb200_halo_exchange_unpack_seg(rpb200_halo_plan* p, int l, int v, int commit, rpb200_stream_t s)
+{
+  if (!p || !p->connected || p->vars.empty() || l < 0 || l >= NNB || v < 0 || v >= p->nvars) return RPB200_EINVAL;
+  const int seg = l * p->nvars + v;
+  return worklist_launch<false, 2>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xunpack_wl[0], plan_xargs(p, false), rpb_stream(s), seg, seg + 1,
+                                   commit ? 1 : 0);
 }
 
 extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
 {
-  if (!p || !p->connected) return RPB200_EINVAL;
+  if (!p || !p->connected || p->vars.empty()) return RPB200_EINVAL;
   const rpb_tuning& t = p->ctx->tune[RPB_K_HALO_EXCHANGE_FUSED];
   if (t.unroll == 2 || t.unroll == 4) {   // tuning field `unroll`: 2 / 4 = the two-launch form (pack + signal, then wait + unpack) without / with L2 hints
     const int rc = rpb200_halo_exchange_pack(p, s);
@@ -846,6 +903,61 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
   halo_exchange_kernel<<<(int)grid, HALO_BLOCK, 0, rpb_stream(s)>>>(P, U, p->d_pack_msgs, p->d_unpack_msgs, p->d_msg_done,
                                                                     p->d_epoch, p->d_unpack_done, p->d_error);
   RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- HALO_SENDRECV (comm/HALO_SENDRECV-Seq.cpp:34-52): transport only -----------------------------------
+extern "C" int rpb200_halo_sendrecv_bind(rpb200_halo_plan* p, double* const* send_buffers)
+{
+  if (!p || !p->connected || !send_buffers) return RPB200_EINVAL;
+  p->send_bound = false;
+  for (int g = 0; g < 2; ++g) {
+    worklist_free(p->xsend_wl[g]);
+    std::vector<rpb200_halo_seg> segs(NNB);
+    for (int l = 0; l < NNB; ++l) {
+      if (!send_buffers[l]) return RPB200_EINVAL;
+      rpb200_halo_seg& s = segs[l];
+      s.buffer = (double*)((unsigned char*)p->peer_windows[p->ranks[l]] + p->recv_off[g][p->opposite[l]]);
+      s.list = nullptr;
+      s.var = send_buffers[l];
+      s.len = (int64_t)p->nvars * p->pack_len[l];
+      s.msg = l;
+      s.flags = SEG_IDENTITY;
+    }
+    const int rc = worklist_build(p->xsend_wl[g], segs.data(), NNB);
+    if (rc != 0) return rc;
+  }
+  // the credit counters of a message count chunks of the whole message: one tuple per message here
+  std::vector<halo_msg> pm(NNB);
+  RPB_CHECK(cudaMemcpy(pm.data(), p->d_pack_msgs, sizeof(halo_msg) * NNB, cudaMemcpyDeviceToHost));
+  if (!p->d_send_msgs) RPB_CHECK(cudaMalloc(&p->d_send_msgs, sizeof(halo_msg) * NNB));
+  for (int l = 0; l < NNB; ++l)
+    pm[l].chunks = (unsigned int)(((int64_t)p->nvars * p->pack_len[l] + HALO_CHUNK - 1) / HALO_CHUNK);
+  RPB_CHECK(cudaMemcpy(p->d_send_msgs, pm.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
+  p->send_bound = true;
+  return 0;
+}
+
+extern "C" int rpb200_halo_sendrecv(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->connected || !p->send_bound) return RPB200_EINVAL;
+  exchange_args x = plan_xargs(p, true);
+  x.other_gen = &p->xsend_wl[1];
+  x.msgs = p->d_send_msgs;
+  const int rc = worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xsend_wl[0], x, rpb_stream(s));
+  if (rc != 0) return rc;
+  halo_wait_kernel<<<1, 32, 0, rpb_stream(s)>>>(p->d_unpack_msgs, p->d_epoch, p->d_error);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int rpb200_halo_recv_buffer(rpb200_halo_plan* p, int l, const double** d_ptr, int64_t* len)
+{
+  if (!p || !p->d_window || l < 0 || l >= NNB || !d_ptr) return RPB200_EINVAL;
+  unsigned long long epoch = 0;                       // committed reps: the last one wrote generation epoch & 1
+  RPB_CHECK(cudaMemcpy(&epoch, p->d_epoch, sizeof(epoch), cudaMemcpyDeviceToHost));
+  *d_ptr = (const double*)(p->d_window + p->recv_off[epoch & 1ull][l]);
+  if (len) *len = (int64_t)p->nvars * p->unpack_len[l];
   return 0;
 }
 

@@ -704,9 +704,15 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, ctx->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, ctx->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16)) return RPB200_EINVAL;
-  // 16 elements per 64-thread CTA, 4 CTAs per SM: the best of {32/128/2, 24/96/3, 16/64/5, 16/64/4} on B200
-  // (5493 / 5521 / 5541 / 5687 GB/s at NE = 4 M, profiles/r01_pa_variants.md)
-  RPB_CHECK((launch_mass<16, 64, 4>(ctx, D, X, Y, NE, st)));
+  // elements per CTA / threads / CTAs per SM: 8/32/8 is the best of the sweep in profiles/r01_pa_variants.md
+  switch (ctx->tune[RPB_K_MASS3DPA].unroll) {
+    case 10: RPB_CHECK((launch_mass<16, 64, 4>(ctx, D, X, Y, NE, st))); break;
+    case 12: RPB_CHECK((launch_mass<8, 64, 6>(ctx, D, X, Y, NE, st))); break;
+    case 13: RPB_CHECK((launch_mass<16, 128, 3>(ctx, D, X, Y, NE, st))); break;
+    case 14: RPB_CHECK((launch_mass<8, 32, 9>(ctx, D, X, Y, NE, st))); break;
+    case 15: RPB_CHECK((launch_mass<16, 64, 5>(ctx, D, X, Y, NE, st))); break;
+    default: RPB_CHECK((launch_mass<8, 32, 8>(ctx, D, X, Y, NE, st))); break;      // 5745 GB/s at NE = 4 M (16/64/4: 5660)
+  }
   RPB_LAUNCH_CHECK();
   return 0;
 }
@@ -722,7 +728,21 @@ extern "C" int rpb200_convection3dpa(rpb200_ctx* ctx, const double* Basis, const
   RPB_LAUNCH_CHECK();
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_conv, ctx->d_basis_tables, 36 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16) || !rpb_aligned(X, 16) || !rpb_aligned(Y, 16)) return RPB200_EINVAL;
-  RPB_CHECK((launch_ring_kernel<16, 256, 2, 2, 192>(convection3dpa_kernel<16, 256, 2, 2>, ctx, D, X, Y, NE, st)));
+  // tuning field `unroll` selects the launch shape {elements per CTA, threads, ring stages, CTAs per SM}
+  // (sweep: profiles/r01_pa_variants.md)
+#define RPB_CONV(E, B, S, M) RPB_CHECK((launch_ring_kernel<E, B, S, M, 192>(convection3dpa_kernel<E, B, S, M>, ctx, D, X, Y, NE, st)))
+  switch (ctx->tune[RPB_K_CONVECTION3DPA].unroll) {
+    case 10: RPB_CONV(16, 256, 2, 2); break;
+    case 11: RPB_CONV(8, 128, 2, 4); break;
+    case 12: RPB_CONV(8, 128, 2, 3); break;
+    case 13: RPB_CONV(8, 128, 3, 3); break;
+    case 14: RPB_CONV(16, 128, 2, 2); break;
+    case 15: RPB_CONV(8, 64, 2, 5); break;
+    case 16: RPB_CONV(4, 64, 2, 8); break;
+    case 17: RPB_CONV(16, 256, 3, 1); break;
+    default: RPB_CONV(8, 128, 2, 5); break;      // 6539 GB/s at NE = 4 M (8/128/2/4: 6028, 16/256/2/2: 5612)
+  }
+#undef RPB_CONV
   RPB_LAUNCH_CHECK();
   return 0;
 }

@@ -55,14 +55,15 @@ private:
 // the ranks sit on different GPUs).
 class HALO_EXCHANGE_FUSED : public HALO_base {
 public:
-  explicit HALO_EXCHANGE_FUSED(const RunParams& params);
+  explicit HALO_EXCHANGE_FUSED(const RunParams& params) : HALO_EXCHANGE_FUSED(rajaperf::Comm_HALO_EXCHANGE_FUSED, params) {}
   ~HALO_EXCHANGE_FUSED() override;
   void setUp(VariantID vid, size_t tune_idx) override;
   void updateChecksum(VariantID vid, size_t tune_idx) override;
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
-private:
+protected:
+  HALO_EXCHANGE_FUSED(KernelID kid, const RunParams& params);
   struct Rank {
     int device = 0;
     rpb200_ctx* c = nullptr;
@@ -72,6 +73,27 @@ private:
   std::vector<Rank> m_ranks;
   std::vector<rpb200_ctx*> m_dev_ctx;     // one context per device used
   int m_first_device = 0, m_num_devices = 1;
+};
+
+// HALO_SENDRECV (widened row; reference comm/HALO_SENDRECV.{hpp,cpp}): transport only.  Per rank 26 send buffers
+// (initData) are put into the neighbours' receive windows; the checksum is over what arrived.
+class HALO_SENDRECV : public HALO_EXCHANGE_FUSED {
+public:
+  explicit HALO_SENDRECV(const RunParams& params);
+  void setUp(VariantID vid, size_t tune_idx) override;
+  void updateChecksum(VariantID vid, size_t tune_idx) override;
+  void tearDown(VariantID vid, size_t tune_idx) override;
+  void enqueueRep(rpb200_stream_t s) override;
+private:
+  std::vector<std::vector<Real_ptr>> m_send;      // [rank][neighbour]
+};
+
+// The unfused exchange (widened row; reference comm/HALO_EXCHANGE.{hpp,cpp}, -Cuda.cpp:26-123): same data,
+// same result, one pack launch and one unpack launch per (neighbour, variable) on every rank.
+class HALO_EXCHANGE : public HALO_EXCHANGE_FUSED {
+public:
+  explicit HALO_EXCHANGE(const RunParams& params);
+  void enqueueRep(rpb200_stream_t s) override;
 };
 
 }  // namespace comm

@@ -9,7 +9,7 @@
 namespace rajaperf {
 namespace comm {
 
-HALO_EXCHANGE_FUSED::HALO_EXCHANGE_FUSED(const RunParams& params) : HALO_base(rajaperf::Comm_HALO_EXCHANGE_FUSED, params)
+HALO_EXCHANGE_FUSED::HALO_EXCHANGE_FUSED(KernelID kid, const RunParams& params) : HALO_base(kid, params)
 {
   setDefaultReps(200);
   setItsPerRep(m_num_vars * m_halo_elems * 2);

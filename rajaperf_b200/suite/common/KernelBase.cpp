@@ -91,7 +91,7 @@ void KernelBase::synchronize()
     const int first = run_params.getDevice();
     int ndev = 1;
     cudaGetDeviceCount(&ndev);
-    const int used = kernel_id == Comm_HALO_EXCHANGE_FUSED ? std::min(ndev - first, run_params.getNumRanks()) : 1;
+    const int used = (kernel_id == Comm_HALO_EXCHANGE_FUSED || kernel_id == Comm_HALO_EXCHANGE || kernel_id == Comm_HALO_SENDRECV) ? std::min(ndev - first, run_params.getNumRanks()) : 1;
     for (int d = 0; d < used; ++d) {
       cudaSetDevice(first + d);
       checkAbi(rpb200_device_synchronize(), "rpb200_device_synchronize");

@@ -19,7 +19,7 @@ static const std::string KernelNames[] = {
   "Stream_ADD", "Stream_COPY", "Stream_DOT", "Stream_MUL", "Stream_TRIAD",
   "Apps_CONVECTION3DPA", "Apps_DIFFUSION3DPA", "Apps_LTIMES", "Apps_MASS3DPA",
   "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS", "Algorithm_REDUCE_SUM", "Algorithm_MEMSET", "Algorithm_MEMCPY",
-  "Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED", "Comm_HALO_EXCHANGE_FUSED",
+  "Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED", "Comm_HALO_SENDRECV", "Comm_HALO_EXCHANGE", "Comm_HALO_EXCHANGE_FUSED",
   "Unknown Kernel"
 };
 
@@ -68,6 +68,8 @@ KernelBase* getKernelObject(KernelID kid, const RunParams& p)
     case Algorithm_MEMCPY: return new algorithm::MEMCPY(p);
     case Comm_HALO_PACKING: return new comm::HALO_PACKING(p);
     case Comm_HALO_PACKING_FUSED: return new comm::HALO_PACKING_FUSED(p);
+    case Comm_HALO_SENDRECV: return new comm::HALO_SENDRECV(p);
+    case Comm_HALO_EXCHANGE: return new comm::HALO_EXCHANGE(p);
     case Comm_HALO_EXCHANGE_FUSED: return new comm::HALO_EXCHANGE_FUSED(p);
     default: getCout() << "\n Unknown Kernel ID = " << kid << std::endl; return nullptr;
   }

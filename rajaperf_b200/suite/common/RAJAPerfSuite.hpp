@@ -23,7 +23,7 @@ enum KernelID {
   Stream_ADD, Stream_COPY, Stream_DOT, Stream_MUL, Stream_TRIAD,
   Apps_CONVECTION3DPA, Apps_DIFFUSION3DPA, Apps_LTIMES, Apps_MASS3DPA,
   Algorithm_SCAN, Algorithm_SORT, Algorithm_SORTPAIRS, Algorithm_REDUCE_SUM, Algorithm_MEMSET, Algorithm_MEMCPY,
-  Comm_HALO_PACKING, Comm_HALO_PACKING_FUSED, Comm_HALO_EXCHANGE_FUSED,
+  Comm_HALO_PACKING, Comm_HALO_PACKING_FUSED, Comm_HALO_SENDRECV, Comm_HALO_EXCHANGE, Comm_HALO_EXCHANGE_FUSED,
   NumKernels
 };
 

@@ -223,6 +223,129 @@ def test_halo_exchange_fused_many_ranks_on_one_gpu_bit_exact(ctx, pdims, dims, h
         plan.close()
 
 
+@pytest.mark.parametrize("pdims", [(1, 1, 1), (2, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("dims,hw,nv", [((6, 6, 6), 1, 3), ((20, 20, 20), 2, 2), ((64, 64, 64), 1, 3)])
+def test_halo_exchange_unfused_per_tuple_launches_bit_exact(ctx, pdims, dims, hw, nv):
+    """The unfused HALO_EXCHANGE: one pack launch and one unpack launch per (neighbour, variable); a rep of
+    unfused launches may follow a rep of fused ones (the epoch and the credit counters are shared)."""
+    P = pdims[0] * pdims[1] * pdims[2]
+    reps = 3
+    plans, dvars, wins = [], [], []
+    for r in range(P):
+        plan = ctx.halo_plan(dims, hw, nv, r, pdims)
+        vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
+        w, nbytes, _ = plan.window(vs, want_handle=False)
+        plans.append(plan); dvars.append(vs); wins.append(w)
+    for plan in plans:
+        plan.connect_ptrs(wins)
+    st = torch.cuda.current_stream().cuda_stream
+    for rep in range(reps):
+        if rep == 1:                       # one fused rep in the middle
+            for plan in plans: plan.exchange_pack()
+            for plan in plans: plan.exchange_unpack()
+            continue
+        for plan in plans:
+            for l in range(26):
+                for v in range(nv):
+                    assert plan.lib.rpb200_halo_exchange_pack_seg(plan.h, l, v, st) == 0
+        for plan in plans:
+            for l in range(26):
+                for v in range(nv):
+                    assert plan.lib.rpb200_halo_exchange_unpack_seg(plan.h, l, v, 1 if (l == 25 and v == nv - 1) else 0, st) == 0
+    torch.cuda.synchronize()
+    ref = simulate_exchange(dims, hw, nv, pdims, reps)
+    for r in range(P):
+        plans[r].status()
+        for v in range(nv):
+            assert np.array_equal(dvars[r][v].cpu().numpy().view(np.int64), ref[r][v].view(np.int64)), (r, v)
+    for plan in plans:
+        plan.close()
+
+
+@pytest.mark.parametrize("pdims", [(1, 1, 1), (2, 1, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("dims,hw,nv", [((6, 6, 6), 1, 3), ((20, 20, 20), 2, 2), ((64, 64, 64), 1, 3)])
+def test_halo_sendrecv_many_ranks_on_one_gpu_bit_exact(ctx, pdims, dims, hw, nv):
+    """HALO_SENDRECV: every rank's 26 send buffers land in the receive slot whose recv_tag matches
+    (HALO_SENDRECV-Seq.cpp:34-52); rank-specific contents make a misrouted message visible."""
+    P = pdims[0] * pdims[1] * pdims[2]
+    plans, sends, wins = [], [], []
+    for r in range(P):
+        plan = ctx.halo_plan(dims, hw, nv, r, pdims)
+        w, _, _ = plan.window(None, want_handle=False)                  # transport-only window
+        plans.append(plan); wins.append(w)
+    for plan in plans:
+        plan.connect_ptrs(wins)
+    for r, plan in enumerate(plans):
+        sb = [torch.arange(nv * nb["pack_len"], dtype=torch.float64, device="cuda") + 1000.0 * l + 1e6 * r
+              for l, nb in enumerate(plan.neighbors)]
+        plan.sendrecv_bind(sb); sends.append(sb)
+    for rep in range(3):
+        for r, plan in enumerate(plans):
+            for b in sends[r]:
+                b += 0.5                                                 # new payload every rep: stale generations would show
+        for plan in plans:
+            plan.sendrecv()
+    torch.cuda.synchronize()
+    for q, plan in enumerate(plans):
+        plan.status()
+        ranks, _, rtags = sd.halo_neighbors(q, pdims)
+        for l in range(26):
+            ptr, n = plan.recv_buffer(l)
+            assert n == nv * plan.neighbors[l]["unpack_len"]
+            got = np.empty(n)
+            import ctypes
+            assert plan.lib.rpb200_memcpy_d2h(got.ctypes.data_as(ctypes.c_void_p), ptr, 8 * n, None) == 0
+            torch.cuda.synchronize()
+            want = sends[ranks[l]][rtags[l]].cpu().numpy()
+            assert np.array_equal(got, want), (q, l)
+    for plan in plans:
+        plan.close()
+
+
+@pytest.mark.parametrize("size,reps,hw,nv", [(0, 1, 1, 3), (27000, 2, 2, 5)])
+def test_halo_sendrecv_suite_checksum_single_rank(ctx, size, reps, hw, nv):
+    """KernelBase flow of Comm_HALO_SENDRECV on one rank against the oracle's whole-kernel driver."""
+    from rajaperf_b200 import cabi
+    dims = cabi.halo_grid_dims(size or 1000000)
+    plan = ctx.halo_plan(dims, hw, nv)
+    plan.window(None, want_handle=False); plan.connect_ptrs([0])
+    L = oracle.lib()
+    L.orc_reset_init_count()
+    dummy = np.zeros(1)
+    for _ in range(52):
+        L.orc_init_const(dummy, 0, 0.0)                                  # setUp_base: 52 list allocations
+    sb = []
+    for nb in plan.neighbors:
+        a = np.empty(nv * nb["pack_len"]); L.orc_init_real(a, a.size); sb.append(torch.from_numpy(a).cuda())
+    plan.sendrecv_bind(sb)
+    for _ in range(reps):
+        plan.sendrecv()
+    torch.cuda.synchronize(); plan.status()
+    ck = np.longdouble(0)
+    import ctypes
+    for l in range(26):
+        ptr, n = plan.recv_buffer(l)
+        got = np.empty(n)
+        assert plan.lib.rpb200_memcpy_d2h(got.ctypes.data_as(ctypes.c_void_p), ptr, 8 * n, None) == 0
+        torch.cuda.synchronize()
+        ck += oracle.checksum(got)
+    ref = oracle.kat("Comm_HALO_SENDRECV", size, reps, [hw, nv, 1, 1, 1])
+    assert abs(ck - ref) <= abs(ref) * np.longdouble(4e-19), (ck, ref)
+    plan.close()
+
+
+def test_halo_exchange_seg_rejects_bad_arguments(ctx):
+    plan = ctx.halo_plan((6, 6, 6), 1, 2)
+    vs = [torch.zeros(plan.var_size, dtype=torch.float64, device="cuda") for _ in range(2)]
+    st = torch.cuda.current_stream().cuda_stream
+    assert plan.lib.rpb200_halo_exchange_pack_seg(plan.h, 0, 0, st) != 0          # not connected yet
+    plan.window(vs, want_handle=False); plan.connect_ptrs([0])
+    for l, v in ((-1, 0), (26, 0), (0, 2), (0, -1)):
+        assert plan.lib.rpb200_halo_exchange_pack_seg(plan.h, l, v, st) != 0
+        assert plan.lib.rpb200_halo_exchange_unpack_seg(plan.h, l, v, 0, st) != 0
+    plan.close()
+
+
 @pytest.mark.parametrize("size,reps,hw,nv", [(0, 1, 1, 3), (0, 3, 1, 3), (27000, 2, 2, 5)])
 def test_halo_exchange_fused_suite_checksum_single_rank(ctx, size, reps, hw, nv):
     """KernelBase flow of Comm_HALO_EXCHANGE_FUSED on one rank (periodic self-exchange) against the

@@ -91,14 +91,26 @@ def test_checkrun_checksum_matches_reference_base_seq(case, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["Comm_HALO_EXCHANGE_FUSED", "Comm_HALO_EXCHANGE"])
 @pytest.mark.parametrize("division", [(1, 1, 1), (2, 1, 1), (2, 2, 2)])
-def test_halo_exchange_fused_rank_grids_match_oracle(division, tmp_path):
+def test_halo_exchange_fused_rank_grids_match_oracle(kernel, division, tmp_path):
     """No MPI in the reference build here, so the oracle's P-rank restatement is the checker."""
-    args = ["--checkrun", "2", "--disable-warmup", "-k", "HALO_EXCHANGE_FUSED", "--size", "27000", "--halo_width", "2",
+    args = ["--checkrun", "2", "--disable-warmup", "-k", kernel, "--size", "27000", "--halo_width", "2",
             "--halo_num_vars", "2", "--mpi_3d_division"] + [str(d) for d in division]
     run_exe(args, tmp_path)
     got = read_checksum(tmp_path)
     ref = oracle.kat("Comm_HALO_EXCHANGE_FUSED", 27000, 2, [2, 2] + list(division))
+    assert abs(got - ref) <= abs(ref) * np.longdouble(1e-18), (got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("division", [(1, 1, 1), (2, 2, 1)])
+def test_halo_sendrecv_rank_grids_match_oracle(division, tmp_path):
+    args = ["--checkrun", "3", "--disable-warmup", "-k", "Comm_HALO_SENDRECV", "--size", "27000", "--halo_width", "2",
+            "--halo_num_vars", "2", "--mpi_3d_division"] + [str(d) for d in division]
+    run_exe(args, tmp_path)
+    got = read_checksum(tmp_path)
+    ref = oracle.kat("Comm_HALO_SENDRECV", 27000, 3, [2, 2] + list(division))
     assert abs(got - ref) <= abs(ref) * np.longdouble(1e-18), (got, ref)
 
 
