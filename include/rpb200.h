@@ -203,7 +203,10 @@ int  rpb200_halo_exchange_unpack_seg(rpb200_halo_plan*, int l, int v, int commit
  * bind() after rpb200_halo_exchange_connect*.  rpb200_halo_recv_buffer returns where message l of the last completed rep
  * lies in this rank's window (it synchronises; the location alternates between two generations).                  */
 int  rpb200_halo_sendrecv_bind(rpb200_halo_plan*, double* const* d_send_buffers);
-int  rpb200_halo_sendrecv(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_sendrecv(rpb200_halo_plan*, rpb200_stream_t);            /* = put, then wait */
+/* the two halves, for hosts that drive several ranks through ONE stream (all puts must be queued before a wait spins) */
+int  rpb200_halo_sendrecv_put(rpb200_halo_plan*, rpb200_stream_t);
+int  rpb200_halo_sendrecv_wait(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_recv_buffer(rpb200_halo_plan*, int l, const double** d_ptr, int64_t* len);
 int  rpb200_halo_exchange(rpb200_halo_plan*, rpb200_stream_t);
 /* 0, or RPB200_ETIMEDOUT if an unpack CTA gave up waiting for a flag (synchronises)        */

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rpb200_halo_exchange_unpack_seg": (c_int, [_P, c_int, c_int, c_int, _P]),
     "rpb200_halo_sendrecv_bind": (c_int, [_P, POINTER(_P)]),
     "rpb200_halo_sendrecv": (c_int, [_P, _P]),
+    "rpb200_halo_sendrecv_put": (c_int, [_P, _P]),
+    "rpb200_halo_sendrecv_wait": (c_int, [_P, _P]),
     "rpb200_halo_recv_buffer": (c_int, [_P, c_int, POINTER(_P), POINTER(c_int64)]),
     "rpb200_halo_exchange": (c_int, [_P, _P]),
     "rpb200_halo_exchange_status": (c_int, [_P]),
@@ -392,6 +394,12 @@ class HaloPlan:
 
     def sendrecv(self):
         check(self.lib.rpb200_halo_sendrecv(self.h, _stream()), "halo_sendrecv")
+
+    def sendrecv_put(self):
+        check(self.lib.rpb200_halo_sendrecv_put(self.h, _stream()), "halo_sendrecv_put")
+
+    def sendrecv_wait(self):
+        check(self.lib.rpb200_halo_sendrecv_wait(self.h, _stream()), "halo_sendrecv_wait")
 
     def recv_buffer(self, l):
         """(device pointer, length in doubles) of message l of the last completed rep."""

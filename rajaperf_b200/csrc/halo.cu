@@ -938,17 +938,27 @@ extern "C" int rpb200_halo_sendrecv_bind(rpb200_halo_plan* p, double* const* sen
   return 0;
 }
 
-extern "C" int rpb200_halo_sendrecv(rpb200_halo_plan* p, rpb200_stream_t s)
+extern "C" int rpb200_halo_sendrecv_put(rpb200_halo_plan* p, rpb200_stream_t s)
 {
   if (!p || !p->connected || !p->send_bound) return RPB200_EINVAL;
   exchange_args x = plan_xargs(p, true);
   x.other_gen = &p->xsend_wl[1];
   x.msgs = p->d_send_msgs;
-  const int rc = worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xsend_wl[0], x, rpb_stream(s));
-  if (rc != 0) return rc;
+  return worklist_launch<true, 1>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, p->xsend_wl[0], x, rpb_stream(s));
+}
+
+extern "C" int rpb200_halo_sendrecv_wait(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->connected || !p->send_bound) return RPB200_EINVAL;
   halo_wait_kernel<<<1, 32, 0, rpb_stream(s)>>>(p->d_unpack_msgs, p->d_epoch, p->d_error);
   RPB_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int rpb200_halo_sendrecv(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  const int rc = rpb200_halo_sendrecv_put(p, s);
+  return rc != 0 ? rc : rpb200_halo_sendrecv_wait(p, s);
 }
 
 extern "C" int rpb200_halo_recv_buffer(rpb200_halo_plan* p, int l, const double** d_ptr, int64_t* len)

@@ -62,9 +62,14 @@ void HALO_SENDRECV::setUp(VariantID, size_t)
 
 void HALO_SENDRECV::enqueueRep(rpb200_stream_t s)
 {
+  // ranks may share a GPU and its stream: every put is queued before the first wait spins
   for (Rank& rk : m_ranks) {
     cudaSetDevice(rk.device);
-    checkAbi(rpb200_halo_sendrecv(rk.plan, s), "rpb200_halo_sendrecv");
+    checkAbi(rpb200_halo_sendrecv_put(rk.plan, s), "rpb200_halo_sendrecv_put");
+  }
+  for (Rank& rk : m_ranks) {
+    cudaSetDevice(rk.device);
+    checkAbi(rpb200_halo_sendrecv_wait(rk.plan, s), "rpb200_halo_sendrecv_wait");
   }
   cudaSetDevice(m_first_device);
 }

@@ -283,8 +283,10 @@ def test_halo_sendrecv_many_ranks_on_one_gpu_bit_exact(ctx, pdims, dims, hw, nv)
         for r, plan in enumerate(plans):
             for b in sends[r]:
                 b += 0.5                                                 # new payload every rep: stale generations would show
+        for plan in plans:                      # ranks share one stream here: all puts before the first wait spins
+            plan.sendrecv_put()
         for plan in plans:
-            plan.sendrecv()
+            plan.sendrecv_wait()
     torch.cuda.synchronize()
     for q, plan in enumerate(plans):
         plan.status()
