@@ -8,7 +8,7 @@
 // interface fidelity and has no effect, exactly as in the reference.
 // This is the one genuinely dense FP64 contraction on the path (north_star), so it runs on
 // mma.sync.m8n8k4.f64 (tcgen05 has no FP64 kind):
-//   * CTA tile 128x64x16 (8 warps, 2 CTAs/SM) for large C, 64x64x16 (4 warps, 4 CTAs/SM) otherwise; 3-stage cp.async ring (zero-filled at the ragged edges), A kept
+//   * CTA tile 64x64x16, 4 warps of 32x32, 4 CTAs per SM (other tilings stay selectable as tunings); 3-stage cp.async ring (zero-filled at the ragged edges), A kept
 //     [m][k] and B [k][n] exactly as they lie in global memory (no transposes);
 //   * padded leading dimensions (GK+4 and BN+4 doubles) make every fragment load -- one LDS.64 per
 //     lane per 8x4 / 4x8 fragment -- bank-conflict-free;
@@ -19,7 +19,6 @@
 
 namespace {
 
-constexpr int GSTAGES = 3;
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 {
@@ -39,8 +38,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // VEC = doubles per cp.async (2 when every row start is 16-byte aligned, else 1)
-template <int BM, int BN, int WM, int WN, int GK, int VEC>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+template <int BM, int BN, int WM, int WN, int GK, int VEC, int GSTAGES, int MINB>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB)
 gemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, double* __restrict__ C,
                  int ni, int nj, int nk, double alpha)
 {
@@ -148,18 +147,15 @@ gemm_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B, dou
   }
 }
 
-template <int BM, int BN, int WM, int WN, int GK, int VEC>
+template <int BM, int BN, int WM, int WN, int GK, int VEC, int GSTAGES = 3, int MINB = 1>
 int gemm_launch(const double* A, const double* B, double* C, int ni, int nj, int nk, double alpha, cudaStream_t st)
 {
   constexpr int THREADS = (BM / WM) * (BN / WN) * 32;
   constexpr size_t smem = sizeof(double) * GSTAGES * (BM * (GK + 4) + GK * (BN + 4));
-  static bool attr_done = false;
-  if (!attr_done) {
-    RPB_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // per call: the attribute belongs to the current device's context, and a process may hold several contexts
+  RPB_CHECK(cudaFuncSetAttribute(gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC, GSTAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((nj + BN - 1) / BN, (ni + BM - 1) / BM);
-  gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC><<<grid, THREADS, smem, st>>>(A, B, C, ni, nj, nk, alpha);
+  gemm_dmma_kernel<BM, BN, WM, WN, GK, VEC, GSTAGES, MINB><<<grid, THREADS, smem, st>>>(A, B, C, ni, nj, nk, alpha);
   RPB_LAUNCH_CHECK();
   return 0;
 }
@@ -181,12 +177,25 @@ extern "C" int rpb200_polybench_gemm(rpb200_ctx* ctx, const double* A, const dou
   // 128 = 128x128 (8 warps of 64x32), 160 = 128x128 (16 warps of 32x32); anything else = automatic
   const int64_t big_tiles = ((ni + 127) / 128) * ((nj + 127) / 128);
   int tile = ctx->tune[RPB_K_POLYBENCH_GEMM].block_size;
-  if (tile != 64 && tile != 96 && tile != 128 && tile != 160) tile = (big_tiles >= 8 * (int64_t)ctx->sm_count ? 96 : 64);   // profiles/r01_widened.md
+  if (tile != 64 && tile != 96 && tile != 128 && tile != 160) tile = 0;     // automatic: 64x64x16, 3 stages, 4 CTAs/SM (profiles/r01_widened.md)
+  (void)big_tiles;
   const int i = (int)ni, j = (int)nj, k = (int)nk;
   const bool k32 = ctx->tune[RPB_K_POLYBENCH_GEMM].unroll == 8;       // tuning field `unroll`: 8 = 32-deep stages, else 16
 #define RPB_GEMM(BM, BN, WM, WN)                                                                                         \
   (k32 ? (vec ? gemm_launch<BM, BN, WM, WN, 32, 2>(A, B, C, i, j, k, alpha, st) : gemm_launch<BM, BN, WM, WN, 32, 1>(A, B, C, i, j, k, alpha, st)) \
        : (vec ? gemm_launch<BM, BN, WM, WN, 16, 2>(A, B, C, i, j, k, alpha, st) : gemm_launch<BM, BN, WM, WN, 16, 1>(A, B, C, i, j, k, alpha, st)))
+  // experiment shapes (tuning `unroll` 20..): 2-stage rings with more CTAs per SM
+  switch (ctx->tune[RPB_K_POLYBENCH_GEMM].unroll) {
+    case 20: return vec ? gemm_launch<64, 64, 32, 32, 16, 2, 2, 5>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 32, 16, 1, 2, 5>(A, B, C, i, j, k, alpha, st);
+    case 21: return vec ? gemm_launch<64, 64, 32, 32, 16, 2, 2, 6>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 32, 16, 1, 2, 6>(A, B, C, i, j, k, alpha, st);
+    case 22: return vec ? gemm_launch<64, 64, 32, 32, 32, 2, 2, 3>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 32, 32, 1, 2, 3>(A, B, C, i, j, k, alpha, st);
+    case 23: return vec ? gemm_launch<128, 64, 32, 32, 16, 2, 2, 3>(A, B, C, i, j, k, alpha, st) : gemm_launch<128, 64, 32, 32, 16, 1, 2, 3>(A, B, C, i, j, k, alpha, st);
+    case 24: return vec ? gemm_launch<64, 64, 32, 32, 16, 2, 3, 4>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 32, 16, 1, 3, 4>(A, B, C, i, j, k, alpha, st);
+    case 25: return vec ? gemm_launch<64, 64, 32, 16, 16, 2, 3, 4>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 16, 16, 1, 3, 4>(A, B, C, i, j, k, alpha, st);
+    default: break;
+  }
+  if (tile == 0)
+    return vec ? gemm_launch<64, 64, 32, 32, 16, 2, 3, 4>(A, B, C, i, j, k, alpha, st) : gemm_launch<64, 64, 32, 32, 16, 1, 3, 4>(A, B, C, i, j, k, alpha, st);
   switch (tile) {
     case 160: return RPB_GEMM(128, 128, 32, 32);
     case 128: return RPB_GEMM(128, 128, 64, 32);

@@ -886,11 +886,9 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
     const int rc = rpb200_halo_exchange_pack(p, s);
     return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
   }
-  static int resident = 0;      // CTAs of the fused kernel that fit one SM: the grid must be fully co-resident
-  if (!resident) {
-    RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_exchange_kernel, HALO_BLOCK, 0));
-    if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
-  }
+  int resident = 0;             // CTAs of the fused kernel that fit one SM: the grid must be fully co-resident
+  RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_exchange_kernel, HALO_BLOCK, 0));
+  if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
   int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 4;
   if (cps > resident) cps = resident;
   const worklist_dev& pw = p->xpack_wl[0]; const worklist_dev& uw = p->xunpack_wl[0];

@@ -284,13 +284,10 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
   if (!rpb_tma::make_row_map(&map, x, rows, IT_BOX_ROWS)) return 0;
 
   const size_t smem = sizeof(il_smem) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
-    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // per call: the attribute belongs to the current device's context, and a process may hold several contexts
+  if (lbw == 4) RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else if (lbw == 2) RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count;
   if (grid > tiles) grid = (int)tiles;
   if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);

@@ -378,13 +378,10 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
 
   const size_t smem = sizeof(unsigned long long) * SORT_TILE + sizeof(unsigned int) * SORT_WARPS * RADIX +
                       sizeof(unsigned int) * RADIX + sizeof(long long) * RADIX + (PAIRS ? SORT_TILE : 0);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[PAIRS ? 1 : 0]) {
-    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[PAIRS ? 1 : 0] = true;
-  }
+  // per call: the attribute belongs to the current device's context, and a process may hold several contexts
+  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
   unsigned long long* kin = (unsigned long long*)keys; unsigned long long* kout = alt_keys;
   unsigned long long* vin = (unsigned long long*)vals; unsigned long long* vout = alt_vals;

@@ -126,14 +126,16 @@ if "indexlist" in which:
     del x, lst
 
 if "gemm" in which:
-    for ni, cfgs in ((1000, ((64, 4), (64, 8), (96, 4))), (4096, ((64, 4), (64, 8), (96, 4), (96, 8), (128, 8), (160, 8))), (8192, ((96, 4), (96, 8), (160, 8)))):
+    shapes = [("64x64x16 s3 (auto small)", 64, 4), ("128x64x16 s3 (auto large)", 96, 4), ("64x64x16 s2 5cta", 64, 20), ("64x64x16 s2 6cta", 64, 21),
+              ("64x64x32 s2 3cta", 64, 22), ("128x64x16 s2 3cta", 64, 23), ("64x64x16 s3 4cta", 64, 24), ("64x64x16 s3 8 warps of 32x16", 64, 25)]
+    for ni in (1000, 4096, 8192):
         nj, nk = ni, int(1.2 * ni)
         A = torch.rand(ni * nk, **f64); B = torch.rand(nk * nj, **f64); C = torch.empty(ni * nj, **f64)
-        for t, u in cfgs:
+        for label, t, u in shapes:
             ctx.set_tuning("Polybench_GEMM", t, -1, u)
-            ms = time_ms(lambda: ctx.polybench_gemm(A, B, C, ni, nj, nk, 0.62), 10)
-            report(f"gemm {ni}x{nj}x{nk} tile={t} gk={16 if u != 8 else 32}", 8 * (ni * nk + nk * nj + ni * nj), ms, tflops=2.0 * ni * nj * nk / ms / 1e9)
-        ms = time_ms(lambda: torch.mm(A.view(ni, nk), B.view(nk, nj), out=C.view(ni, nj)), 10)
+            ms = time_ms(lambda: ctx.polybench_gemm(A, B, C, ni, nj, nk, 0.62), 10 if ni < 8192 else 4)
+            report(f"gemm {ni}x{nj}x{nk} {label}", 8 * (ni * nk + nk * nj + ni * nj), ms, tflops=2.0 * ni * nj * nk / ms / 1e9)
+        ms = time_ms(lambda: torch.mm(A.view(ni, nk), B.view(nk, nj), out=C.view(ni, nj)), 10 if ni < 8192 else 4)
         report(f"gemm {ni} cuBLAS dgemm (incumbent)", 8 * (ni * nk + nk * nj + ni * nj), ms, tflops=2.0 * ni * nj * nk / ms / 1e9)
         ctx.set_tuning("Polybench_GEMM", 256, -1, 4)
         del A, B, C
