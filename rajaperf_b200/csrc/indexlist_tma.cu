@@ -4,13 +4,14 @@
 // shared-memory ring by cp.async.bulk.tensor, dedicated look-back warps, mbarrier hand-offs only), with
 // the per-tile work of the index list.  A tile is only 64 KB of reads (1.5 us of one SM's share of HBM),
 // less than one look-back round trip, so the roles are split further than in the scan: warp 0 only
-// produces (full/empty ring), and TWO look-back warps take alternate tiles:
+// produces (full/empty ring), THREE look-back warps take every third tile, and the compute warps run two
+// tiles ahead of the one they are waiting for:
 //   * A(k): a compute thread reads its 16 contiguous doubles from the ring and keeps ONE register of them,
 //     the 16-bit mask of x[i] < 0.0; warp-shuffle scan of the popcounts; the stage is free again as soon
 //     as the 16 warps have done this (the look-back never holds a stage);
 //   * a look-back warp resolves the tile's exclusive prefix by decoupled look-back over 8-byte
 //     {epoch | status | count} descriptors and hands every warp its output offset;
-//   * B(k), software-pipelined behind A(k+1): each warp compacts its (<= 512) selected indices in its own
+//   * B(k), software-pipelined behind A(k+1) and A(k+2): each warp compacts its (<= 512) selected indices in its own
 //     2 KB shared-memory slice (__syncwarp only) and writes them as one contiguous, coalesced run.
 // Traffic stays algorithmic: 8 B read per element + 4 B written per selected element.
 #include "common.cuh"
@@ -21,7 +22,8 @@
 namespace {
 
 constexpr int IT_WARPS = 16;
-constexpr int IT_THREADS = (IT_WARPS + 3) * 32;    // + producer warp 0 + look-back warps 17, 18
+constexpr int IT_SLOTS = 3;                        // tiles a CTA may have between A (count) and B (write): look-back depth
+constexpr int IT_THREADS = (IT_WARPS + 1 + IT_SLOTS) * 32;    // + producer warp 0 + look-back warps 17..19
 constexpr int IT_IPT = 16;
 constexpr int IT_ROWS = IT_WARPS * 32;            // 512 rows of 16 doubles
 constexpr int IT_TILE = IT_ROWS * IT_IPT;         // 8192 elements = 64 KiB
@@ -46,13 +48,13 @@ struct il_smem {
   int slice[IT_WARPS][32 * IT_IPT];                  // per-warp compaction buffer
   unsigned long long full[IT_STAGES];
   unsigned long long empty[IT_STAGES];               // 16 compute warps are done reading the stage
-  unsigned long long agg_ready[2];
-  unsigned long long prefix_ready[2];
-  unsigned int wtot[2][IT_WARPS];
-  unsigned int woff[2][IT_WARPS];
+  unsigned long long agg_ready[IT_SLOTS];
+  unsigned long long prefix_ready[IT_SLOTS];
+  unsigned int wtot[IT_SLOTS][IT_WARPS];
+  unsigned int woff[IT_SLOTS][IT_WARPS];
   unsigned int tile_id[IT_STAGES];
-  unsigned int lb_tile[2];                           // tile of the sequence number a look-back warp is handed
-  unsigned int arrived[2];
+  unsigned int lb_tile[IT_SLOTS];                           // tile of the sequence number a look-back warp is handed
+  unsigned int arrived[IT_SLOTS];
 };
 
 // IT_LBW = descriptors per lane per look-back round; dstride = distance between descriptors in 8-byte words
@@ -69,7 +71,7 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < IT_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], IT_WARPS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&S.agg_ready[s], IT_WARPS); mbar_init(&S.prefix_ready[s], 1); S.arrived[s] = 0u; }
+    for (int s = 0; s < IT_SLOTS; ++s) { mbar_init(&S.agg_ready[s], IT_WARPS); mbar_init(&S.prefix_ready[s], 1); S.arrived[s] = 0u; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -106,11 +108,11 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
     // ---------------------------------------------------------------- look-back warps: tiles k = slot, slot + 2, ...
     // (they never touch the stage ring: the compute warps hand them the tile number with agg_ready, and
     //  cannot run two sequence numbers ahead of a look-back warp, so the barrier phases cannot alias)
-    // num_lb == 1: warp 17 alone takes every tile (experiment switch, RPB200_IL_NLB)
+    // num_lb == 1: warp 17 alone takes every tile (experiment switch, RPB200_IL_NLB); else one warp per slot
     if (num_lb == 1 && warp != IT_WARPS + 1) return;
     for (int k = warp - IT_WARPS - 1;; k += num_lb) {
-      const int slot = k & 1;
-      mbar_wait(&S.agg_ready[slot], (k >> 1) & 1);
+      const int slot = k % IT_SLOTS;
+      mbar_wait(&S.agg_ready[slot], (k / IT_SLOTS) & 1);
       const unsigned int tile = S.lb_tile[slot];
       if (tile == IT_INVALID) break;
       const unsigned int wt = (lane < IT_WARPS) ? S.wtot[slot][lane] : 0u;
@@ -174,7 +176,7 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
   unsigned int tile = IT_INVALID, ntile = IT_INVALID;
 
   auto stage_A = [&](int k, unsigned int& m, unsigned int& lexcl, unsigned int& wsum, unsigned int& t) {
-    const int st = k % IT_STAGES, slot = k & 1;
+    const int st = k % IT_STAGES, slot = k % IT_SLOTS;
     mbar_wait(&S.full[st], (k / IT_STAGES) & 1);
     t = S.tile_id[st];
     if (t == IT_INVALID) {              // end of the stream: release the look-back warp of this sequence number
@@ -216,12 +218,17 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
     if (lane == 0) { S.lb_tile[slot] = t; mbar_arrive(&S.empty[st]); mbar_arrive(&S.agg_ready[slot]); }
   };
 
+  // Software pipeline of depth 2: the counts of tiles k+1 and k+2 are taken (and their look-backs started) before
+  // this warp waits for the prefix of tile k, so a look-back has two tile times (~3.6 us) to resolve.
   int* __restrict__ slice = &S.slice[cw][0];
+  unsigned int mask2 = 0, lane_excl2 = 0, wtotal2 = 0, tile2 = IT_INVALID;
   stage_A(0, mask, lane_excl, wtotal, tile);
+  if (tile != IT_INVALID) stage_A(1, nmask, n_lane_excl, n_wtotal, ntile);
   int k = 0;
   for (; tile != IT_INVALID; ++k) {
-    stage_A(k + 1, nmask, n_lane_excl, n_wtotal, ntile);         // overlaps the look-back of tile k
-    const int slot = k & 1;
+    tile2 = IT_INVALID;
+    if (ntile != IT_INVALID) stage_A(k + 2, mask2, lane_excl2, wtotal2, tile2);      // never past the terminating sequence number
+    const int slot = k % IT_SLOTS;
     // compact this warp's indices into its slice while the prefix is being resolved
     {
       unsigned int at = lane_excl, m = mask;
@@ -233,14 +240,16 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
       }
     }
     __syncwarp();
-    mbar_wait(&S.prefix_ready[slot], (k >> 1) & 1);
+    mbar_wait(&S.prefix_ready[slot], (k / IT_SLOTS) & 1);
     int* __restrict__ out = list + S.woff[slot][cw];
     for (unsigned int q = lane; q < wtotal; q += 32) out[q] = slice[q];
     __syncwarp();                                                // the slice is rewritten by the next tile
     mask = nmask; lane_excl = n_lane_excl; wtotal = n_wtotal; tile = ntile;
+    nmask = mask2; n_lane_excl = lane_excl2; n_wtotal = wtotal2; ntile = tile2;
   }
-  // sequence number k was the terminating one (its look-back warp is released); release the other one too
-  if (lane == 0) { S.lb_tile[(k + 1) & 1] = IT_INVALID; mbar_arrive(&S.agg_ready[(k + 1) & 1]); }
+  // sequence number k was the terminating one (the look-back warp of its slot is released); release the others too
+  if (lane == 0)
+    for (int d = 1; d < IT_SLOTS; ++d) { S.lb_tile[(k + d) % IT_SLOTS] = IT_INVALID; mbar_arrive(&S.agg_ready[(k + d) % IT_SLOTS]); }
 }
 
 // the n % 16 elements after the last full row + the length (m_len): count so far = inclusive prefix of the last tile
@@ -268,12 +277,12 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
   if (rows < (int64_t)IT_ROWS * ctx->sm_count * 2) return 0;
   if (!rpb_aligned(x, 16) || rows > 0x7fffffffll) return 0;
   const int64_t tiles = (rows + IT_ROWS - 1) / IT_ROWS;
-  static int lbw = -1, dstride = -1, backoff = 0, nlb = 2;
+  static int lbw = -1, dstride = -1, backoff = 0, nlb = IT_SLOTS;
   if (lbw < 0) {
     const char* e = getenv("RPB200_IL_LBW"); lbw = e ? atoi(e) : 1;
     e = getenv("RPB200_IL_DSTRIDE"); dstride = e ? atoi(e) : 16;
     e = getenv("RPB200_IL_BACKOFF"); backoff = e ? atoi(e) : 0;
-    e = getenv("RPB200_IL_NLB"); nlb = (e && atoi(e) == 1) ? 1 : 2;
+    e = getenv("RPB200_IL_NLB"); nlb = (e && atoi(e) == 1) ? 1 : IT_SLOTS;
     if (lbw != 1 && lbw != 2 && lbw != 4) lbw = 1;
     if (dstride < 1) dstride = 1;
   }
