@@ -71,7 +71,6 @@ if "halo" in which:
 if "gemm" in which:
     ni = nj = 4096; nk = 4915
     A = torch.rand(ni * nk, **f64); B = torch.rand(nk * nj, **f64); C = torch.empty(ni * nj, **f64)
-    ctx.set_tuning("Polybench_GEMM", 96, -1, 4)
     ctx.polybench_gemm(A, B, C, ni, nj, nk, 0.62)
     torch.cuda.synchronize()
 if "indexlist" in which:
