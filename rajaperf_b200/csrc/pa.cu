@@ -45,7 +45,9 @@ __constant__ double c_diff[48];      // B[q][d] | G*sign [q][d] | Bt[d][q] | Gt*
 // (cp.async.bulk + mbarrier: the TMA path, no registers, no LSU queue) into a 2-stage shared-memory
 // ring, one batch of E elements ahead of the math; the X slab of the NEXT batch is prefetched into
 // registers while the current batch is in stages B and C, and the Y slab is requested before stage B.
-template <int E, int BLOCK, int MINB>
+// YRING: the Y slab of the next batch is staged too -- every stage-A/C thread bulk-copies its own 128-byte (e, dz) row
+// into a 144-byte-pitched shared-memory row (conflict-free 128-bit reads) -- instead of being loaded through the LSU.
+template <int E, int BLOCK, int MINB, bool YRING>
 __global__ void __launch_bounds__(BLOCK, MINB)
 mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
                 int64_t NE)
@@ -58,7 +60,9 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   extern __shared__ __align__(128) unsigned char pa_smem[];
   double* Ds = reinterpret_cast<double*>(pa_smem);                         // [2][E*125]
   double* T = Ds + 2 * E * 125;                                            // [E*4][25], stride 25 (odd)
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(T + E * ND * SLAB);   // [2]
+  constexpr int YPITCH = 18;                                               // doubles: 16 + 2 pad = 144 bytes
+  double* Yr = T + E * ND * SLAB;                                          // [2][E*4][YPITCH]   (YRING only)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(Yr + (YRING ? 2 * E * ND * YPITCH : 0));   // [2]
 
   const int t = threadIdx.x;
   const int64_t nbatch = (NE + E - 1) / E;
@@ -73,11 +77,16 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   auto issue_D = [&](int64_t batch, int stage) {          // thread 0 only
     const int64_t e0 = batch * E;
     if (NE - e0 >= E) {
-      mbar_arrive_expect_tx(&full[stage], DBYTES);
+      mbar_arrive_expect_tx(&full[stage], DBYTES + (YRING ? E * ND * 128u : 0u));
       bulk_g2s(Ds + stage * E * 125, D + e0 * 125, DBYTES, &full[stage]);
     } else {
       mbar_arrive(&full[stage]);
     }
+  };
+  // every stage-A/C thread: its own Y row of a FULL batch (after thread 0 announced the bytes)
+  auto issue_Y = [&](int64_t batch, int stage) {
+    const int64_t e0 = batch * E;
+    if (NE - e0 >= E && t < E * ND) bulk_g2s(Yr + (stage * E * ND + t) * YPITCH, Y + e0 * 64 + t * 16, 128u, &full[stage]);
   };
   auto load_X = [&](int64_t batch, dbl4 (&xv)[ND]) {
     const int64_t e0 = batch * E;
@@ -93,6 +102,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   dbl4 xv[ND], xn[ND];
   if (batch < nbatch) {
     if (t == 0) issue_D(batch, 0);
+    if (YRING) { __syncthreads(); issue_Y(batch, 0); }
     load_X(batch, xv);
   }
   for (int it = 0; batch < nbatch; batch += gridDim.x, ++it) {
@@ -103,6 +113,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     const int64_t next = batch + gridDim.x;
     // the other stage was last read in stage B of iteration it-1, which ended with a barrier
     if (t == 0 && next < nbatch) issue_D(next, stage ^ 1);
+    if (YRING && next < nbatch) { __syncthreads(); issue_Y(next, stage ^ 1); }
 
     // ---- stage A: (e, dz) -> contract x, then y
     if (has_slab) {
@@ -133,7 +144,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     // requests that land during stages B and C: this batch's Y slab, the next batch's X slab
     double* yp = Y + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
     dbl4 yo[ND];
-    if (has_slab) {
+    if (has_slab && !(YRING && cnt == E)) {
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy) yo[dy] = ldg256(yp + 4 * dy);
     }
@@ -180,6 +191,14 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     __syncthreads();
 
     // ---- stage C: (e, dz) -> contract y, then x, accumulate into Y
+    if (YRING && cnt == E && has_slab) {        // the staged Y row (the mbarrier wait of stage B covered it)
+      const double* yr = Yr + (stage * E * ND + t) * YPITCH;
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) {
+        const double2 lo = *reinterpret_cast<const double2*>(yr + 4 * dy), hi = *reinterpret_cast<const double2*>(yr + 4 * dy + 2);
+        yo[dy].x = lo.x; yo[dy].y = lo.y; yo[dy].z = hi.x; yo[dy].w = hi.y;
+      }
+    }
     if (has_slab) {
       const double* tp = T + t * SLAB;
       double a[ND][NQ];
@@ -676,17 +695,17 @@ cudaError_t launch_ring_kernel(K kernel, const rpb200_ctx* ctx, const double* D,
   return cudaGetLastError();
 }
 
-template <int E, int BLOCK, int MINB>
+template <int E, int BLOCK, int MINB, bool YRING = false>
 cudaError_t launch_mass(const rpb200_ctx* ctx, const double* D, const double* X, double* Y, int64_t NE, cudaStream_t st)
 {
-  constexpr size_t smem = sizeof(double) * (2 * E * 125 + E * 4 * 25) + 2 * sizeof(unsigned long long);
+  constexpr size_t smem = sizeof(double) * (2 * E * 125 + E * 4 * 25 + (YRING ? 2 * E * 4 * 18 : 0)) + 2 * sizeof(unsigned long long);
   static_assert(smem * MINB <= 227 * 1024, "ring does not fit");
-  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB, YRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t nbatch = (NE + E - 1) / E;
   int64_t grid = (int64_t)ctx->sm_count * MINB;
   if (grid > nbatch) grid = nbatch;
-  mass3dpa_kernel<E, BLOCK, MINB><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
+  mass3dpa_kernel<E, BLOCK, MINB, YRING><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
   return cudaGetLastError();
 }
 
@@ -710,6 +729,13 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
     case 12: RPB_CHECK((launch_mass<8, 64, 6>(ctx, D, X, Y, NE, st))); break;
     case 13: RPB_CHECK((launch_mass<16, 128, 3>(ctx, D, X, Y, NE, st))); break;
     case 14: RPB_CHECK((launch_mass<8, 32, 9>(ctx, D, X, Y, NE, st))); break;
+    case 16: RPB_CHECK((launch_mass<8, 32, 7, true>(ctx, D, X, Y, NE, st))); break;
+    case 19: RPB_CHECK((launch_mass<4, 32, 16>(ctx, D, X, Y, NE, st))); break;
+    case 20: RPB_CHECK((launch_mass<4, 32, 12>(ctx, D, X, Y, NE, st))); break;
+    case 21: RPB_CHECK((launch_mass<8, 64, 7>(ctx, D, X, Y, NE, st))); break;
+    case 22: RPB_CHECK((launch_mass<4, 32, 14>(ctx, D, X, Y, NE, st))); break;
+    case 17: RPB_CHECK((launch_mass<8, 32, 6, true>(ctx, D, X, Y, NE, st))); break;
+    case 18: RPB_CHECK((launch_mass<16, 64, 3, true>(ctx, D, X, Y, NE, st))); break;
     case 15: RPB_CHECK((launch_mass<16, 64, 5>(ctx, D, X, Y, NE, st))); break;
     default: RPB_CHECK((launch_mass<8, 32, 8>(ctx, D, X, Y, NE, st))); break;      // 5745 GB/s at NE = 4 M (16/64/4: 5660)
   }

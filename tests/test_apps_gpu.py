@@ -93,6 +93,26 @@ def test_pa_integer_valued_random_data_bit_exact(ctx, name, NE):
     assert np.array_equal(bits(run_pa(ctx, name, d, 1)), bits(run_pa_oracle(name, d, 1)))
 
 
+@pytest.mark.parametrize("name,variant", [("mass", 10), ("mass", 12), ("mass", 13), ("mass", 16), ("mass", 17), ("mass", 18), ("mass", 19), ("mass", 21),
+                                          ("convection", 10), ("convection", 11), ("convection", 14), ("convection", 16)])
+def test_pa_launch_shape_tunings_bit_exact(ctx, name, variant):
+    """Every selectable launch shape (elements per CTA / threads / ring stages / CTAs per SM, Y staged or not) on
+    integer-valued random data, two reps, with a ragged last batch."""
+    NE = 1029
+    rng = np.random.default_rng(variant)
+    d = MAKE[name](NE * (125 if name == "mass" else 64))
+    for k in d:
+        if k not in ("NE",):
+            d[k] = rng.integers(-3, 4, d[k].size).astype(np.float64)
+    kernel = "Apps_MASS3DPA" if name == "mass" else "Apps_CONVECTION3DPA"
+    ctx.set_tuning(kernel, -1, -1, variant)
+    try:
+        got = run_pa(ctx, name, d, 2)
+    finally:
+        ctx.set_tuning(kernel, -1, -1, 1)
+    assert np.array_equal(bits(got), bits(run_pa_oracle(name, d, 2)))
+
+
 @pytest.mark.parametrize("name", ["mass", "diffusion", "convection"])
 def test_pa_random_real_data_rounding_level(ctx, name):
     rng = np.random.default_rng(5)

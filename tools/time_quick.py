@@ -58,13 +58,13 @@ if "pa" in which:
     NE = 4000000
     one = lambda m: torch.ones(m, **f64)
     B, Bt, D, X, Y = one(20), one(20), one(125 * NE), one(64 * NE), one(64 * NE)
-    for var, shape in ((1, "8/32/8 (default)"), (10, "16/64/4"), (14, "8/32/9")):
+    for var, shape in ((1, "8/32/8 (default)"), (19, "4/32/16"), (20, "4/32/12"), (22, "4/32/14"), (21, "8/64/7")):
         ctx.set_tuning("Apps_MASS3DPA", -1, -1, var)
         report(f"mass3dpa E/BLOCK/CTAs={shape}", 2536 * NE, time_ms(lambda: ctx.mass3dpa(B, Bt, D, X, Y, NE), 10))
     ctx.set_tuning("Apps_MASS3DPA", -1, -1, 1)
     del D, X, Y
     B, G, D, X, Y = one(12), one(12), one(192 * NE), one(27 * NE), one(27 * NE)
-    for var, shape in ((1, "8/128/2/5 (default)"), (10, "16/256/2/2"), (11, "8/128/2/4")):
+    for var, shape in ((1, "8/128/2/5 (default)"),):
         ctx.set_tuning("Apps_CONVECTION3DPA", -1, -1, var)
         report(f"convection3dpa E/BLOCK/S/CTAs={shape}", 2184 * NE, time_ms(lambda: ctx.convection3dpa(B, B, G, D, X, Y, NE), 10))
     ctx.set_tuning("Apps_CONVECTION3DPA", -1, -1, 1)
