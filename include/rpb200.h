@@ -43,7 +43,15 @@ const char* rpb200_version(void);
 
 /* Launch tuning, the analogue of the reference's block-size tunings
  * (GPUUtils.hpp:345-373).  kernel = full kernel name ("Stream_TRIAD");
- * <=0 keeps the built-in default for that field.                                    */
+ * <=0 keeps the current value of that field (ctas_per_sm: < 0).  Meaning of the fields:
+ *   Stream_*, Stream_DOT, Algorithm_REDUCE_SUM, Algorithm_SCAN (small n), Basic_INDEXLIST (small n):
+ *       threads per CTA, persistent CTAs per SM (0 = one tile per CTA), independent vectors per thread;
+ *   Comm_HALO_PACKING_FUSED / Comm_HALO_EXCHANGE_FUSED: block_size 256 = contiguous chunk ranges per CTA,
+ *       192 = the same with pack launches walking the list backwards (default), 128 = round-robin; ctas_per_sm; unroll 4 = L2 eviction-priority hints on; for the exchange
+ *       unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch (default 2);
+ *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
+ *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.
+ * Every setting computes the same result; the defaults are the measured best (profiles/).            */
 int rpb200_set_tuning(rpb200_ctx* ctx, const char* kernel, int block_size,
                       int ctas_per_sm, int unroll);
 

@@ -27,12 +27,14 @@ static void default_tunings(rpb200_ctx* c)
   c->tune[RPB_K_DIFFUSION3DPA]  = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_CONVECTION3DPA] = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_INDEXLIST]      = rpb_tuning{512, 4, 4};
-  // halo kernels: block_size 256 = contiguous chunk ranges (128 = round-robin); unroll 4 = L2 eviction hints;
-  // exchange: unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch.  The alternatives win on
-  // some B200s and lose on others (SM enumeration differs per chip); these are the settings that never lose
-  // (profiles/r01_halo_variants.md)
-  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{256, 8, 1};
-  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{256, 4, 2};     // 4 CTAs/SM: 119 / 117 / 120 / 137 us at 1 / 2 / 4 / 8 GPUs
+  // halo kernels: block_size 256 = contiguous chunk ranges, 192 = the same with the PACK launches walking the work
+  // list backwards (the strided x faces are packed last, so the unpack -- which walks forward and starts with the ghost
+  // cells sharing their L2 lines -- finds them resident: 108 -> 98 us pack+unpack, 120 -> 103 us exchange on every box
+  // tried), 128 = round-robin; unroll 4 = L2 eviction hints; exchange: unroll 1 = ONE fused launch per rep, 2 / 4 = pack
+  // launch + unpack launch.  Round-robin, hints and the single launch win on some B200s and lose on others
+  // (profiles/r01_halo_variants.md); these settings never lost.
+  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{192, 4, 1};
+  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{192, 4, 2};
 }
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }

@@ -106,8 +106,11 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
             const int* __restrict__ chunk_seg, const long long* __restrict__ seg_first_chunk, int total_chunks,
             const halo_msg* __restrict__ msgs, unsigned int* __restrict__ msg_done,
             unsigned long long* __restrict__ d_epoch, unsigned int* __restrict__ unpack_done,
-            int* __restrict__ error, int chunk_lo, int commit)
+            int* __restrict__ error, int chunk_lo, int commit, int reverse)
 {
+  // reverse (pack launches): walk the chunks from the end of the work list, so that the strided x faces -- first in the
+  // list -- are packed LAST and are the most recently used L2 lines when the unpack, which walks forward, starts with
+  // the ghost cells that share those lines (LIFO reuse across the two launches).
   // The launch covers chunks [chunk_lo, total_chunks) of the work list (the whole list for the fused kernels, one
   // (neighbour, variable) tuple for the unfused HALO_EXCHANGE); `commit` = this is the last unpack launch of the rep.
   constexpr int EPT = HALO_CHUNK / HALO_BLOCK;     // 8 elements per thread per chunk
@@ -125,7 +128,9 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   int waited_msg = -1;
   const unsigned long long pol_keep = HINT ? policy_keep() : 0ull, pol_once = HINT ? policy_once() : 0ull;
 
-  for (int c = c_begin; c < c_end; c += c_step) {
+  const int c_flip = chunk_lo + total_chunks - 1;          // reverse: chunk c stands for chunk c_flip - c
+  for (int cc = c_begin; cc < c_end; cc += c_step) {
+    const int c = reverse ? c_flip - cc : cc;
     const int s = __ldg(chunk_seg + c);
     const rpb200_halo_seg seg = segs[s];
     const int64_t i0 = ((int64_t)c - __ldg(seg_first_chunk + s)) * HALO_CHUNK;
@@ -203,9 +208,9 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
       __threadfence_system();
       int c = c_begin;
       while (c < c_end) {
-        const int m = segs[__ldg(chunk_seg + c)].msg;
+        const int m = segs[__ldg(chunk_seg + (reverse ? c_flip - c : c))].msg;
         int run = 1;
-        while (c + run * c_step < c_end && segs[__ldg(chunk_seg + c + run * c_step)].msg == m) ++run;
+        while (c + run * c_step < c_end && segs[__ldg(chunk_seg + (reverse ? c_flip - (c + run * c_step) : c + run * c_step))].msg == m) ++run;
         const halo_msg hm = msgs[m];
         const unsigned int prev = atomicAdd(msg_done + m, (unsigned int)run);
         if (prev + run == hm.chunks) {
@@ -447,10 +452,11 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
   // tuning field `block_size`: 128 = chunks dealt round-robin (c = b, b + grid, ...) instead of in
   // contiguous ranges, so the slow strided faces are spread over every CTA
   const bool hint = ctx->tune[kid].unroll == 4, strided = ctx->tune[kid].block_size == 128;
+  const int reverse = (PACK && ctx->tune[kid].block_size == 192) ? 1 : 0;      // block_size 192: contiguous ranges, packs walk backwards
 #define RPB_HALO_LAUNCH(H, S)                                                                                  \
   halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
       w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)chunk_hi,         \
-      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error, (int)chunk_lo, commit)
+      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error, (int)chunk_lo, commit, reverse)
   if (hint && strided) RPB_HALO_LAUNCH(true, true);
   else if (hint) RPB_HALO_LAUNCH(true, false);
   else if (strided) RPB_HALO_LAUNCH(false, true);

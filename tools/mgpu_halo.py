@@ -45,11 +45,11 @@ def graph_ms(body, reps=100):
     return best
 
 res = {}
-for blk, cps, xu in ((256, 8, 2), (256, 4, 2), (128, 8, 2), (128, 4, 1), (256, 4, 1), (256, 8, 1)):
+for blk, cps, xu in ((256, 4, 2), (192, 4, 2), (192, 8, 2)):
     ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
     ms = graph_ms(plan.exchange)
     plan.status()
-    res[f"{'rr' if blk == 128 else 'ct'}{cps}/{'1L' if xu == 1 else '2L'}"] = round(ms * 1e3, 1)
+    res[f"{'rr' if blk == 128 else ('rv' if blk == 192 else 'ct')}{cps}/{'1L' if xu == 1 else '2L'}"] = round(ms * 1e3, 1)
 if rank == 0:
     print(json.dumps({"n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": g, "us_per_rep": res}), flush=True)
 if world > 1:
