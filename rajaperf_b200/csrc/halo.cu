@@ -451,8 +451,9 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
   // tuning field `unroll` of the two halo kernels: 4 = L2 eviction-priority hints on, else off;
   // tuning field `block_size`: 128 = chunks dealt round-robin (c = b, b + grid, ...) instead of in
   // contiguous ranges, so the slow strided faces are spread over every CTA
-  const bool hint = ctx->tune[kid].unroll == 4, strided = ctx->tune[kid].block_size == 128;
-  const int reverse = (PACK && ctx->tune[kid].block_size == 192) ? 1 : 0;      // block_size 192: contiguous ranges, packs walk backwards
+  const bool hint = ctx->tune[kid].unroll == 4, strided = ctx->tune[kid].block_size == 128 || ctx->tune[kid].block_size == 160;
+  // block_size 192: contiguous ranges, packs walk backwards; 160: round-robin, packs walk backwards
+  const int reverse = (PACK && (ctx->tune[kid].block_size == 192 || ctx->tune[kid].block_size == 160)) ? 1 : 0;
 #define RPB_HALO_LAUNCH(H, S)                                                                                  \
   halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
       w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)chunk_hi,         \

@@ -31,12 +31,12 @@ for trial in range(2):
     plan.bind(vars_, pb, ub)
     plan.window(vars_, want_handle=False); plan.connect_ptrs([0])
     out = []
-    for blk, cps in ((256, 8), (192, 8), (256, 4), (192, 4)):
+    for blk, cps in ((192, 4), (160, 4), (160, 8), (192, 2), (192, 3)):
         ctx.set_tuning("Comm_HALO_PACKING_FUSED", blk, cps, 1)
-        out.append(f"pk {'rr' if blk == 128 else ('rv' if blk == 192 else 'ct')}{cps} {graph_ms(lambda: (plan.pack(), plan.unpack())):6.1f}")
-    for blk, cps, xu in ((256, 4, 2), (192, 4, 2), (256, 8, 2), (192, 8, 2)):
+        out.append(f"pk {'rr' if blk == 128 else ('rv' if blk == 192 else ('rrv' if blk == 160 else 'ct'))}{cps} {graph_ms(lambda: (plan.pack(), plan.unpack())):6.1f}")
+    for blk, cps, xu in ((192, 4, 2), (160, 4, 2), (160, 8, 2), (192, 3, 2)):
         ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
-        out.append(f"ex {'rr' if blk == 128 else ('rv' if blk == 192 else 'ct')}{cps}/{'1L' if xu == 1 else '2L'} {graph_ms(plan.exchange):6.1f}")
+        out.append(f"ex {'rr' if blk == 128 else ('rv' if blk == 192 else ('rrv' if blk == 160 else 'ct'))}{cps}/{'1L' if xu == 1 else '2L'} {graph_ms(plan.exchange):6.1f}")
     print(f"trial {trial} var0@{vars_[0].data_ptr():#x}: " + " | ".join(out), flush=True)
     plan.status(); plan.close()
     del vars_, pb, ub, plan
