@@ -110,6 +110,141 @@ ltimes_dmma_kernel(double* __restrict__ phi, const double* __restrict__ ell,
   }
 }
 
+
+// ---- the same contraction with psi staged by bulk-async copies (opt-in tunings: measured SLOWER) ---------
+// ncu on the kernel above: 8 warps per SM (242 registers), `long_scoreboard` the top stall, ~45 KB of loads in
+// flight per SM -- so a staged variant was built to test whether memory-level parallelism was the limit.  It is not:
+// 3, 4 or 6 stages all land at 5190-5230 GB/s against 6070 for the register prefetch (the wait -> LDS -> DMMA chain
+// per 4 KB tile costs more than the prefetch registers).  Kept selectable (`unroll` 5..8) and covered by the tests.
+// Every warp owns a 3-stage ring of
+// psi tiles in shared memory (8 rows x 512 B, 576-byte pitch) filled two tiles ahead by cp.async.bulk (one row per
+// lane 0..7, completion on a per-warp mbarrier): no prefetch registers, 64+ KB in flight per SM.  A lane reads its
+// 128 bytes as eight 16-byte chunks starting at chunk kk (conflict-free with the 64-byte row padding); that is one
+// more permutation of d, applied identically to the resident ell fragments.  phi of the NEXT tile is prefetched
+// into the registers the psi prefetch no longer needs.
+constexpr int LR_PITCH = 72;                    // doubles per staged row: 64 + 8 pad = 576 bytes (ONE_COPY: 64, no pad)
+
+template <int LR_STAGES, bool ONE_COPY>
+struct lt_ring_smem {
+  alignas(128) double psi[LT_WARPS][LR_STAGES][LT_ROWS * (ONE_COPY ? LT_D : LR_PITCH)];
+  alignas(32) double c[LT_WARPS][LT_ROWS * LT_M];
+  unsigned long long full[LT_WARPS][LR_STAGES];
+};
+
+template <int LR_STAGES, bool ONE_COPY>
+__global__ void __launch_bounds__(LT_WARPS * 32, 2)
+ltimes_dmma_ring_kernel(double* __restrict__ phi, const double* __restrict__ ell,
+                        const double* __restrict__ psi, int64_t ntiles)
+{
+  extern __shared__ __align__(128) unsigned char lt_smem_raw[];
+  using smem_t = lt_ring_smem<LR_STAGES, ONE_COPY>;
+  constexpr int PITCH = ONE_COPY ? LT_D : LR_PITCH;
+  smem_t& S = *reinterpret_cast<smem_t*>(lt_smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = lane >> 2, kk = lane & 3;
+  double* sc = S.c[warp];
+  unsigned long long* full = S.full[warp];
+  if (lane == 0) {
+    for (int s = 0; s < LR_STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+
+  // element e of this lane's chunk list is psi[row][16 kk + perm(e)], perm(2c + h) = 2 ((c + kk) & 7) + h
+  double b[3][16], e24[16];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int d = 16 * kk + 2 * ((c + kk) & 7) + h;
+#pragma unroll
+      for (int t = 0; t < 3; ++t) b[t][2 * c + h] = __ldg(ell + (8 * t + i) * LT_D + d);
+      e24[2 * c + h] = __ldg(ell + 24 * LT_D + d);
+    }
+
+  const int64_t wstride = (int64_t)gridDim.x * LT_WARPS;
+  const int64_t tile0 = (int64_t)blockIdx.x * LT_WARPS + warp;
+  auto issue = [&](int64_t tile, int stage) {         // lanes 0..7: one 512-byte row each
+    if (lane == 0) mbar_arrive_expect_tx(&full[stage], LT_ROWS * LT_D * 8u);
+    __syncwarp();
+    if (ONE_COPY) {
+      if (lane == 0) bulk_g2s(&S.psi[warp][stage][0], psi + tile * (LT_ROWS * LT_D), LT_ROWS * LT_D * 8u, &full[stage]);
+    } else if (lane < LT_ROWS) {
+      bulk_g2s(&S.psi[warp][stage][lane * PITCH], psi + (tile * LT_ROWS + lane) * LT_D, LT_D * 8u, &full[stage]);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < LR_STAGES - 1; ++s)
+    if (tile0 + s * wstride < ntiles) issue(tile0 + s * wstride, s);
+
+  dbl4 old0 = {0.0, 0.0, 0.0, 0.0}, old1 = {0.0, 0.0, 0.0, 0.0};
+  if (tile0 < ntiles) {
+    const double* ptile = phi + tile0 * (LT_ROWS * LT_M);
+    old0 = ldg256(ptile + 4 * lane);
+    if (lane < 18) old1 = ldg256(ptile + 4 * (lane + 32));
+  }
+  int it = 0;
+  for (int64_t tile = tile0; tile < ntiles; tile += wstride, ++it) {
+    const int stage = it % LR_STAGES;
+    // the stage read in the previous iteration is free (every lane passed the __syncwarp that ended it)
+    const int64_t ahead = tile + (int64_t)(LR_STAGES - 1) * wstride;
+    if (ahead < ntiles) issue(ahead, (it + LR_STAGES - 1) % LR_STAGES);
+    // phi of the next tile: lands while this one is in the tensor pipe
+    const int64_t nxt = tile + wstride;
+    dbl4 nold0 = {0.0, 0.0, 0.0, 0.0}, nold1 = {0.0, 0.0, 0.0, 0.0};
+    if (nxt < ntiles) {
+      const double* pn = phi + nxt * (LT_ROWS * LT_M);
+      nold0 = ldg256(pn + 4 * lane);
+      if (lane < 18) nold1 = ldg256(pn + 4 * (lane + 32));
+    }
+
+    mbar_wait(&full[stage], (it / LR_STAGES) & 1);
+    double a[16];
+    {
+      const double* rowp = &S.psi[warp][stage][i * PITCH + 16 * kk];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const double2 q = *reinterpret_cast<const double2*>(rowp + 2 * ((c + kk) & 7));
+        a[2 * c] = q.x; a[2 * c + 1] = q.y;
+      }
+    }
+
+    double c[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    double c24 = 0.0;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      dmma_884(c[0][0], c[0][1], a[s], b[0][s]);
+      dmma_884(c[1][0], c[1][1], a[s], b[1][s]);
+      dmma_884(c[2][0], c[2][1], a[s], b[2][s]);
+      c24 = fma(a[s], e24[s], c24);
+    }
+    c24 += __shfl_xor_sync(0xffffffffu, c24, 1);
+    c24 += __shfl_xor_sync(0xffffffffu, c24, 2);
+
+    double* ptile = phi + tile * (LT_ROWS * LT_M);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      sc[i * LT_M + 8 * t + 2 * kk] = c[t][0];
+      sc[i * LT_M + 8 * t + 2 * kk + 1] = c[t][1];
+    }
+    if (kk == 0) sc[i * LT_M + 24] = c24;
+    __syncwarp();
+    {
+      const dbl4 add = *reinterpret_cast<const dbl4*>(sc + 4 * lane);
+      dbl4 o; o.x = old0.x + add.x; o.y = old0.y + add.y; o.z = old0.z + add.z; o.w = old0.w + add.w;
+      stg256(ptile + 4 * lane, o);
+    }
+    if (lane < 18) {
+      const dbl4 add = *reinterpret_cast<const dbl4*>(sc + 4 * (lane + 32));
+      dbl4 o; o.x = old1.x + add.x; o.y = old1.y + add.y; o.z = old1.z + add.z; o.w = old1.w + add.w;
+      stg256(ptile + 4 * (lane + 32), o);
+    }
+    __syncwarp();
+    old0 = nold0; old1 = nold1;
+  }
+}
+
 // any shape: one thread per (row, m), FMA chain over d in the reference's order
 __global__ void __launch_bounds__(256)
 ltimes_generic_kernel(double* __restrict__ phi, const double* __restrict__ ell,
@@ -144,7 +279,24 @@ extern "C" int rpb200_ltimes(rpb200_ctx* ctx, double* phi, const double* ell, co
     int64_t grid = (int64_t)ctx->sm_count * cps;
     const int64_t need = (ntiles + LT_WARPS - 1) / LT_WARPS;
     if (need < grid) grid = need;
-    ltimes_dmma_kernel<<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+    const int variant = ctx->tune[RPB_K_LTIMES].unroll;
+    if (variant < 5 || variant > 8) {                   // default: the register-prefetch kernel (6070 GB/s; the staged variants
+                                                        // below measure 4790-5230 GB/s, profiles/r01_widened.md)
+      ltimes_dmma_kernel<<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+    } else {
+#define RPB_LT_RING(S, O)                                                                                                   \
+  do {                                                                                                                      \
+    RPB_CHECK(cudaFuncSetAttribute(ltimes_dmma_ring_kernel<S, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(lt_ring_smem<S, O>))); \
+    ltimes_dmma_ring_kernel<S, O><<<(int)grid, LT_WARPS * 32, sizeof(lt_ring_smem<S, O>), st>>>(phi, ell, psi, ntiles);      \
+  } while (0)
+      switch (variant) {
+        case 5: RPB_LT_RING(3, true); break;
+        case 6: RPB_LT_RING(4, true); break;
+        case 7: RPB_LT_RING(6, true); break;
+        default: RPB_LT_RING(3, false); break;       // 8
+      }
+#undef RPB_LT_RING
+    }
   } else {
     const int64_t total = rows * num_m;
     int64_t grid = (total + 255) / 256;

@@ -167,6 +167,25 @@ def test_ltimes_matches_oracle_elementwise(ctx, nz):
     assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))     # dot of length 64, reordered
 
 
+@pytest.mark.parametrize("variant", [5, 6, 8])
+def test_ltimes_staged_variants_integer_valued_bit_exact(ctx, variant):
+    """The opt-in psi-ring kernels (another permutation of d, applied to psi and ell alike) on integer-valued data."""
+    nz, nd, ng, nm = 37, 64, 32, 25
+    rng = np.random.default_rng(variant)
+    phi = rng.integers(-5, 6, nz * ng * nm).astype(np.float64)
+    ell = rng.integers(-3, 4, nm * nd).astype(np.float64)
+    psi = rng.integers(-3, 4, nz * ng * nd).astype(np.float64)
+    ref = phi.copy()
+    oracle.lib().orc_ltimes(ref, ell, psi, nd, ng, nm, nz)
+    d_phi = dev(phi)
+    ctx.set_tuning("Apps_LTIMES", -1, -1, variant)
+    try:
+        ctx.ltimes(d_phi, dev(ell), dev(psi), nd, ng, nm, nz)
+    finally:
+        ctx.set_tuning("Apps_LTIMES", -1, -1, 4)
+    assert np.array_equal(bits(d_phi.cpu().numpy()), bits(ref))
+
+
 def test_ltimes_integer_valued_data_bit_exact(ctx):
     rng = np.random.default_rng(2)
     d = sd.ltimes(40 * 2048)

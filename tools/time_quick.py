@@ -70,6 +70,17 @@ if "pa" in which:
     ctx.set_tuning("Apps_CONVECTION3DPA", -1, -1, 1)
     del D, X, Y
 
+if "ltimes" in which:
+    nz = 500000
+    phi = torch.zeros(800 * nz, **f64); psi = torch.rand(2048 * nz, **f64); ell = torch.rand(1600, **f64)
+    for var, label in ((4, "register prefetch (default)"), (8, "psi ring 3 stages, row copies"), (5, "ring 3 stages, one 4 KB copy"), (6, "ring 4 stages one copy"), (7, "ring 6 stages one copy")):
+        for cps in (2,):
+            ctx.set_tuning("Apps_LTIMES", -1, cps, var)
+            ms = time_ms(lambda: ctx.ltimes(phi, ell, psi, 64, 32, 25, nz), 10)
+            report(f"ltimes {label} cps={cps}", 912 * 32 * nz, ms, tflops=3200 * 32 * nz / ms / 1e9)
+    ctx.set_tuning("Apps_LTIMES", -1, 2, 4)
+    del phi, psi
+
 if "halo" in which:
     for g in (512,):
         nv = 3
