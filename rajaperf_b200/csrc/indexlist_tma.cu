@@ -63,7 +63,7 @@ template <int IT_LBW>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict__ list, long long rows,
                      unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long tag,
-                     unsigned int num_tiles, int dstride, unsigned int backoff_ns, int num_lb)
+                     unsigned int num_tiles, int dstride, unsigned int backoff_ns, int num_lb, int evict_first)
 {
   extern __shared__ unsigned char smem_raw[];
   il_smem& S = *reinterpret_cast<il_smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,8 +91,14 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
           const long long row0 = (long long)t * IT_ROWS;
           const bool second = row0 + IT_BOX_ROWS < rows;
           mbar_arrive_expect_tx(&S.full[st], (second ? 2u : 1u) * IT_BOX_ROWS * 128u);
-          rpb_tma::tma_load_2d(&S.tile[st][0], &x_map, 0, (int)row0, &S.full[st]);
-          if (second) rpb_tma::tma_load_2d(&S.tile[st][IT_BOX_ROWS * IT_IPT], &x_map, 0, (int)(row0 + IT_BOX_ROWS), &S.full[st]);
+          if (evict_first) {
+            const unsigned long long pol = rpb_tma::policy_evict_first();
+            rpb_tma::tma_load_2d_hint(&S.tile[st][0], &x_map, 0, (int)row0, &S.full[st], pol);
+            if (second) rpb_tma::tma_load_2d_hint(&S.tile[st][IT_BOX_ROWS * IT_IPT], &x_map, 0, (int)(row0 + IT_BOX_ROWS), &S.full[st], pol);
+          } else {
+            rpb_tma::tma_load_2d(&S.tile[st][0], &x_map, 0, (int)row0, &S.full[st]);
+            if (second) rpb_tma::tma_load_2d(&S.tile[st][IT_BOX_ROWS * IT_IPT], &x_map, 0, (int)(row0 + IT_BOX_ROWS), &S.full[st]);
+          }
         } else {
           --invalid_left;
           mbar_arrive(&S.full[st]);
@@ -299,9 +305,9 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
   else RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count;
   if (grid > tiles) grid = (int)tiles;
-  if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
-  else if (lbw == 2) indexlist_tma_kernel<2><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
-  else indexlist_tma_kernel<1><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb);
+  if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
+  else if (lbw == 2) indexlist_tma_kernel<2><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
+  else indexlist_tma_kernel<1><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
   RPB_LAUNCH_CHECK();
   indexlist_tail_kernel<<<1, 32, 0, st>>>(x, list, (long long)rows * IT_IPT, (int)(n - rows * IT_IPT), d_desc + (tiles - 1) * ds, d_len);
   RPB_LAUNCH_CHECK();

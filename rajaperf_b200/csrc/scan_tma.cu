@@ -298,7 +298,7 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
   const cuuint32_t box[2] = {(cuuint32_t)ST_IPT, (cuuint32_t)ST_BOX_ROWS};
   const cuuint32_t estr[2] = {1, 1};
   if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(x), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, rpb_tma::l2_promotion(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return 0;
 
