@@ -37,8 +37,9 @@ template <int VPT>   // vectors (of 4 doubles) per thread
 __global__ void __launch_bounds__(512)
 scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
             tile_desc* __restrict__ desc, unsigned int* __restrict__ ticket,
-            unsigned long long epoch, unsigned int num_tiles, int vector_ok)
+            unsigned long long epoch, unsigned int num_tiles, int vector_ok, int dstride)
 {
+  // dstride: distance between tile descriptors in 16-byte units (see scan_tma.cu)
   constexpr int IPT = VPT * 4;
   __shared__ double s_warp[32];
   __shared__ double s_prefix;
@@ -106,16 +107,16 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
     if (warp == 0) {
       double prefix = 0.0;
       if (tile == 0) {
-        if (lane == 0) desc_store(desc, (epoch << 2) | ST_INCLUSIVE, tile_total);
+        if (lane == 0) desc_store(desc, (epoch << 2) | ST_INCLUSIVE, tile_total);      // tile 0 sits at index 0 for any spacing
       } else {
-        if (lane == 0) desc_store(desc + tile, (epoch << 2) | ST_PARTIAL, tile_total);
+        if (lane == 0) desc_store(desc + (int64_t)tile * dstride, (epoch << 2) | ST_PARTIAL, tile_total);
         int64_t look = (int64_t)tile - 1;
         for (;;) {
           const int64_t idx = look - lane;
           unsigned long long word = (epoch << 2) | ST_INCLUSIVE;
           double val = 0.0;
           if (idx >= 0) {
-            do { desc_load(desc + idx, word, val); } while ((word >> 2) != epoch || (word & 3ull) == 0ull);
+            do { desc_load(desc + idx * dstride, word, val); } while ((word >> 2) != epoch || (word & 3ull) == 0ull);
           }
           const unsigned int incl_mask = __ballot_sync(0xffffffffu, (word & 3ull) == ST_INCLUSIVE);
           const int first = __ffs(incl_mask) - 1;            // nearest tile holding an inclusive prefix
@@ -124,7 +125,7 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
           if (first >= 0) break;
           look -= 32;
         }
-        if (lane == 0) desc_store(desc + tile, (epoch << 2) | ST_INCLUSIVE, prefix + tile_total);
+        if (lane == 0) desc_store(desc + (int64_t)tile * dstride, (epoch << 2) | ST_INCLUSIVE, prefix + tile_total);
       }
       if (lane == 0) s_prefix = prefix;
     }
@@ -171,7 +172,7 @@ extern "C" int rpb200_scan_reserve(rpb200_ctx* ctx, int64_t n)
   if (!ctx || n < 0) return RPB200_EINVAL;
   // the smallest tile any tuning can select (32 threads x 4 doubles) bounds the tile count
   const size_t tiles = (size_t)((n + 127) / 128);
-  return scan_grow_state(ctx, sizeof(tile_desc) * tiles, nullptr);
+  return scan_grow_state(ctx, 2 * sizeof(tile_desc) * tiles, nullptr);
 }
 
 extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y, int64_t n,
@@ -191,7 +192,7 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   const unsigned int tiles = (unsigned int)tiles64;
 
   // the TMA path spreads its descriptors one per 128-byte line (8192-element tiles)
-  size_t need = sizeof(tile_desc) * (size_t)tiles;
+  size_t need = 2 * sizeof(tile_desc) * (size_t)tiles;        // descriptors one per 32-byte sector
   { const size_t spread = 128 * (size_t)((n + 8191) / 8192 + 1); if (spread > need) need = spread; }
   { const int rc = scan_grow_state(ctx, need, st); if (rc != 0) return rc; }
   const unsigned long long epoch = ++ctx->scan_epoch;
@@ -208,10 +209,12 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   if ((unsigned int)grid > tiles) grid = (int)tiles;
   tile_desc* desc = (tile_desc*)ctx->d_scan_state;
   const int vok = aligned ? 1 : 0;   // unaligned sub-ranges take the bounds-checked scalar path
+  int ds = 2;                        // one descriptor per 32-byte sector when the state allows it
+  while (ds > 1 && sizeof(tile_desc) * (size_t)tiles * ds > ctx->scan_state_bytes) ds >>= 1;
   switch (vpt) {
-    case 4: scan_kernel<4><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok); break;
-    case 2: scan_kernel<2><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok); break;
-    default: scan_kernel<1><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok); break;
+    case 4: scan_kernel<4><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
+    case 2: scan_kernel<2><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
+    default: scan_kernel<1><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
   }
   RPB_LAUNCH_CHECK();
   return 0;
