@@ -42,12 +42,16 @@ __constant__ double c_diff[48];      // B[q][d] | G*sign [q][d] | Bt[d][q] | Gt*
 // MASS3DPA: D1D = 4, Q1D = 5
 // ------------------------------------------------------------------------------------------------
 // Persistent kernel.  D (1000 of the 2536 bytes per element) is staged by bulk-async copies
-// (cp.async.bulk + mbarrier: the TMA path, no registers, no LSU queue) into a 2-stage shared-memory
-// ring, one batch of E elements ahead of the math; the X slab of the NEXT batch is prefetched into
-// registers while the current batch is in stages B and C, and the Y slab is requested before stage B.
+// (cp.async.bulk + mbarrier: the TMA path, no registers, no LSU queue) into shared memory; the X slab of the NEXT
+// batch is prefetched into registers while the current batch is in stages B and C, and the Y slab is requested
+// before stage B.  The kernel is latency-bound on resident warps, so the default keeps ONE D stage per (one-warp)
+// CTA -- requested at the top of its own batch, behind stage A -- and spends the shared memory on 12 CTAs per SM
+// instead of a second stage (6261 vs 5760 GB/s).
 // YRING: the Y slab of the next batch is staged too -- every stage-A/C thread bulk-copies its own 128-byte (e, dz) row
 // into a 144-byte-pitched shared-memory row (conflict-free 128-bit reads) -- instead of being loaded through the LSU.
-template <int E, int BLOCK, int MINB, bool YRING>
+// DS = stages of the D ring: 2 = one batch ahead; 1 = requested at the top of the batch it belongs to (less shared memory
+// per CTA, hence more CTAs per SM to hide the exposed latency).
+template <int E, int BLOCK, int MINB, bool YRING, int DS = 2>
 __global__ void __launch_bounds__(BLOCK, MINB)
 mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
                 int64_t NE)
@@ -58,8 +62,9 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   static_assert(E * ND <= BLOCK, "one stage-A/C task per thread");
   static_assert(DBYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(128) unsigned char pa_smem[];
-  double* Ds = reinterpret_cast<double*>(pa_smem);                         // [2][E*125]
-  double* T = Ds + 2 * E * 125;                                            // [E*4][25], stride 25 (odd)
+  static_assert(DS == 2 || !YRING, "the staged-Y variant uses the two-stage ring");
+  double* Ds = reinterpret_cast<double*>(pa_smem);                         // [DS][E*125]
+  double* T = Ds + DS * E * 125;                                            // [E*4][25], stride 25 (odd)
   constexpr int YPITCH = 18;                                               // doubles: 16 + 2 pad = 144 bytes
   double* Yr = T + E * ND * SLAB;                                          // [2][E*4][YPITCH]   (YRING only)
   unsigned long long* full = reinterpret_cast<unsigned long long*>(Yr + (YRING ? 2 * E * ND * YPITCH : 0));   // [2]
@@ -106,13 +111,14 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     load_X(batch, xv);
   }
   for (int it = 0; batch < nbatch; batch += gridDim.x, ++it) {
-    const int stage = it & 1;
+    const int stage = DS == 2 ? (it & 1) : 0;
     const int64_t e0 = batch * E;
     const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
     const bool has_slab = t < cnt * ND;
     const int64_t next = batch + gridDim.x;
     // the other stage was last read in stage B of iteration it-1, which ended with a barrier
-    if (t == 0 && next < nbatch) issue_D(next, stage ^ 1);
+    if (DS == 2) { if (t == 0 && next < nbatch) issue_D(next, stage ^ 1); }
+    else if (t == 0 && it > 0) issue_D(batch, 0);             // single stage: this batch's D, now that stage B of it-1 is over
     if (YRING && next < nbatch) { __syncthreads(); issue_Y(next, stage ^ 1); }
 
     // ---- stage A: (e, dz) -> contract x, then y
@@ -152,7 +158,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     __syncthreads();
 
     // ---- stage B: (e, pencil) -> contract z, scale by D (from the ring), contract z back
-    mbar_wait(&full[stage], (it >> 1) & 1);
+    mbar_wait(&full[stage], DS == 2 ? ((it >> 1) & 1) : (it & 1));
     const double* dsm = Ds + stage * E * 125;
 #pragma unroll
     for (int bt = 0; bt < BT; ++bt) {
@@ -695,17 +701,17 @@ cudaError_t launch_ring_kernel(K kernel, const rpb200_ctx* ctx, const double* D,
   return cudaGetLastError();
 }
 
-template <int E, int BLOCK, int MINB, bool YRING = false>
+template <int E, int BLOCK, int MINB, bool YRING = false, int DS = 2>
 cudaError_t launch_mass(const rpb200_ctx* ctx, const double* D, const double* X, double* Y, int64_t NE, cudaStream_t st)
 {
-  constexpr size_t smem = sizeof(double) * (2 * E * 125 + E * 4 * 25 + (YRING ? 2 * E * 4 * 18 : 0)) + 2 * sizeof(unsigned long long);
+  constexpr size_t smem = sizeof(double) * (DS * E * 125 + E * 4 * 25 + (YRING ? 2 * E * 4 * 18 : 0)) + 2 * sizeof(unsigned long long);
   static_assert(smem * MINB <= 227 * 1024, "ring does not fit");
-  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB, YRING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB, YRING, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t nbatch = (NE + E - 1) / E;
   int64_t grid = (int64_t)ctx->sm_count * MINB;
   if (grid > nbatch) grid = nbatch;
-  mass3dpa_kernel<E, BLOCK, MINB, YRING><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
+  mass3dpa_kernel<E, BLOCK, MINB, YRING, DS><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
   return cudaGetLastError();
 }
 
@@ -723,7 +729,7 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, ctx->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, ctx->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16)) return RPB200_EINVAL;
-  // elements per CTA / threads / CTAs per SM: 8/32/8 is the best of the sweep in profiles/r01_pa_variants.md
+  // elements per CTA / threads / CTAs per SM / D stages: 8/32/12/1 is the best of the sweeps in profiles/r01_pa_variants.md
   switch (ctx->tune[RPB_K_MASS3DPA].unroll) {
     case 10: RPB_CHECK((launch_mass<16, 64, 4>(ctx, D, X, Y, NE, st))); break;
     case 12: RPB_CHECK((launch_mass<8, 64, 6>(ctx, D, X, Y, NE, st))); break;
@@ -734,10 +740,18 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
     case 20: RPB_CHECK((launch_mass<4, 32, 12>(ctx, D, X, Y, NE, st))); break;
     case 21: RPB_CHECK((launch_mass<8, 64, 7>(ctx, D, X, Y, NE, st))); break;
     case 22: RPB_CHECK((launch_mass<4, 32, 14>(ctx, D, X, Y, NE, st))); break;
+    case 23: RPB_CHECK((launch_mass<8, 32, 10, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 24: RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 25: RPB_CHECK((launch_mass<8, 32, 14, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 26: RPB_CHECK((launch_mass<8, 32, 8, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 27: RPB_CHECK((launch_mass<8, 32, 11, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 28: RPB_CHECK((launch_mass<8, 32, 13, false, 1>(ctx, D, X, Y, NE, st))); break;
+    case 29: RPB_CHECK((launch_mass<16, 64, 6, false, 1>(ctx, D, X, Y, NE, st))); break;
     case 17: RPB_CHECK((launch_mass<8, 32, 6, true>(ctx, D, X, Y, NE, st))); break;
     case 18: RPB_CHECK((launch_mass<16, 64, 3, true>(ctx, D, X, Y, NE, st))); break;
     case 15: RPB_CHECK((launch_mass<16, 64, 5>(ctx, D, X, Y, NE, st))); break;
-    default: RPB_CHECK((launch_mass<8, 32, 8>(ctx, D, X, Y, NE, st))); break;      // 5745 GB/s at NE = 4 M (16/64/4: 5660)
+    case 30: RPB_CHECK((launch_mass<8, 32, 8>(ctx, D, X, Y, NE, st))); break;
+    default: RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st))); break;   // 6261 GB/s at NE = 4 M (two D stages, 8 CTAs: 5760)
   }
   RPB_LAUNCH_CHECK();
   return 0;

@@ -93,7 +93,7 @@ def test_pa_integer_valued_random_data_bit_exact(ctx, name, NE):
     assert np.array_equal(bits(run_pa(ctx, name, d, 1)), bits(run_pa_oracle(name, d, 1)))
 
 
-@pytest.mark.parametrize("name,variant", [("mass", 10), ("mass", 12), ("mass", 13), ("mass", 16), ("mass", 17), ("mass", 18), ("mass", 19), ("mass", 21),
+@pytest.mark.parametrize("name,variant", [("mass", 10), ("mass", 12), ("mass", 13), ("mass", 16), ("mass", 17), ("mass", 18), ("mass", 19), ("mass", 21), ("mass", 23), ("mass", 25), ("mass", 30),
                                           ("convection", 10), ("convection", 11), ("convection", 14), ("convection", 16)])
 def test_pa_launch_shape_tunings_bit_exact(ctx, name, variant):
     """Every selectable launch shape (elements per CTA / threads / ring stages / CTAs per SM, Y staged or not) on

@@ -58,7 +58,7 @@ if "pa" in which:
     NE = 4000000
     one = lambda m: torch.ones(m, **f64)
     B, Bt, D, X, Y = one(20), one(20), one(125 * NE), one(64 * NE), one(64 * NE)
-    for var, shape in ((1, "8/32/8 (default)"), (19, "4/32/16"), (20, "4/32/12"), (22, "4/32/14"), (21, "8/64/7")):
+    for var, shape in ((1, "8/32/12 one D stage (default)"), (30, "8/32/8 two D stages"), (27, "8/32/11 one D stage"), (28, "8/32/13 one D stage"), (29, "16/64/6 one D stage")):
         ctx.set_tuning("Apps_MASS3DPA", -1, -1, var)
         report(f"mass3dpa E/BLOCK/CTAs={shape}", 2536 * NE, time_ms(lambda: ctx.mass3dpa(B, Bt, D, X, Y, NE), 10))
     ctx.set_tuning("Apps_MASS3DPA", -1, -1, 1)
