@@ -54,6 +54,9 @@ const char* rpb200_version(void);
  * Every setting computes the same result; the defaults are the measured best (profiles/).            */
 int rpb200_set_tuning(rpb200_ctx* ctx, const char* kernel, int block_size,
                       int ctas_per_sm, int unroll);
+/* Back to the built-in (measured best) launch shape of `kernel`; NULL = of every kernel.  The suite harness brackets
+ * each non-default tuning of a kernel with set / reset (KernelBase::execute).                                          */
+int rpb200_reset_tuning(rpb200_ctx* ctx, const char* kernel);
 
 /* ---- Stream group ----------------------------------------------------------------
  * stream/COPY-Cuda.cpp:26, MUL-Cuda.cpp:26, ADD-Cuda.cpp:27, TRIAD-Cuda.cpp:26-58.
@@ -118,12 +121,12 @@ int rpb200_indexlist(rpb200_ctx*, const double* x, int* list, int64_t n, int64_t
 /* Optional: grow the look-back state for n elements now (synchronises); required before
  * capturing rpb200_indexlist into a CUDA graph.                                        */
 int rpb200_indexlist_reserve(rpb200_ctx*, int64_t n);
-/* polybench/POLYBENCH_GEMM-Cuda.cpp:44-85: C[i][j] = sum_k alpha * A[i][k] * B[k][j], row-major
- * A (ni x nk), B (nk x nj), C (ni x nj).  `beta` is dead in the reference body
- * (POLYBENCH_GEMM.hpp:32-39: "C *= beta" is overwritten by "C = dot") and is ignored here too. */
 /* algorithm/MEMSET-Cuda.cpp:27-76: x[i] = val, the write-only calibration stream; Algorithm_MEMCPY
  * (MEMCPY-Cuda.cpp:27-76, y[i] = x[i]) is rpb200_stream_copy.                              */
 int rpb200_memset_f64(rpb200_ctx*, double* x, double val, int64_t n, rpb200_stream_t);
+/* polybench/POLYBENCH_GEMM-Cuda.cpp:44-85: C[i][j] = sum_k alpha * A[i][k] * B[k][j], row-major
+ * A (ni x nk), B (nk x nj), C (ni x nj).  `beta` is dead in the reference body
+ * (POLYBENCH_GEMM.hpp:32-39: "C *= beta" is overwritten by "C = dot") and is ignored here too. */
 int rpb200_polybench_gemm(rpb200_ctx*, const double* A, const double* B, double* C,
                           int64_t ni, int64_t nj, int64_t nk, double alpha, double beta,
                           rpb200_stream_t);

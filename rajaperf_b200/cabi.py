@@ -37,6 +37,7 @@ SIGNATURES = {
     "rpb200_sm_count": (c_int, [_P]),
     "rpb200_version": (c_char_p, []),
     "rpb200_set_tuning": (c_int, [_P, c_char_p, c_int, c_int, c_int]),
+    "rpb200_reset_tuning": (c_int, [_P, c_char_p]),
     "rpb200_stream_copy": (c_int, [_P, _P, _P, c_int64, _P]),
     "rpb200_stream_mul": (c_int, [_P, _P, _P, c_double, c_int64, _P]),
     "rpb200_stream_add": (c_int, [_P, _P, _P, _P, c_int64, _P]),
@@ -175,6 +176,10 @@ class Context:
     def set_tuning(self, kernel: str, block_size: int = -1, ctas_per_sm: int = -1, unroll: int = -1):
         check(self.lib.rpb200_set_tuning(self.h, kernel.encode(), block_size, ctas_per_sm, unroll),
               f"set_tuning({kernel})")
+
+    def reset_tuning(self, kernel: str | None = None):
+        """Built-in launch shape of `kernel` (None: of every kernel) again."""
+        check(self.lib.rpb200_reset_tuning(self.h, kernel.encode() if kernel else None), f"reset_tuning({kernel})")
 
     # ---- Stream --------------------------------------------------------------------------
     def stream_copy(self, c, a, n=None):

@@ -113,6 +113,17 @@ extern "C" int rpb200_set_tuning(rpb200_ctx* c, const char* kernel, int block_si
   return RPB200_EINVAL;
 }
 
+extern "C" int rpb200_reset_tuning(rpb200_ctx* c, const char* kernel)
+{
+  if (!c) return RPB200_EINVAL;
+  rpb200_ctx d;                       // only the tuning table of this scratch copy is used
+  default_tunings(&d);
+  if (!kernel) { memcpy(c->tune, d.tune, sizeof(c->tune)); return 0; }
+  for (int k = 0; k < RPB_K_COUNT; ++k)
+    if (strcmp(kernel, k_kernel_names[k]) == 0) { c->tune[k] = d.tune[k]; return 0; }
+  return RPB200_EINVAL;
+}
+
 // ---- memory helpers ----------------------------------------------------------------
 extern "C" int rpb200_malloc(void** p, size_t bytes) { RPB_CHECK(cudaMalloc(p, bytes)); return 0; }
 extern "C" int rpb200_free(void* p) { RPB_CHECK(cudaFree(p)); return 0; }

@@ -15,6 +15,7 @@ public:
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
+  void setB200TuningDefinitions(VariantID vid) override;
   static constexpr Index_type D1D = 4, Q1D = 5;
 private:
   Real_ptr m_B = nullptr, m_Bt = nullptr, m_D = nullptr, m_X = nullptr, m_Y = nullptr;
@@ -43,6 +44,7 @@ public:
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
+  void setB200TuningDefinitions(VariantID vid) override;
   static constexpr Index_type D1D = 3, Q1D = 4, VDIM = 3;
 private:
   Real_ptr m_B = nullptr, m_Bt = nullptr, m_G = nullptr, m_D = nullptr, m_X = nullptr, m_Y = nullptr;

@@ -11,5 +11,13 @@ void CONVECTION3DPA::enqueueRep(rpb200_stream_t s)
 
 void CONVECTION3DPA::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+// launch shapes of csrc/pa.cu as suite tunings: elements per CTA / threads / ring stages / CTAs per SM
+void CONVECTION3DPA::setB200TuningDefinitions(VariantID vid)
+{
+  addB200Tuning(vid, getDefaultTuningName());               // 8 / 128 / 2 / 5
+  addB200Tuning(vid, "elems8_ctas4", 0, -1, 11);            // 8 / 128 / 2 / 4
+  addB200Tuning(vid, "elems16_block256", 0, -1, 10);        // 16 / 256 / 2 / 2
+}
+
 }  // namespace apps
 }  // namespace rajaperf

@@ -11,5 +11,13 @@ void MASS3DPA::enqueueRep(rpb200_stream_t s)
 
 void MASS3DPA::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+// launch shapes of csrc/pa.cu as suite tunings: elements per CTA / threads / CTAs per SM / D ring stages
+void MASS3DPA::setB200TuningDefinitions(VariantID vid)
+{
+  addB200Tuning(vid, getDefaultTuningName());               // 8 / 32 / 12 / 1
+  addB200Tuning(vid, "elems8_ctas8_ring2", 0, -1, 30);      // 8 / 32 / 8 / 2
+  addB200Tuning(vid, "elems16_block64", 0, -1, 10);         // 16 / 64 / 4 / 2
+}
+
 }  // namespace apps
 }  // namespace rajaperf

@@ -29,6 +29,7 @@ public:
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
+  void setB200TuningDefinitions(VariantID vid) override;
 protected:
   HALO_PACKING_FUSED(KernelID kid, const RunParams& params);
   rpb200_halo_plan* m_plan = nullptr;

@@ -2,6 +2,7 @@
 
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <cmath>
 #include <fstream>
 #include <iomanip>
@@ -29,6 +30,33 @@ void Executor::setupSuite()
   getCout() << "\nSetting up suite based on input..." << std::endl;
   for (KernelID kid : run_params.getKernelIDsToRun()) kernels.push_back(getKernelObject(kid, run_params));
   for (VariantID vid : run_params.getVariantIDsToRun()) variant_ids.push_back(vid);   // std::set => enum order
+
+  // Executor.cpp:290-358: per variant the ordered union of the tuning names the selected kernels define, filtered by
+  // --tunings / --exclude-tunings, "default" first.  A name no selected kernel defines is bad input.
+  const std::vector<std::string>& selected = run_params.getTuningInput();
+  const std::vector<std::string>& excluded = run_params.getExcludeTuningInput();
+  auto listed = [](const std::vector<std::string>& v, const std::string& s) { return std::find(v.begin(), v.end(), s) != v.end(); };
+  std::vector<std::string> known;
+  for (VariantID vid : variant_ids) {
+    std::vector<std::string>& names = tuning_names[vid];
+    for (KernelBase* k : kernels)
+      for (const std::string& t : k->getVariantTuningNames(vid)) {
+        if (listed(names, t)) continue;
+        if ((selected.empty() || listed(selected, t)) && !listed(excluded, t)) names.push_back(t);
+      }
+    auto def = std::find(names.begin(), names.end(), KernelBase::getDefaultTuningName());
+    if (def != names.end()) std::rotate(names.begin(), def, def + 1);
+  }
+  for (KernelBase* k : kernels)                    // a name is valid if any variant of a selected kernel defines it
+    for (int v = 0; v < NumVariants; ++v)
+      for (const std::string& t : k->getVariantTuningNames((VariantID)v)) if (!listed(known, t)) known.push_back(t);
+  std::vector<std::string> invalid;
+  for (const std::vector<std::string>* in : {&selected, &excluded})
+    for (const std::string& t : *in) if (!listed(known, t) && !listed(invalid, t)) invalid.push_back(t);
+  if (!invalid.empty()) {
+    run_params.setInvalidTuningInput(invalid);
+    run_params.setInputState(RunParams::BadInput);
+  }
 }
 
 void Executor::reportRunSummary(std::ostream& str) const
@@ -54,7 +82,8 @@ void Executor::reportRunSummary(std::ostream& str) const
       << run_params.getOutputFilePrefix() << "*" << std::endl;
   str << "\nThe following kernels and variants (when available for a kernel) will be run:" << std::endl;
   str << "\nVariants\n--------\n";
-  for (VariantID v : variant_ids) str << getVariantName(v) << std::endl;
+  for (VariantID v : variant_ids)                                  // Executor.cpp:488-496
+    for (const std::string& t : tuningNames(v)) str << getVariantName(v) << "-" << t << std::endl;
   str << std::endl;
   writeKernelInfoSummary(str);
   str.flush();
@@ -95,8 +124,14 @@ void Executor::runKernel(KernelBase* kern, bool print_kernel_name)    // Executo
       if (run_params.showProgress()) getCout() << "\tNo " << getVariantName(vid) << " variant" << std::endl;
       continue;
     }
-    for (size_t t = 0; t < kern->getNumVariantTunings(vid); ++t) {
-      if (run_params.showProgress()) getCout() << "\tRunning " << getVariantName(vid) << "-" << kern->getVariantTuningName(vid, t) << " variant" << std::endl;
+    for (size_t t = 0; t < kern->getNumVariantTunings(vid); ++t) {          // Executor.cpp:697-722
+      const std::string& tname = kern->getVariantTuningName(vid, t);
+      const std::vector<std::string>& run = tuningNames(vid);
+      if (std::find(run.begin(), run.end(), tname) == run.end()) {
+        if (run_params.showProgress()) getCout() << "\t\tSkipping " << tname << " tuning" << std::endl;
+        continue;
+      }
+      if (run_params.showProgress()) getCout() << "\tRunning " << getVariantName(vid) << "-" << tname << " variant" << std::endl;
       kern->execute(vid, t);
     }
   }
@@ -150,17 +185,19 @@ void Executor::writeTimingCSV(const std::string& filename, int combiner)
   static const char* title[] = {"Mean Runtime Report (sec.) ", "Min Runtime Report (sec.) ", "Max Runtime Report (sec.) "};
   file << title[combiner] << std::endl;
   file << "Kernel";
-  for (VariantID v : variant_ids) file << ", " << getVariantName(v) << "-default";
+  for (VariantID v : variant_ids) for (const std::string& tn : tuningNames(v)) file << ", " << getVariantName(v) << "-" << tn;
   file << std::endl;
   file << std::setprecision(9) << std::scientific;
   for (KernelBase* k : kernels) {
     file << k->getName();
-    for (VariantID v : variant_ids) {
-      if (k->hasVariantDefined(v) && k->wasVariantTuningRun(v, 0)) {
-        const double t = combiner == 0 ? k->getTotTime(v, 0) / run_params.getNumPasses() : combiner == 1 ? k->getMinTime(v, 0) : k->getMaxTime(v, 0);
-        file << ", " << t;
-      } else file << ", Not run";
-    }
+    for (VariantID v : variant_ids)
+      for (const std::string& tn : tuningNames(v)) {
+        const size_t ti = k->getVariantTuningIndex(v, tn);
+        if (ti != std::string::npos && k->wasVariantTuningRun(v, ti)) {
+          const double t = combiner == 0 ? k->getTotTime(v, ti) / run_params.getNumPasses() : combiner == 1 ? k->getMinTime(v, ti) : k->getMaxTime(v, ti);
+          file << ", " << t;
+        } else file << ", Not run";
+      }
     file << std::endl;
   }
 }
@@ -174,7 +211,7 @@ void Executor::writeChecksumReport(const std::string& filename)
   const size_t prec = 20, checksum_width = prec + 8;
   size_t namecol_width = 0;
   for (KernelBase* k : kernels) namecol_width = std::max(namecol_width, k->getName().size());
-  for (VariantID v : variant_ids) namecol_width = std::max(namecol_width, getVariantName(v).size() + 9);
+  for (VariantID v : variant_ids) for (const std::string& tn : tuningNames(v)) namecol_width = std::max(namecol_width, getVariantName(v).size() + 1 + tn.size());
   namecol_width += 2;
   file << equal_line << std::endl;
   file << "Checksum Report " << std::endl;
@@ -189,21 +226,27 @@ void Executor::writeChecksumReport(const std::string& filename)
   for (KernelBase* k : kernels) {
     file << std::left << std::setw(namecol_width) << k->getName() << std::endl;
     file << dot_line << std::endl;
-    Checksum_type ref = 0.0;
+    Checksum_type ref = 0.0;                 // the first (variant, tuning) listed that ran (Executor.cpp:1359-1373)
     bool found = false;
     for (size_t i = 0; i < variant_ids.size() && !found; ++i)
-      if (k->hasVariantDefined(variant_ids[i]) && k->wasVariantTuningRun(variant_ids[i], 0)) { ref = k->getChecksum(variant_ids[i], 0); found = true; }
-    for (VariantID v : variant_ids) {
-      const std::string vname = getVariantName(v) + "-default";
-      if (k->hasVariantDefined(v) && k->wasVariantTuningRun(v, 0)) {
-        const Checksum_type ck = k->getChecksum(v, 0);
-        file << std::left << std::setw(namecol_width) << vname << std::showpoint << std::setprecision(prec) << std::left
-             << std::setw(checksum_width) << ck << std::left << std::setw(checksum_width) << (ref - ck) << std::endl;
-      } else {
-        file << std::left << std::setw(namecol_width) << vname << std::left << std::setw(checksum_width) << "Not Run" << std::left
-             << std::setw(checksum_width) << "Not Run" << std::endl;
+      for (const std::string& tn : tuningNames(variant_ids[i])) {
+        const size_t ti = k->getVariantTuningIndex(variant_ids[i], tn);
+        if (ti != std::string::npos && k->wasVariantTuningRun(variant_ids[i], ti)) { ref = k->getChecksum(variant_ids[i], ti); found = true; break; }
       }
-    }
+    for (VariantID v : variant_ids)
+      for (const std::string& tn : tuningNames(v)) {
+        const size_t ti = k->getVariantTuningIndex(v, tn);
+        if (ti == std::string::npos) continue;               // the reference lists only tunings the kernel defines
+        const std::string vname = getVariantName(v) + "-" + tn;
+        if (k->wasVariantTuningRun(v, ti)) {
+          const Checksum_type ck = k->getChecksum(v, ti);
+          file << std::left << std::setw(namecol_width) << vname << std::showpoint << std::setprecision(prec) << std::left
+               << std::setw(checksum_width) << ck << std::left << std::setw(checksum_width) << (ref - ck) << std::endl;
+        } else {
+          file << std::left << std::setw(namecol_width) << vname << std::left << std::setw(checksum_width) << "Not Run" << std::left
+               << std::setw(checksum_width) << "Not Run" << std::endl;
+        }
+      }
     file << std::endl << dash_line << std::endl;
   }
 }
@@ -225,23 +268,27 @@ void Executor::writeBandwidthCSV(const std::string& filename)
 {
   std::ofstream file(filename);
   std::ostream& out = getCout();
-  const char* hdr = "Kernel, Variant, Problem size, Reps, Bytes/rep, FLOPs/rep, Host time (s), Device time (s), GB/s (device time), "
+  const char* hdr = "Kernel, Variant-tuning, Problem size, Reps, Bytes/rep, FLOPs/rep, Host time (s), Device time (s), GB/s (device time), "
                     "GFLOP/s (device time), Fraction of 8000 GB/s, Fraction of measured 6540.2 GB/s copy";
   if (file) file << hdr << std::endl;
   out << "\nBandwidth report (best pass)\n" << std::left << std::setw(28) << "Kernel" << std::right << std::setw(14) << "ms/rep" << std::setw(12)
       << "GB/s" << std::setw(12) << "GFLOP/s" << std::setw(12) << "%8TB/s" << std::setw(12) << "%copy" << std::endl;
   for (KernelBase* k : kernels)
-    for (VariantID v : variant_ids) {
-      if (!k->hasVariantDefined(v) || !k->wasVariantTuningRun(v, 0)) continue;
+    for (VariantID v : variant_ids)
+     for (const std::string& tn : tuningNames(v)) {
+      const size_t ti = k->getVariantTuningIndex(v, tn);
+      if (ti == std::string::npos || !k->wasVariantTuningRun(v, ti)) continue;
+      const bool is_default = tn == KernelBase::getDefaultTuningName();
+      const std::string label = is_default ? k->getName() : "  " + k->getName().substr(k->getName().find('_') + 1) + "-" + tn;
       const double reps = (double)k->getRunReps();
-      const double th = k->getMinTime(v, 0), td = k->getMinDeviceTime(v, 0);
+      const double th = k->getMinTime(v, ti), td = k->getMinDeviceTime(v, ti);
       const double gbs = td > 0 ? k->getBytesPerRep() * reps / td * 1e-9 : 0.0;
       const double gfs = td > 0 ? k->getFLOPsPerRep() * reps / td * 1e-9 : 0.0;
       if (file)
-        file << k->getName() << ", " << getVariantName(v) << ", " << k->getActualProblemSize() << ", " << k->getRunReps() << ", "
+        file << k->getName() << ", " << getVariantName(v) << (is_default ? std::string() : "-" + tn) << ", " << k->getActualProblemSize() << ", " << k->getRunReps() << ", "
              << k->getBytesPerRep() << ", " << k->getFLOPsPerRep() << ", " << std::setprecision(9) << th << ", " << td << ", " << gbs << ", "
              << gfs << ", " << gbs / kNominalGBs << ", " << gbs / kMeasuredCopyGBs << std::endl;
-      out << std::left << std::setw(28) << k->getName() << std::right << std::fixed << std::setprecision(4) << std::setw(14)
+      out << std::left << std::setw(28) << label << std::right << std::fixed << std::setprecision(4) << std::setw(14)
           << (reps > 0 ? td / reps * 1e3 : 0.0) << std::setprecision(1) << std::setw(12) << gbs << std::setw(12) << gfs << std::setw(12)
           << 100.0 * gbs / kNominalGBs << std::setw(12) << 100.0 * gbs / kMeasuredCopyGBs << std::endl;
       out.unsetf(std::ios::fixed);

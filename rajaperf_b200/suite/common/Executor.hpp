@@ -35,9 +35,12 @@ private:
   void writeKernelsCSV(const std::string& filename);
   void writeBandwidthCSV(const std::string& filename);
 
+  const std::vector<std::string>& tuningNames(VariantID vid) const { return tuning_names[vid]; }
+
   RunParams run_params;
   std::vector<KernelBase*> kernels;
   std::vector<VariantID> variant_ids;
+  std::vector<std::string> tuning_names[NumVariants];     // per variant: the ordered tunings to run and report
 };
 
 }  // namespace rajaperf

@@ -60,15 +60,30 @@ void KernelBase::setVariantDefined(VariantID vid)
   min_dev_time[vid].assign(n, std::numeric_limits<double>::max());
 }
 
+size_t KernelBase::getVariantTuningIndex(VariantID vid, const std::string& tuning_name) const
+{
+  const std::vector<std::string>& names = variant_tuning_names[vid];
+  for (size_t t = 0; t < names.size(); ++t) if (names[t] == tuning_name) return t;
+  return std::string::npos;
+}
+
 void KernelBase::execute(VariantID vid, size_t tune_idx)
 {
   running_variant = vid;
   running_tuning = tune_idx;
   detail::resetDataInitCount();
+  // a non-default tuning is a launch shape of the library: set it for this run only
+  const bool shaped = vid == Base_B200 && tune_idx < b200_tunings.size() &&
+                      (b200_tunings[tune_idx].block_size > 0 || b200_tunings[tune_idx].ctas_per_sm >= 0 || b200_tunings[tune_idx].unroll > 0);
+  if (shaped) {
+    const LaunchShape& t = b200_tunings[tune_idx];
+    checkAbi(rpb200_set_tuning(ctx(), tuningKernelName().c_str(), t.block_size, t.ctas_per_sm, t.unroll), "rpb200_set_tuning");
+  }
   this->setUp(vid, tune_idx);
   this->runKernel(vid, tune_idx);
   this->updateChecksum(vid, tune_idx);
   this->tearDown(vid, tune_idx);
+  if (shaped) checkAbi(rpb200_reset_tuning(ctx(), tuningKernelName().c_str()), "rpb200_reset_tuning");
   running_variant = NumVariants;
   running_tuning = std::numeric_limits<size_t>::max();
 }

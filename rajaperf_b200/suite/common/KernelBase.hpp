@@ -27,6 +27,8 @@ public:
 
   KernelID getKernelID() const { return kernel_id; }
   const std::string& getName() const { return name; }
+  // the library's tuning-table entry of this kernel (rpb200_set_tuning's `kernel`): its own full name
+  virtual const std::string& tuningKernelName() const { return name; }
 
   // properties set by kernel constructors (KernelBase.hpp:100-116)
   void setDefaultProblemSize(Index_type size) { default_prob_size = size; }
@@ -39,7 +41,12 @@ public:
   void setFLOPsPerRep(Index_type f) { FLOPs_per_rep = f; }
   void setVariantDefined(VariantID vid);
   void addVariantTuningName(VariantID vid, std::string n) { variant_tuning_names[vid].emplace_back(std::move(n)); }
-  virtual void setB200TuningDefinitions(VariantID vid) { addVariantTuningName(vid, "default"); }
+  static const std::string& getDefaultTuningName() { static const std::string n("default"); return n; }   // KernelBase.hpp:76
+  // A Base_B200 tuning = a named launch shape: the rpb200_set_tuning arguments execute() applies around the run
+  // (the reference's block_128/block_256/... tunings, GPUUtils.hpp:345-373).  {0,-1,0} keeps the library default.
+  void addB200Tuning(VariantID vid, std::string n, int block_size = 0, int ctas_per_sm = -1, int unroll = 0)
+  { addVariantTuningName(vid, std::move(n)); b200_tunings.push_back({block_size, ctas_per_sm, unroll}); }
+  virtual void setB200TuningDefinitions(VariantID vid) { addB200Tuning(vid, getDefaultTuningName()); }
 
   Index_type getDefaultProblemSize() const { return default_prob_size; }
   Index_type getActualProblemSize() const { return actual_prob_size; }
@@ -56,6 +63,11 @@ public:
   bool hasVariantDefined(VariantID vid) const { return !variant_tuning_names[vid].empty(); }
   size_t getNumVariantTunings(VariantID vid) const { return variant_tuning_names[vid].size(); }
   const std::string& getVariantTuningName(VariantID vid, size_t t) const { return variant_tuning_names[vid][t]; }
+  const std::vector<std::string>& getVariantTuningNames(VariantID vid) const { return variant_tuning_names[vid]; }
+  // KernelBase.hpp:196-204: npos when this kernel does not define that tuning
+  size_t getVariantTuningIndex(VariantID vid, const std::string& tuning_name) const;
+  bool hasVariantTuningDefined(VariantID vid, const std::string& tuning_name) const
+  { return getVariantTuningIndex(vid, tuning_name) != std::string::npos; }
   bool wasVariantTuningRun(VariantID vid, size_t t) const { return num_exec[vid][t] > 0; }
 
   // results (KernelBase.hpp:206-226)
@@ -98,6 +110,8 @@ private:
   Index_type default_prob_size = 0, actual_prob_size = 0, default_reps = 0;
   Index_type its_per_rep = 0, kernels_per_rep = 0, bytes_read_per_rep = 0, bytes_written_per_rep = 0, FLOPs_per_rep = 0;
   std::vector<std::string> variant_tuning_names[NumVariants];
+  struct LaunchShape { int block_size, ctas_per_sm, unroll; };
+  std::vector<LaunchShape> b200_tunings;      // parallel to variant_tuning_names[Base_B200]
   VariantID running_variant = NumVariants;
   size_t running_tuning = std::numeric_limits<size_t>::max();
   std::vector<int> num_exec[NumVariants];

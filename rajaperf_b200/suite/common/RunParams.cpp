@@ -45,6 +45,18 @@ void RunParams::parseCommandLineOptions(int argc, char** argv)
     else if (opt == "--variants" || opt == "-v") {
       while (i + 1 < argc && !is_opt(argv[i + 1])) variant_input.push_back(argv[++i]);
     }
+    else if (opt == "--exclude-kernels" || opt == "-ek") {       // RunParams.cpp:853-867
+      while (i + 1 < argc && !is_opt(argv[i + 1])) exclude_kernel_input.push_back(argv[++i]);
+    }
+    else if (opt == "--exclude-variants" || opt == "-ev") {      // RunParams.cpp:885-899
+      while (i + 1 < argc && !is_opt(argv[i + 1])) exclude_variant_input.push_back(argv[++i]);
+    }
+    else if (opt == "--tunings" || opt == "-t") {                // RunParams.cpp:1023-1037
+      while (i + 1 < argc && !is_opt(argv[i + 1])) tuning_input.push_back(argv[++i]);
+    }
+    else if (opt == "--exclude-tunings" || opt == "-et") {       // RunParams.cpp:1039-1053
+      while (i + 1 < argc && !is_opt(argv[i + 1])) exclude_tuning_input.push_back(argv[++i]);
+    }
     else if (opt == "--outdir" || opt == "-od") { if (i + 1 < argc && !is_opt(argv[i + 1])) outdir = argv[++i]; }
     else if (opt == "--outfile" || opt == "-of") { if (i + 1 < argc && !is_opt(argv[i + 1])) outfile_prefix = argv[++i]; }
     else if (opt == "--halo_width") { need_value(i, opt, 1, v); halo_width = (Index_type)v; }
@@ -79,31 +91,45 @@ void RunParams::parseCommandLineOptions(int argc, char** argv)
 }
 
 // group name | kernel name | full kernel name -> std::set<KernelID> (RunParams.cpp:1893-2102)
+static bool matchKernels(const std::string& in, std::set<KernelID>& out)
+{
+  for (int g = 0; g < NumGroups; ++g)
+    if (getGroupName((GroupID)g) == in) {
+      for (int k = 0; k < NumKernels; ++k) if (getKernelGroup((KernelID)k) == (GroupID)g) out.insert((KernelID)k);
+      return true;
+    }
+  for (int k = 0; k < NumKernels; ++k)
+    if (getKernelName((KernelID)k) == in || getFullKernelName((KernelID)k) == in) { out.insert((KernelID)k); return true; }
+  return false;
+}
+
 void RunParams::processKernelInput()
 {
+  std::set<KernelID> excluded;                                   // RunParams.cpp:1903-1972
+  for (const std::string& in : exclude_kernel_input)
+    if (!matchKernels(in, excluded)) { invalid_kernel_input.push_back(in); input_state = BadInput; }
   if (kernel_input.empty()) {
     for (int k = 0; k < NumKernels; ++k) run_kernels.insert((KernelID)k);
-    return;
+  } else {
+    for (const std::string& in : kernel_input)
+      if (!matchKernels(in, run_kernels)) { invalid_kernel_input.push_back(in); input_state = BadInput; }
   }
-  for (const std::string& in : kernel_input) {
-    bool found = false;
-    for (int g = 0; g < NumGroups && !found; ++g)
-      if (getGroupName((GroupID)g) == in) {
-        for (int k = 0; k < NumKernels; ++k) if (getKernelGroup((KernelID)k) == (GroupID)g) run_kernels.insert((KernelID)k);
-        found = true;
-      }
-    for (int k = 0; k < NumKernels && !found; ++k)
-      if (getKernelName((KernelID)k) == in || getFullKernelName((KernelID)k) == in) { run_kernels.insert((KernelID)k); found = true; }
-    if (!found) { invalid_kernel_input.push_back(in); input_state = BadInput; }
-  }
+  for (KernelID k : excluded) run_kernels.erase(k);
 }
 
 // RunParams.cpp:2295-2440: requested ∩ available; unknown names are bad input, known-but-unavailable
 // names are reported and dropped (as when the reference is built without that back-end).
 void RunParams::processVariantInput()
 {
+  std::set<VariantID> excluded;                                  // RunParams.cpp:2305-2345
+  for (const std::string& in : exclude_variant_input) {
+    bool found = false;
+    for (int v = 0; v < NumVariants; ++v) if (getVariantName((VariantID)v) == in) { excluded.insert((VariantID)v); found = true; }
+    if (!found) { invalid_variant_input.push_back(in); input_state = BadInput; }
+  }
   if (variant_input.empty()) {
-    for (int v = 0; v < NumVariants; ++v) if (isVariantAvailable((VariantID)v)) run_variants.insert((VariantID)v);
+    for (int v = 0; v < NumVariants; ++v)
+      if (isVariantAvailable((VariantID)v) && !excluded.count((VariantID)v)) run_variants.insert((VariantID)v);
     return;
   }
   for (const std::string& in : variant_input) {
@@ -111,7 +137,7 @@ void RunParams::processVariantInput()
     for (int v = 0; v < NumVariants; ++v)
       if (getVariantName((VariantID)v) == in) {
         found = true;
-        if (isVariantAvailable((VariantID)v)) run_variants.insert((VariantID)v);
+        if (isVariantAvailable((VariantID)v)) { if (!excluded.count((VariantID)v)) run_variants.insert((VariantID)v); }
         else getCout() << "\nVariant " << in << " is not available in this build (CPU variants: run the reference binary)" << std::endl;
       }
     if (!found) { invalid_variant_input.push_back(in); input_state = BadInput; }
@@ -120,6 +146,7 @@ void RunParams::processVariantInput()
 
 void RunParams::print(std::ostream& str) const
 {
+  if (!invalid_tuning_input.empty()) { str << "\n Invalid tuning input:"; for (auto& s : invalid_tuning_input) str << ' ' << s; }
   str << "\n npasses = " << npasses << "\n rep_fact = " << rep_fact << "\n size_meaning = "
       << (size_meaning == SizeMeaning::Direct ? "Direct" : "Factor") << "\n size = " << size << "\n size_factor = " << size_factor
       << "\n checkrun_reps = " << checkrun_reps << "\n halo_width = " << halo_width << "\n halo_num_vars = " << halo_num_vars
@@ -134,7 +161,11 @@ void RunParams::printHelpMessage(std::ostream& str) const
       << "\t --help, -h (print options with descriptions)\n"
       << "\t --print-kernels, -pk / --print-variants, -pv\n"
       << "\t --kernels, -k <space-separated strings> (group names, kernel names or full names; default: all)\n"
+      << "\t --exclude-kernels, -ek <space-separated strings> (same name forms; removed from the selection)\n"
       << "\t --variants, -v <space-separated strings> (default: every available variant: Base_B200)\n"
+      << "\t --exclude-variants, -ev <space-separated strings>\n"
+      << "\t --tunings, -t <space-separated strings> (default: every tuning a kernel defines; 'default' = the measured best)\n"
+      << "\t --exclude-tunings, -et <space-separated strings>\n"
       << "\t --npasses <int> (passes through the suite; default 1)\n"
       << "\t --repfact <double> (multiplies each kernel's default rep count)\n"
       << "\t --size <int> (problem size of every kernel run) | --sizefact <double> (multiplies each default size)\n"

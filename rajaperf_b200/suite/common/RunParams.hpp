@@ -1,5 +1,6 @@
 // RunParams.hpp -- the driver's command line (reference: common/RunParams.{hpp,cpp}), hot-path subset:
-//   -k/--kernels, -v/--variants, --size | --sizefact, --npasses, --repfact, --checkrun N, --dryrun,
+//   -k/--kernels, -ek/--exclude-kernels, -v/--variants, -ev/--exclude-variants, -t/--tunings, -et/--exclude-tunings,
+//   --size | --sizefact, --npasses, --repfact, --checkrun N, --dryrun,
 //   -od/--outdir, -of/--outfile, --disable-warmup, -sp/--show-progress, -pk/--print-kernels,
 //   -pv/--print-variants, --halo_width, --halo_num_vars, --ltimes_num_{d,g,m}, --mpi_3d_division,
 //   plus --device N (first CUDA device of this process) and --graph (capture the rep loop in a CUDA graph).
@@ -43,6 +44,11 @@ public:
   const std::string& getOutputFilePrefix() const { return outfile_prefix; }
   const std::set<KernelID>& getKernelIDsToRun() const { return run_kernels; }
   const std::set<VariantID>& getVariantIDsToRun() const { return run_variants; }
+  // tuning names are validated by the Executor once the kernel objects exist (Executor.cpp:290-358)
+  const std::vector<std::string>& getTuningInput() const { return tuning_input; }
+  const std::vector<std::string>& getExcludeTuningInput() const { return exclude_tuning_input; }
+  void setInvalidTuningInput(const std::vector<std::string>& v) { invalid_tuning_input = v; }
+  void setInputState(InputOpt s) { input_state = s; }
 
   void print(std::ostream& str) const;
 
@@ -68,6 +74,7 @@ private:
   int device = 0;
   std::string outdir, outfile_prefix = "RAJAPerf";
   std::vector<std::string> kernel_input, variant_input, invalid_kernel_input, invalid_variant_input;
+  std::vector<std::string> exclude_kernel_input, exclude_variant_input, tuning_input, exclude_tuning_input, invalid_tuning_input;
   std::set<KernelID> run_kernels;
   std::set<VariantID> run_variants;
 };

@@ -10,5 +10,13 @@ void POLYBENCH_GEMM::enqueueRep(rpb200_stream_t s)
 
 void POLYBENCH_GEMM::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+// CTA tilings of csrc/gemm.cu as suite tunings (default: chosen from the problem shape)
+void POLYBENCH_GEMM::setB200TuningDefinitions(VariantID vid)
+{
+  addB200Tuning(vid, getDefaultTuningName());
+  addB200Tuning(vid, "tile_64", 64, -1, 0);
+  addB200Tuning(vid, "tile_128", 128, -1, 0);
+}
+
 }  // namespace polybench
 }  // namespace rajaperf

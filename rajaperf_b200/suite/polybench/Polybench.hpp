@@ -13,6 +13,7 @@ public:
   void tearDown(VariantID vid, size_t tune_idx) override;
   void runB200Variant(VariantID vid, size_t tune_idx) override;
   void enqueueRep(rpb200_stream_t s) override;
+  void setB200TuningDefinitions(VariantID vid) override;
 private:
   Index_type m_ni, m_nj, m_nk;
   Real_type m_alpha, m_beta;

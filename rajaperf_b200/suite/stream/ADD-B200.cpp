@@ -11,5 +11,7 @@ void ADD::enqueueRep(rpb200_stream_t s)
 
 void ADD::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+void ADD::setB200TuningDefinitions(VariantID vid) { defineElementwiseTunings(*this, vid); }
+
 }  // namespace stream
 }  // namespace rajaperf

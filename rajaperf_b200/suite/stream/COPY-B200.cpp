@@ -11,5 +11,7 @@ void COPY::enqueueRep(rpb200_stream_t s)
 
 void COPY::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+void COPY::setB200TuningDefinitions(VariantID vid) { defineElementwiseTunings(*this, vid); }
+
 }  // namespace stream
 }  // namespace rajaperf

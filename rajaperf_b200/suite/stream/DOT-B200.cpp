@@ -29,5 +29,11 @@ void DOT::runB200Variant(VariantID, size_t)
   deallocData(m_d_dot);
 }
 
+void DOT::setB200TuningDefinitions(VariantID vid)
+{
+  addB200Tuning(vid, getDefaultTuningName());        // 256 threads, 8 persistent CTAs per SM, 2 vectors per thread per input
+  addB200Tuning(vid, "block_512", 512, 4, 2);
+}
+
 }  // namespace stream
 }  // namespace rajaperf

@@ -11,5 +11,7 @@ void MUL::enqueueRep(rpb200_stream_t s)
 
 void MUL::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+void MUL::setB200TuningDefinitions(VariantID vid) { defineElementwiseTunings(*this, vid); }
+
 }  // namespace stream
 }  // namespace rajaperf

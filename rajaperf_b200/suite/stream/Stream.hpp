@@ -7,6 +7,15 @@
 namespace rajaperf {
 namespace stream {
 
+// Launch shapes of the element-wise kernels as suite tunings (the reference's block_<N> tunings, stream/TRIAD-Cuda.cpp:
+// 60-100): {threads per CTA, persistent CTAs per SM (0 = one tile per CTA), 256-bit vectors per thread}.
+inline void defineElementwiseTunings(KernelBase& k, VariantID vid)
+{
+  k.addB200Tuning(vid, KernelBase::getDefaultTuningName());      // 512 threads, one tile per CTA, 2 vectors per thread
+  k.addB200Tuning(vid, "block_256", 256, 0, 2);
+  k.addB200Tuning(vid, "persistent_8", 512, 8, 4);               // grid-stride, 8 CTAs per SM, 4 vectors per thread
+}
+
 #define RPB_STREAM_KERNEL(NAME, MEMBERS)                                   \
   class NAME : public KernelBase {                                         \
   public:                                                                  \
@@ -16,6 +25,7 @@ namespace stream {
     void tearDown(VariantID vid, size_t tune_idx) override;                \
     void runB200Variant(VariantID vid, size_t tune_idx) override;          \
     void enqueueRep(rpb200_stream_t s) override;                           \
+    void setB200TuningDefinitions(VariantID vid) override;                 \
   private:                                                                 \
     MEMBERS                                                                \
   };

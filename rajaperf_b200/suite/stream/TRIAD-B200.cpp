@@ -11,5 +11,7 @@ void TRIAD::enqueueRep(rpb200_stream_t s)
 
 void TRIAD::runB200Variant(VariantID, size_t) { runRepLoop(); }
 
+void TRIAD::setB200TuningDefinitions(VariantID vid) { defineElementwiseTunings(*this, vid); }
+
 }  // namespace stream
 }  // namespace rajaperf

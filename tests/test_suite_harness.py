@@ -72,6 +72,34 @@ def test_bad_input_is_reported_and_nothing_runs():
     assert "not available in this build" in r.stdout
 
 
+def _variant_lines(out):
+    lines = out.splitlines()
+    i = lines.index("Variants")
+    return [l for l in lines[i + 2:lines.index("", i + 2)]]
+
+
+def test_tunings_are_listed_selected_and_excluded_like_the_reference():
+    """Executor.cpp:290-358: the run summary lists Variant-tuning pairs, 'default' first; -t / -et filter them;
+    -ek / -ev remove kernels / variants; a tuning no selected kernel defines is bad input."""
+    out = run_exe(["--dryrun", "-k", "Stream", "MASS3DPA", "HALO_PACKING", "HALO_PACKING_FUSED"]).stdout
+    names = _variant_lines(out)
+    assert names[0] == "Base_B200-default"
+    for t in ("block_256", "persistent_8", "block_512", "elems8_ctas8_ring2", "forward", "round_robin"):
+        assert f"Base_B200-{t}" in names
+    assert _variant_lines(run_exe(["--dryrun", "-k", "Stream", "-t", "block_256", "default"]).stdout) == \
+        ["Base_B200-default", "Base_B200-block_256"]
+    assert "Base_B200-persistent_8" not in _variant_lines(run_exe(["--dryrun", "-k", "Stream", "-et", "persistent_8"]).stdout)
+    # the unfused HALO_PACKING shares HALO_PACKING_FUSED's constructor but keeps the default tuning only
+    assert _variant_lines(run_exe(["--dryrun", "-k", "Comm_HALO_PACKING"]).stdout) == ["Base_B200-default"]
+    out = run_exe(["--dryrun", "-k", "Stream", "-ek", "DOT", "Stream_ADD"]).stdout
+    rows = [l.split()[0] for l in out.splitlines() if l.startswith("Stream_")]
+    assert rows == ["Stream_COPY", "Stream_MUL", "Stream_TRIAD"]
+    r = run_exe(["--dryrun", "-k", "Stream", "-t", "block_257"], check=False)
+    assert r.returncode == 1 and "Invalid tuning input: block_257" in r.stdout and "will not be run" in r.stdout
+    r = run_exe(["--dryrun", "-ek", "NOT_A_KERNEL"], check=False)
+    assert r.returncode == 1 and "Invalid kernel input" in r.stdout
+
+
 def _flags(case):
     return list(case["flags"])
 
@@ -131,3 +159,30 @@ def test_npasses_accumulate_checksums_and_graph_mode_agrees(tmp_path):
         assert abs(x - z) <= abs(x) * np.longdouble(1e-15)           # same kernels, one graph launch
     for f in ("RAJAPerf-timing-Minimum.csv", "RAJAPerf-timing-Average.csv", "RAJAPerf-kernels.csv", "RAJAPerf-bandwidth.csv"):
         assert os.path.getsize(os.path.join(a, f)) > 0
+
+
+@pytest.mark.gpu
+def test_every_tuning_of_every_kernel_reproduces_the_default_checksum(tmp_path):
+    """The suite's own cross-variant check (test/test-raja-perf-suite.cpp:124-167) applied to the Base_B200 tunings:
+    every launch shape is a tuning column of the checksum report, and its diff against the first column is zero --
+    exactly zero for the bit-exact kernels, within the suite's 1e-7 for DOT."""
+    run_exe(["--checkrun", "2", "--disable-warmup", "-k", "Stream", "MASS3DPA", "CONVECTION3DPA", "Polybench_GEMM",
+             "HALO_PACKING_FUSED", "--size", "300000"], tmp_path)
+    txt = open(os.path.join(tmp_path, "RAJAPerf-checksum.txt")).read()
+    blocks = re.split(r"^-{80,}$", txt, flags=re.M)
+    seen = {}
+    for b in blocks:
+        rows = re.findall(r"^(Base_B200-\S+)\s+(\S+)\s+(\S+)", b, re.M)
+        name = re.search(r"^((?:Stream|Apps|Polybench|Comm)_\S+)", b, re.M)
+        if not rows or not name:
+            continue
+        seen[name.group(1)] = [r[0] for r in rows]
+        for tun, ck, diff in rows:
+            assert ck != "Not" and abs(np.longdouble(diff)) <= (1e-7 if name.group(1) in ("Stream_DOT", "Polybench_GEMM") else 0), (name.group(1), tun, diff)
+    assert seen["Stream_TRIAD"] == ["Base_B200-default", "Base_B200-block_256", "Base_B200-persistent_8"]
+    assert seen["Stream_DOT"] == ["Base_B200-default", "Base_B200-block_512"]
+    assert len(seen["Apps_MASS3DPA"]) == 3 and len(seen["Apps_CONVECTION3DPA"]) == 3 and len(seen["Polybench_GEMM"]) == 3
+    assert seen["Comm_HALO_PACKING_FUSED"] == ["Base_B200-default", "Base_B200-forward", "Base_B200-round_robin"]
+    timing = open(os.path.join(tmp_path, "RAJAPerf-timing-Minimum.csv")).read().splitlines()
+    assert timing[1].startswith("Kernel, Base_B200-default, Base_B200-block_256, Base_B200-persistent_8")
+    assert "Not run" in [l for l in timing if l.startswith("Apps_MASS3DPA")][0]       # MASS3DPA has no block_256 tuning
