@@ -31,16 +31,26 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 constexpr int LT_D = 64, LT_M = 25, LT_ROWS = 8;
 constexpr int LT_WARPS = 4;
 
+// LINE = false: lane (i,kk) owns the 128 contiguous bytes psi[row][16kk .. 16kk+15]; each of its four 256-bit loads
+//   touches a different 128-byte line than the other three lanes of the row (32 lines per warp instruction).
+// LINE = true:  lane (i,kk) owns the 32-byte piece kk of each of the row's four 128-byte lines, d = 16j + 4kk + e; one warp
+//   instruction then covers 8 whole lines (one per row) -- a quarter of the L1 line requests for the same bytes.
+// Either way k-step s pairs element s of the four lanes of a row: one more permutation of d, applied to ell alike.
+template <bool LINE>
+__device__ __forceinline__ int lt_d_of(int kk, int s) { return LINE ? 16 * (s >> 2) + 4 * kk + (s & 3) : 16 * kk + s; }
+
+template <bool LINE>
 __device__ __forceinline__ void lt_load_a(double (&a)[16], const double* __restrict__ psi, int64_t row, int kk)
 {
-  const double* p = psi + row * LT_D + kk * 16;
+  const double* p = psi + row * LT_D + (LINE ? kk * 4 : kk * 16);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const dbl4 v = ldg256_stream(p + 4 * j);
+    const dbl4 v = ldg256_stream(p + (LINE ? 16 : 4) * j);
     a[4 * j] = v.x; a[4 * j + 1] = v.y; a[4 * j + 2] = v.z; a[4 * j + 3] = v.w;
   }
 }
 
+template <bool LINE>
 __global__ void __launch_bounds__(LT_WARPS * 32, 2)
 ltimes_dmma_kernel(double* __restrict__ phi, const double* __restrict__ ell,
                    const double* __restrict__ psi, int64_t ntiles)
@@ -55,18 +65,18 @@ ltimes_dmma_kernel(double* __restrict__ phi, const double* __restrict__ ell,
 #pragma unroll
   for (int t = 0; t < 3; ++t)
 #pragma unroll
-    for (int s = 0; s < 16; ++s) b[t][s] = __ldg(ell + (8 * t + i) * LT_D + 16 * kk + s);
+    for (int s = 0; s < 16; ++s) b[t][s] = __ldg(ell + (8 * t + i) * LT_D + lt_d_of<LINE>(kk, s));
 #pragma unroll
-  for (int s = 0; s < 16; ++s) e24[s] = __ldg(ell + 24 * LT_D + 16 * kk + s);
+  for (int s = 0; s < 16; ++s) e24[s] = __ldg(ell + 24 * LT_D + lt_d_of<LINE>(kk, s));
 
   const int64_t wstride = (int64_t)gridDim.x * LT_WARPS;
   int64_t tile = (int64_t)blockIdx.x * LT_WARPS + warp;
   double a[16], an[16];
-  if (tile < ntiles) lt_load_a(a, psi, tile * LT_ROWS + i, kk);
+  if (tile < ntiles) lt_load_a<LINE>(a, psi, tile * LT_ROWS + i, kk);
 
   for (; tile < ntiles; tile += wstride) {
     const int64_t nxt = tile + wstride;
-    if (nxt < ntiles) lt_load_a(an, psi, nxt * LT_ROWS + i, kk);
+    if (nxt < ntiles) lt_load_a<LINE>(an, psi, nxt * LT_ROWS + i, kk);
 
     // old phi of this tile: 200 contiguous doubles = 50 vectors of 4
     double* ptile = phi + tile * (LT_ROWS * LT_M);
@@ -282,7 +292,8 @@ extern "C" int rpb200_ltimes(rpb200_ctx* ctx, double* phi, const double* ell, co
     const int variant = ctx->tune[RPB_K_LTIMES].unroll;
     if (variant < 5 || variant > 8) {                   // default: the register-prefetch kernel (6070 GB/s; the staged variants
                                                         // below measure 4790-5230 GB/s, profiles/r01_widened.md)
-      ltimes_dmma_kernel<<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+      if (variant == 9) ltimes_dmma_kernel<true><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+      else ltimes_dmma_kernel<false><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
     } else {
 #define RPB_LT_RING(S, O)                                                                                                   \
   do {                                                                                                                      \

@@ -31,14 +31,14 @@ CPU_REPS = 3            # reps of the Base_OpenMP / RAJA_OpenMP leg (a bounded s
 
 # (tag, kernels, --size, --checkrun reps, extra flags for both, reference-only flags)
 GROUPS = [
-    ("stream", ["Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT"], 1 << 27, 20, [], []),
+    ("stream", ["Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT"], 1 << 26, 20, [], []),
     ("algo", ["Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP"], 1 << 26, 20, [], []),
     ("sort", ["Algorithm_SORT", "Algorithm_SORTPAIRS"], 1 << 25, 3, [], []),
-    ("mass", ["Apps_MASS3DPA"], 125000000, 10, [], []),
-    ("pa", ["Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA"], 64000000, 10, [], []),
-    ("ltimes", ["Apps_LTIMES"], 256000000, 10, [], []),
+    ("mass", ["Apps_MASS3DPA"], 62500000, 10, [], []),
+    ("pa", ["Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA"], 32000000, 10, [], []),
+    ("ltimes", ["Apps_LTIMES"], 128000000, 10, [], []),
+    ("comm", ["Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED"], 1 << 24, 50, [], []),
     ("gemm", ["Polybench_GEMM"], 1000000, 10, [], []),
-    ("comm", ["Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED"], 1 << 27, 20, [], []),
 ]
 QUICK = {"stream": 1 << 24, "algo": 1 << 24, "sort": 1 << 22, "mass": 12500000, "pa": 6400000, "ltimes": 25600000,
          "gemm": 1000000, "comm": 1 << 21}
@@ -141,8 +141,8 @@ def main():
         common = ["-k"] + kernels + ["--size", str(size), "--checkrun", str(reps)] + both
         rdir, odir, gdir = (os.path.join(a.out, f"{tag}_{w}") for w in ("ref", "b200", "b200_graph"))
         rc_r, t_r = run([REF] + common + ["-v", "Base_CUDA", "RAJA_CUDA"] + ref_only + ["--outdir", rdir], rdir + ".log", a.timeout)
-        rc_o, t_o = run([OURS] + common + ["-v", "Base_B200", "--outdir", odir], odir + ".log", a.timeout)
-        rc_g, t_g = run([OURS] + common + ["-v", "Base_B200", "--graph", "--outdir", gdir], gdir + ".log", a.timeout)
+        rc_o, t_o = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--outdir", odir], odir + ".log", a.timeout)
+        rc_g, t_g = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--graph", "--outdir", gdir], gdir + ".log", a.timeout)
         wall[tag] = {"reference_s": round(t_r, 1), "b200_s": round(t_o, 1), "b200_graph_s": round(t_g, 1), "rc": [rc_r, rc_o, rc_g]}
         cdir = os.path.join(a.out, f"{tag}_omp")
         if not a.no_cpu and time.time() - t_begin < a.budget:

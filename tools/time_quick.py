@@ -81,6 +81,31 @@ if "ltimes" in which:
     ctx.set_tuning("Apps_LTIMES", -1, 2, 4)
     del phi, psi
 
+if "ltimes_line" in which:
+    # A fragments owned line-major (unroll 9) against the default row-chunk mapping (unroll 4): parity, then A/B/A/B
+    nz0 = 37
+    g = torch.Generator(device="cuda").manual_seed(9)
+    phi0 = torch.randint(-5, 6, (nz0 * 32, 25), generator=g, **{**f64, "dtype": torch.int64}).to(torch.float64)
+    ell0 = torch.randint(-3, 4, (25, 64), generator=g, device="cuda").to(torch.float64)
+    psi0 = torch.randint(-3, 4, (nz0 * 32, 64), generator=g, device="cuda").to(torch.float64)
+    want = phi0 + psi0 @ ell0.t()
+    for var in (4, 9):
+        got = phi0.clone().reshape(-1)
+        ctx.set_tuning("Apps_LTIMES", -1, 2, var)
+        ctx.ltimes(got, ell0.reshape(-1).contiguous(), psi0.reshape(-1).contiguous(), 64, 32, 25, nz0)
+        ok = bool(torch.equal(got.reshape(-1, 25), want))
+        print(f"ltimes variant {var}: integer-valued parity {'OK' if ok else 'FAILED'}", flush=True)
+        res[f"ltimes parity variant {var}"] = ok
+    nz = 500000
+    phi = torch.zeros(800 * nz, **f64); psi = torch.rand(2048 * nz, **f64); ell = torch.rand(1600, **f64)
+    for rnd in range(2):
+        for var, label in ((4, "row chunks (default)"), (9, "line-major fragments")):
+            ctx.set_tuning("Apps_LTIMES", -1, 2, var)
+            ms = time_ms(lambda: ctx.ltimes(phi, ell, psi, 64, 32, 25, nz), 10)
+            report(f"ltimes {label} round {rnd}", 912 * 32 * nz, ms, tflops=3200 * 32 * nz / ms / 1e9)
+    ctx.reset_tuning("Apps_LTIMES")
+    del phi, psi
+
 if "halo" in which:
     for g in (512,):
         nv = 3
