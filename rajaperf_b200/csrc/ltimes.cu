@@ -10,9 +10,11 @@
 //     columns 0..23 are three 8-wide DMMA tiles, column 24 is a 16-FMA dot per lane + 2 shuffles --
 //     exactly 1600 FMA-equivalents per row, nothing padded;
 //   * the A fragments (psi) are loaded STRAIGHT from global memory in fragment order with 256-bit
-//     loads: lane (i,kk) owns psi[r0+i][16kk .. 16kk+15]; k-step s pairs element s of every lane's
-//     chunk, which is a permutation of d -- legal because the sum over d is order-free -- so no
-//     shared-memory staging or transposition of psi exists at all;
+//     loads: lane (i,kk) owns the 32-byte piece kk of each of the four 128-byte lines of row r0+i
+//     (d = 16j + 4kk + e), so one warp load instruction covers 8 whole lines; k-step s = 4j + e pairs
+//     element s of every lane's pieces, which is a permutation of d -- legal because the sum over d
+//     is order-free -- so no shared-memory staging or transposition of psi exists at all (owning the
+//     contiguous 128 bytes 16kk .. 16kk+15 instead spreads every load over 32 lines: 3 % slower);
 //   * the matching B fragments (ell) are loop-invariant and live in registers for the whole kernel;
 //   * phi tiles (8 rows x 25 = 1600 contiguous bytes) are updated with coalesced 256-bit
 //     read-modify-writes through a per-warp shared staging slab; the next tile's psi is prefetched
@@ -60,7 +62,7 @@ ltimes_dmma_kernel(double* __restrict__ phi, const double* __restrict__ ell,
   const int i = lane >> 2, kk = lane & 3;
   double* sc = s_c[warp];
 
-  // loop-invariant B fragments: b[t][s] = ell[m = 8t + i][d = 16kk + s]; e24[s] = ell[24][16kk + s]
+  // loop-invariant B fragments: b[t][s] = ell[m = 8t + i][d(kk, s)]; e24[s] = ell[24][d(kk, s)]
   double b[3][16], e24[16];
 #pragma unroll
   for (int t = 0; t < 3; ++t)
@@ -290,10 +292,11 @@ extern "C" int rpb200_ltimes(rpb200_ctx* ctx, double* phi, const double* ell, co
     const int64_t need = (ntiles + LT_WARPS - 1) / LT_WARPS;
     if (need < grid) grid = need;
     const int variant = ctx->tune[RPB_K_LTIMES].unroll;
-    if (variant < 5 || variant > 8) {                   // default: the register-prefetch kernel (6070 GB/s; the staged variants
-                                                        // below measure 4790-5230 GB/s, profiles/r01_widened.md)
-      if (variant == 9) ltimes_dmma_kernel<true><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
-      else ltimes_dmma_kernel<false><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+    if (variant < 5 || variant > 8) {                   // default: the register-prefetch kernel with line-major A fragments
+                                                        // (6125-6260 GB/s; row chunks, variant 10: 5905-6066 in the same run; the
+                                                        // staged variants below measure 4790-5230 GB/s, profiles/r01_widened.md)
+      if (variant == 10) ltimes_dmma_kernel<false><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
+      else ltimes_dmma_kernel<true><<<(int)grid, LT_WARPS * 32, 0, st>>>(phi, ell, psi, ntiles);
     } else {
 #define RPB_LT_RING(S, O)                                                                                                   \
   do {                                                                                                                      \

@@ -167,9 +167,9 @@ def test_ltimes_matches_oracle_elementwise(ctx, nz):
     assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))     # dot of length 64, reordered
 
 
-@pytest.mark.parametrize("variant", [5, 6, 8, 9])
+@pytest.mark.parametrize("variant", [5, 6, 8, 10])
 def test_ltimes_staged_variants_integer_valued_bit_exact(ctx, variant):
-    """The opt-in psi-ring kernels and the line-major fragment mapping (9): other permutations of d, applied to psi and
+    """The opt-in psi-ring kernels and the row-chunk fragment mapping (10; the default is line-major): other permutations of d, applied to psi and
     ell alike, on integer-valued data."""
     nz, nd, ng, nm = 37, 64, 32, 25
     rng = np.random.default_rng(variant)

@@ -40,6 +40,10 @@ GROUPS = [
     ("comm", ["Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED"], 1 << 24, 50, [], []),
     ("gemm", ["Polybench_GEMM"], 1000000, 10, [], []),
 ]
+# --fast: sizes still > the 126 MB L2 per dominant array, reference = Base_CUDA only (RAJA_CUDA where no Base_CUDA exists),
+# no OpenMP leg, Base_B200 through --graph only (plus the plain rep loop for the launch-bound Comm kernels)
+FAST = {"stream": 1 << 25, "algo": 1 << 25, "sort": 1 << 24, "mass": 31250000, "pa": 16000000, "ltimes": 64000000,
+        "gemm": 1000000, "comm": 1 << 24}
 QUICK = {"stream": 1 << 24, "algo": 1 << 24, "sort": 1 << 22, "mass": 12500000, "pa": 6400000, "ltimes": 25600000,
          "gemm": 1000000, "comm": 1 << 21}
 
@@ -120,6 +124,7 @@ def main():
     ap.add_argument("--timeout", type=int, default=120, help="seconds per binary per group")
     ap.add_argument("--budget", type=float, default=1e9, help="stop starting new runs after this many seconds in total")
     ap.add_argument("--no-cpu", action="store_true", help="skip the Base_OpenMP / RAJA_OpenMP leg")
+    ap.add_argument("--fast", action="store_true", help="smaller sizes, Base_CUDA only, no OpenMP leg (bounded box time)")
     a = ap.parse_args()
     for exe in (REF, OURS):
         if not os.path.exists(exe):
@@ -130,18 +135,24 @@ def main():
     threads = os.cpu_count() or 1
     omp_env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="cores")
     cpu_exe = REF_CPU if os.path.exists(REF_CPU) else REF
-    for tag, kernels, size, reps, both, ref_only in GROUPS:
-        if a.groups and tag not in a.groups:
-            continue
+    order = [g for t in a.groups for g in GROUPS if g[0] == t] if a.groups else GROUPS     # --groups also orders the runs
+    for tag, kernels, size, reps, both, ref_only in order:
         if time.time() - t_begin > a.budget:
             wall[tag] = {"skipped": "time budget"}
             continue
         if a.quick:
             size = QUICK[tag]
+        if a.fast:
+            size = FAST[tag]
+            a.no_cpu = True
+        ref_variants = ["Base_CUDA", "RAJA_CUDA"] if (not a.fast or tag == "sort") else ["Base_CUDA"]
         common = ["-k"] + kernels + ["--size", str(size), "--checkrun", str(reps)] + both
         rdir, odir, gdir = (os.path.join(a.out, f"{tag}_{w}") for w in ("ref", "b200", "b200_graph"))
-        rc_r, t_r = run([REF] + common + ["-v", "Base_CUDA", "RAJA_CUDA"] + ref_only + ["--outdir", rdir], rdir + ".log", a.timeout)
-        rc_o, t_o = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--outdir", odir], odir + ".log", a.timeout)
+        rc_r, t_r = run([REF] + common + ["-v"] + ref_variants + ref_only + ["--outdir", rdir], rdir + ".log", a.timeout)
+        if a.fast and tag != "comm":
+            rc_o, t_o = None, 0.0
+        else:
+            rc_o, t_o = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--outdir", odir], odir + ".log", a.timeout)
         rc_g, t_g = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--graph", "--outdir", gdir], gdir + ".log", a.timeout)
         wall[tag] = {"reference_s": round(t_r, 1), "b200_s": round(t_o, 1), "b200_graph_s": round(t_g, 1), "rc": [rc_r, rc_o, rc_g]}
         cdir = os.path.join(a.out, f"{tag}_omp")
@@ -155,9 +166,9 @@ def main():
         our_t = read_timing(os.path.join(odir, "RAJAPerf-timing-Average.csv"))
         gra_t = read_timing(os.path.join(gdir, "RAJAPerf-timing-Average.csv"))
         ref_k = read_reps(os.path.join(rdir, "RAJAPerf-kernels.csv"))
-        our_k = read_reps(os.path.join(odir, "RAJAPerf-kernels.csv"))
+        our_k = read_reps(os.path.join(odir, "RAJAPerf-kernels.csv")) or read_reps(os.path.join(gdir, "RAJAPerf-kernels.csv"))
         ref_c = read_checksums(os.path.join(rdir, "RAJAPerf-checksum.txt"))
-        our_c = read_checksums(os.path.join(odir, "RAJAPerf-checksum.txt"))
+        our_c = read_checksums(os.path.join(odir, "RAJAPerf-checksum.txt")) or read_checksums(os.path.join(gdir, "RAJAPerf-checksum.txt"))
         for k in kernels:
             row = {"kernel": k, "size": size}
             if k in ref_t and ref_t[k] and k in ref_k:
@@ -181,13 +192,13 @@ def main():
                     s = next(iter(t[k].values()))
                     row[key] = s / r * 1e3
                     row["b200_bytes_per_rep"] = b
-            if "b200_ms" in row:
-                row["b200_gbs"] = row["b200_bytes_per_rep"] / row["b200_ms"] / 1e6
+            if "b200_ms" in row or "b200_graph_ms" in row:
+                row["b200_gbs"] = row["b200_bytes_per_rep"] / row.get("b200_graph_ms", row.get("b200_ms")) / 1e6
                 row["b200_checksum"] = next(iter(our_c.get(k, {}).values()), None)
             if "incumbent_ms" in row and "b200_ms" in row:
                 row["speedup"] = row["incumbent_ms"] / row["b200_ms"]
-                if "b200_graph_ms" in row:
-                    row["speedup_graph"] = row["incumbent_ms"] / row["b200_graph_ms"]
+            if "incumbent_ms" in row and "b200_graph_ms" in row:
+                row["speedup_graph"] = row["incumbent_ms"] / row["b200_graph_ms"]
             table.append(row)
     res = {"what": "reference Base_CUDA/RAJA_CUDA (fastest tuning per kernel) vs Base_B200, same B200, same flags, host timers "
                    "around the rep loop as the reference times them; openmp = the reference's Base_OpenMP/RAJA_OpenMP (fastest) "

@@ -82,14 +82,14 @@ if "ltimes" in which:
     del phi, psi
 
 if "ltimes_line" in which:
-    # A fragments owned line-major (unroll 9) against the default row-chunk mapping (unroll 4): parity, then A/B/A/B
+    # A fragments owned line-major (the default) against the row-chunk mapping (unroll 10): parity, then A/B/A/B
     nz0 = 37
     g = torch.Generator(device="cuda").manual_seed(9)
     phi0 = torch.randint(-5, 6, (nz0 * 32, 25), generator=g, **{**f64, "dtype": torch.int64}).to(torch.float64)
     ell0 = torch.randint(-3, 4, (25, 64), generator=g, device="cuda").to(torch.float64)
     psi0 = torch.randint(-3, 4, (nz0 * 32, 64), generator=g, device="cuda").to(torch.float64)
     want = phi0 + psi0 @ ell0.t()
-    for var in (4, 9):
+    for var in (10, 4):
         got = phi0.clone().reshape(-1)
         ctx.set_tuning("Apps_LTIMES", -1, 2, var)
         ctx.ltimes(got, ell0.reshape(-1).contiguous(), psi0.reshape(-1).contiguous(), 64, 32, 25, nz0)
@@ -99,7 +99,7 @@ if "ltimes_line" in which:
     nz = 500000
     phi = torch.zeros(800 * nz, **f64); psi = torch.rand(2048 * nz, **f64); ell = torch.rand(1600, **f64)
     for rnd in range(2):
-        for var, label in ((4, "row chunks (default)"), (9, "line-major fragments")):
+        for var, label in ((10, "row chunks"), (4, "line-major fragments (default)")):
             ctx.set_tuning("Apps_LTIMES", -1, 2, var)
             ms = time_ms(lambda: ctx.ltimes(phi, ell, psi, 64, 32, 25, nz), 10)
             report(f"ltimes {label} round {rnd}", 912 * 32 * nz, ms, tflops=3200 * 32 * nz / ms / 1e9)
