@@ -51,7 +51,12 @@ __constant__ double c_diff[48];      // B[q][d] | G*sign [q][d] | Bt[d][q] | Gt*
 // into a 144-byte-pitched shared-memory row (conflict-free 128-bit reads) -- instead of being loaded through the LSU.
 // DS = stages of the D ring: 2 = one batch ahead; 1 = requested at the top of the batch it belongs to (less shared memory
 // per CTA, hence more CTAs per SM to hide the exposed latency).
-template <int E, int BLOCK, int MINB, bool YRING, int DS = 2>
+// LM (line-major global accesses; needs E*4 == BLOCK): thread t's (e, dz) slab of X / Y is the 128-byte line t of the batch.
+// Loading it with four 256-bit loads per thread makes every warp instruction touch 32 different lines, one 32-byte sector
+// each.  With LM, instruction j moves the 32 consecutive 32-byte pieces j*1024 + 32t of the batch instead (8 whole lines), and
+// a 144-byte-pitched shared-memory tile (aliasing T while T is dead) turns pieces into slabs (X, before stage A) and slabs
+// back into pieces (the result, after stage C; the old Y stays in piece form and is added there).  Same arithmetic, same order.
+template <int E, int BLOCK, int MINB, bool YRING, int DS = 2, bool LM = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, double* __restrict__ Y,
                 int64_t NE)
@@ -63,6 +68,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   static_assert(DBYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
   extern __shared__ __align__(128) unsigned char pa_smem[];
   static_assert(DS == 2 || !YRING, "the staged-Y variant uses the two-stage ring");
+  static_assert(!LM || (E * ND == BLOCK && !YRING && E * ND * 18 <= E * ND * SLAB), "line-major mode: one line per thread, tile inside T");
   double* Ds = reinterpret_cast<double*>(pa_smem);                         // [DS][E*125]
   double* T = Ds + DS * E * 125;                                            // [E*4][25], stride 25 (odd)
   constexpr int YPITCH = 18;                                               // doubles: 16 + 2 pad = 144 bytes
@@ -95,8 +101,12 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   };
   auto load_X = [&](int64_t batch, dbl4 (&xv)[ND]) {
     const int64_t e0 = batch * E;
-    const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
-    if (t < cnt * ND) {
+    const int cnt = LM ? E : (int)((NE - e0) < E ? (NE - e0) : E);
+    if constexpr (LM) {                                     // pieces: instruction j = the batch's bytes [1024j, 1024j + 1024)
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        if (j * (BLOCK / 4) + (t >> 2) < cnt * ND) xv[j] = ldg256_stream(X + e0 * 64 + j * (BLOCK * 4) + t * 4);
+    } else if (t < cnt * ND) {
       const double* xp = X + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy) xv[dy] = ldg256_stream(xp + 4 * dy);
@@ -113,7 +123,7 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
   for (int it = 0; batch < nbatch; batch += gridDim.x, ++it) {
     const int stage = DS == 2 ? (it & 1) : 0;
     const int64_t e0 = batch * E;
-    const int cnt = (int)((NE - e0) < E ? (NE - e0) : E);
+    const int cnt = LM ? E : (int)((NE - e0) < E ? (NE - e0) : E);     // LM is launched for whole batches only (NE % E == 0)
     const bool has_slab = t < cnt * ND;
     const int64_t next = batch + gridDim.x;
     // the other stage was last read in stage B of iteration it-1, which ended with a barrier
@@ -122,6 +132,23 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     if (YRING && next < nbatch) { __syncthreads(); issue_Y(next, stage ^ 1); }
 
     // ---- stage A: (e, dz) -> contract x, then y
+    if constexpr (LM) {                                      // pieces -> slabs through the tile (T is dead here)
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        if (j * (BLOCK / 4) + (t >> 2) >= cnt * ND) continue;  // lines beyond a ragged last batch were not loaded
+        double* d = T + (j * (BLOCK / 4) + (t >> 2)) * YPITCH + (t & 3) * 4;
+        *reinterpret_cast<double2*>(d) = make_double2(xv[j].x, xv[j].y);
+        *reinterpret_cast<double2*>(d + 2) = make_double2(xv[j].z, xv[j].w);
+      }
+      __syncthreads();
+      if (has_slab)
+#pragma unroll
+      for (int dy = 0; dy < ND; ++dy) {
+        const double2 lo = *reinterpret_cast<const double2*>(T + t * YPITCH + 4 * dy), hi = *reinterpret_cast<const double2*>(T + t * YPITCH + 4 * dy + 2);
+        xv[dy].x = lo.x; xv[dy].y = lo.y; xv[dy].z = hi.x; xv[dy].w = hi.y;
+      }
+      __syncthreads();                                       // the tile is T: every slab is out before stage A writes T
+    }
     if (has_slab) {
       double x[ND][ND];
 #pragma unroll
@@ -150,7 +177,11 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
     // requests that land during stages B and C: this batch's Y slab, the next batch's X slab
     double* yp = Y + (e0 + (t >> 2)) * 64 + (t & 3) * 16;
     dbl4 yo[ND];
-    if (has_slab && !(YRING && cnt == E)) {
+    if constexpr (LM) {                                      // the old Y in piece form
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+        if (j * (BLOCK / 4) + (t >> 2) < cnt * ND) yo[j] = ldg256(Y + e0 * 64 + j * (BLOCK * 4) + t * 4);
+    } else if (has_slab && !(YRING && cnt == E)) {
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy) yo[dy] = ldg256(yp + 4 * dy);
     }
@@ -205,9 +236,9 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
         yo[dy].x = lo.x; yo[dy].y = lo.y; yo[dy].z = hi.x; yo[dy].w = hi.y;
       }
     }
+    double a[ND][NQ];
     if (has_slab) {
       const double* tp = T + t * SLAB;
-      double a[ND][NQ];
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy)
 #pragma unroll
@@ -220,6 +251,9 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
 #pragma unroll
           for (int dy = 0; dy < ND; ++dy) a[dy][qx] = fma(c, c_mass_Bt[dy * NQ + qy], a[dy][qx]);
         }
+    }
+    if constexpr (LM) __syncthreads();                       // every thread has read T: it becomes the tile again
+    if (has_slab) {
 #pragma unroll
       for (int dy = 0; dy < ND; ++dy) {
         double r[ND];
@@ -230,9 +264,26 @@ mass3dpa_kernel(const double* __restrict__ D, const double* __restrict__ X, doub
           for (int qx = 0; qx < NQ; ++qx) s = fma(a[dy][qx], c_mass_Bt[dx * NQ + qx], s);
           r[dx] = s;
         }
+        if constexpr (LM) {                                  // result slab -> tile row t
+          *reinterpret_cast<double2*>(T + t * YPITCH + 4 * dy) = make_double2(r[0], r[1]);
+          *reinterpret_cast<double2*>(T + t * YPITCH + 4 * dy + 2) = make_double2(r[2], r[3]);
+        } else {
+          dbl4 o;
+          o.x = yo[dy].x + r[0]; o.y = yo[dy].y + r[1]; o.z = yo[dy].z + r[2]; o.w = yo[dy].w + r[3];
+          stg256(yp + 4 * dy, o);
+        }
+      }
+    }
+    if constexpr (LM) {                                      // tile -> pieces, added to the old Y pieces, stored line-major
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < ND; ++j) {
+        if (j * (BLOCK / 4) + (t >> 2) >= cnt * ND) continue;
+        const double* d = T + (j * (BLOCK / 4) + (t >> 2)) * YPITCH + (t & 3) * 4;
+        const double2 lo = *reinterpret_cast<const double2*>(d), hi = *reinterpret_cast<const double2*>(d + 2);
         dbl4 o;
-        o.x = yo[dy].x + r[0]; o.y = yo[dy].y + r[1]; o.z = yo[dy].z + r[2]; o.w = yo[dy].w + r[3];
-        stg256(yp + 4 * dy, o);
+        o.x = yo[j].x + lo.x; o.y = yo[j].y + lo.y; o.z = yo[j].z + hi.x; o.w = yo[j].w + hi.y;
+        stg256(Y + e0 * 64 + j * (BLOCK * 4) + t * 4, o);
       }
     }
 #pragma unroll
@@ -701,17 +752,17 @@ cudaError_t launch_ring_kernel(K kernel, const rpb200_ctx* ctx, const double* D,
   return cudaGetLastError();
 }
 
-template <int E, int BLOCK, int MINB, bool YRING = false, int DS = 2>
+template <int E, int BLOCK, int MINB, bool YRING = false, int DS = 2, bool LM = false>
 cudaError_t launch_mass(const rpb200_ctx* ctx, const double* D, const double* X, double* Y, int64_t NE, cudaStream_t st)
 {
   constexpr size_t smem = sizeof(double) * (DS * E * 125 + E * 4 * 25 + (YRING ? 2 * E * 4 * 18 : 0)) + 2 * sizeof(unsigned long long);
   static_assert(smem * MINB <= 227 * 1024, "ring does not fit");
-  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB, YRING, DS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(mass3dpa_kernel<E, BLOCK, MINB, YRING, DS, LM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t nbatch = (NE + E - 1) / E;
   int64_t grid = (int64_t)ctx->sm_count * MINB;
   if (grid > nbatch) grid = nbatch;
-  mass3dpa_kernel<E, BLOCK, MINB, YRING, DS><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
+  mass3dpa_kernel<E, BLOCK, MINB, YRING, DS, LM><<<(int)grid, BLOCK, smem, st>>>(D, X, Y, NE);
   return cudaGetLastError();
 }
 
@@ -751,7 +802,18 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
     case 18: RPB_CHECK((launch_mass<16, 64, 3, true>(ctx, D, X, Y, NE, st))); break;
     case 15: RPB_CHECK((launch_mass<16, 64, 5>(ctx, D, X, Y, NE, st))); break;
     case 30: RPB_CHECK((launch_mass<8, 32, 8>(ctx, D, X, Y, NE, st))); break;
-    default: RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st))); break;   // 6261 GB/s at NE = 4 M (two D stages, 8 CTAs: 5760)
+    case 31:                                                  // line-major X / Y accesses (whole batches only)
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 12, false, 1, true>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
+      break;
+    case 32:
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 11, false, 1, true>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 11, false, 1>(ctx, D, X, Y, NE, st)));
+      break;
+    default:                                                  // = 31; slab-per-thread accesses (24): 6261 GB/s at NE = 4 M, two D stages and 8 CTAs (30): 5760
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 12, false, 1, true>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
+      break;
   }
   RPB_LAUNCH_CHECK();
   return 0;

@@ -167,6 +167,27 @@ def test_ltimes_matches_oracle_elementwise(ctx, nz):
     assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))     # dot of length 64, reordered
 
 
+@pytest.mark.parametrize("variant", [1, 24, 32])
+@pytest.mark.parametrize("NE", [8, 1024, 40000, 1029])
+def test_mass_line_major_accesses_bit_exact(ctx, variant, NE):
+    """MASS3DPA with line-major X / Y accesses (pieces <-> slabs through a shared-memory tile): whole batches take the
+    line-major kernel (the default, 1; 32 = 11 CTAs per SM), a ragged element count (1029) falls back to the
+    slab-per-thread kernel (24); random integer-valued data and basis, two reps (Y accumulates)."""
+    rng = np.random.default_rng(NE + variant)
+    d = sd.mass3dpa(NE * 125)
+    assert d["NE"] == NE
+    for k in ("D", "X", "Y"):
+        d[k] = rng.integers(-3, 4, d[k].size).astype(np.float64)
+    d["B"] = rng.integers(-2, 3, d["B"].size).astype(np.float64)
+    d["Bt"] = rng.integers(-2, 3, d["Bt"].size).astype(np.float64)
+    ctx.set_tuning("Apps_MASS3DPA", -1, -1, variant)
+    try:
+        got = run_pa(ctx, "mass", d, 2)
+    finally:
+        ctx.set_tuning("Apps_MASS3DPA", -1, -1, 1)
+    assert np.array_equal(bits(got), bits(run_pa_oracle("mass", d, 2)))
+
+
 @pytest.mark.parametrize("variant", [5, 6, 8, 10])
 def test_ltimes_staged_variants_integer_valued_bit_exact(ctx, variant):
     """The opt-in psi-ring kernels and the row-chunk fragment mapping (10; the default is line-major): other permutations of d, applied to psi and
