@@ -780,7 +780,8 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, ctx->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, ctx->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16)) return RPB200_EINVAL;
-  // elements per CTA / threads / CTAs per SM / D stages: 8/32/12/1 is the best of the sweeps in profiles/r01_pa_variants.md
+  // elements per CTA / threads / CTAs per SM / D stages: 8/32/11/1 with line-major accesses is the best of the sweeps in
+  // profiles/r01_pa_variants.md
   switch (ctx->tune[RPB_K_MASS3DPA].unroll) {
     case 10: RPB_CHECK((launch_mass<16, 64, 4>(ctx, D, X, Y, NE, st))); break;
     case 12: RPB_CHECK((launch_mass<8, 64, 6>(ctx, D, X, Y, NE, st))); break;
@@ -808,10 +809,19 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
       break;
     case 32:
       if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 11, false, 1, true>(ctx, D, X, Y, NE, st)));
-      else RPB_CHECK((launch_mass<8, 32, 11, false, 1>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
       break;
-    default:                                                  // = 31; slab-per-thread accesses (24): 6261 GB/s at NE = 4 M, two D stages and 8 CTAs (30): 5760
-      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 12, false, 1, true>(ctx, D, X, Y, NE, st)));
+    case 33:
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 10, false, 1, true>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
+      break;
+    case 34:
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 9, false, 1, true>(ctx, D, X, Y, NE, st)));
+      else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
+      break;
+    default:                                                  // = 32: 6905 GB/s at NE = 4 M; 31 (12 CTAs): 6800; slab-per-thread accesses (24): 6250;
+                                                              // with two D stages and 8 CTAs (30): 5760 (profiles/r01_pa_variants.md)
+      if (NE % 8 == 0) RPB_CHECK((launch_mass<8, 32, 11, false, 1, true>(ctx, D, X, Y, NE, st)));
       else RPB_CHECK((launch_mass<8, 32, 12, false, 1>(ctx, D, X, Y, NE, st)));
       break;
   }
