@@ -49,6 +49,8 @@ const char* rpb200_version(void);
  *   Comm_HALO_PACKING_FUSED / Comm_HALO_EXCHANGE_FUSED: block_size 256 = contiguous chunk ranges per CTA,
  *       192 = the same with pack launches walking the list backwards (default), 128 = round-robin; ctas_per_sm; unroll 4 = L2 eviction-priority hints on; for the exchange
  *       unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch (default 2);
+ *   Algorithm_SCAN (large n, the TMA-staged kernel): unroll 9 = line-major result stores after a 4-lane transpose
+ *       (opt-in, first measurement pending: tools/time_quick.py scan_line);
  *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
  *   Apps_LTIMES: ctas_per_sm; unroll 5..8 = psi staged through a bulk-async ring, 10 = row-chunk A fragments, else line-major (default);
  *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.

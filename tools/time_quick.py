@@ -81,6 +81,30 @@ if "ltimes" in which:
     ctx.set_tuning("Apps_LTIMES", -1, 2, 4)
     del phi, psi
 
+if "scan_line" in which:
+    # Algorithm_SCAN, TMA path: row-per-thread stores (default) against line-major stores after a 4-lane transpose (unroll 9;
+    # written after the GPU budget of round 1 was spent -- this section is its first measurement): parity, then A/B/A/B
+    n = 1 << 27
+    x = torch.rand(n, **f64); ya = torch.empty(n, **f64); yb = torch.empty(n, **f64)
+    ctx.set_tuning("Algorithm_SCAN", -1, -1, 4); ctx.scan_exclusive(x, ya)
+    ctx.set_tuning("Algorithm_SCAN", -1, -1, 9); ctx.scan_exclusive(x, yb)
+    ok = bool(torch.equal(ya, yb))
+    print(f"scan line-major stores parity n=2^27: {'OK' if ok else 'FAILED'}", flush=True)
+    res["scan line-major parity 2^27"] = ok
+    for m_ in (n - 12345, 148 * 2 * 8192 + 16 * 7 + 3):          # ragged last tile, tail elements
+        ctx.set_tuning("Algorithm_SCAN", -1, -1, 4); ya.fill_(-1.0); ctx.scan_exclusive(x[:m_], ya[:m_], n=m_)
+        ctx.set_tuning("Algorithm_SCAN", -1, -1, 9); yb.fill_(-1.0); ctx.scan_exclusive(x[:m_], yb[:m_], n=m_)
+        ok = bool(torch.equal(ya, yb))
+        print(f"scan line-major stores parity n={m_}: {'OK' if ok else 'FAILED'}", flush=True)
+        res[f"scan line-major parity {m_}"] = ok
+    for rnd in range(2):
+        for var, label in ((4, "row-per-thread stores (default)"), (9, "line-major stores")):
+            ctx.set_tuning("Algorithm_SCAN", -1, -1, var)
+            ms = time_ms(lambda: ctx.scan_exclusive(x, ya), 20)
+            report(f"scan {label} round {rnd}", 16 * n, ms)
+    ctx.reset_tuning("Algorithm_SCAN")
+    del x, ya, yb
+
 if "ltimes_line" in which:
     # A fragments owned line-major (the default) against the row-chunk mapping (unroll 10): parity, then A/B/A/B
     nz0 = 37
