@@ -9,6 +9,13 @@ The binary is the reference's own raja-perf.exe built CPU-only from /root/refere
     raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [kernel flags]
 and the Base_Seq checksum printed in RAJAPerf-checksum.txt is recorded verbatim (20 digits).
 Output: tests/golden/ref_checksums.json.  The GPU box never runs this script.
+
+    python tests/golden/make_golden.py --mpi      (-> tests/golden/ref_checksums_mpi1.json)
+mints the goldens of the three kernels the reference only compiles WITH MPI -- Comm_HALO_EXCHANGE,
+Comm_HALO_EXCHANGE_FUSED, Comm_HALO_SENDRECV -- from oracle/_ref/raja-perf-mpi1.exe: the same unmodified sources built
+with ENABLE_MPI=On against the one-rank in-process MPI stand-in of oracle/mpi_stub/ (oracle/build_ref_mpi.sh), i.e. the
+periodic self-exchange of a 1 x 1 x 1 rank grid.  The HALO_PACKING / HALO_PACKING_FUSED cases are re-run there too: they
+must (and do) equal the non-MPI binary's.
 """
 import argparse
 import json
@@ -42,6 +49,16 @@ for k in ["Algorithm_MEMCPY", "Algorithm_MEMSET"]:      # calibration streams: t
 CASES += [("Comm_HALO_PACKING", 0, 1, []), ("Comm_HALO_PACKING", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"])]
 
 
+# the kernels that exist only in an MPI build, on one rank (+ the two pack kernels as a cross-check of the binary)
+MPI_CASES = []
+for k in ["Comm_HALO_EXCHANGE_FUSED", "Comm_HALO_EXCHANGE", "Comm_HALO_SENDRECV"]:
+    MPI_CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
+                  (k, 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1"]), (k, 8000, 2, []),
+                  (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "2"])]
+MPI_CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, []), ("Comm_HALO_PACKING_FUSED", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
+              ("Comm_HALO_PACKING", 0, 1, [])]
+
+
 def run_case(exe, kernel, size, reps, extra, workdir):
     out = os.path.join(workdir, "out")
     shutil.rmtree(out, ignore_errors=True)
@@ -59,18 +76,28 @@ def run_case(exe, kernel, size, reps, extra, workdir):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--exe", default=os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe"))
-    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "ref_checksums.json"))
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--mpi", action="store_true", help="the MPI-only Comm kernels from the one-rank MPI-stub build")
     a = ap.parse_args()
+    cases = CASES
+    if a.mpi:
+        cases = MPI_CASES
+        if a.exe.endswith("raja-perf.exe"):
+            a.exe = os.path.join(ROOT, "oracle", "_ref", "raja-perf-mpi1.exe")
+    if a.out is None:
+        a.out = os.path.join(ROOT, "tests", "golden", "ref_checksums_mpi1.json" if a.mpi else "ref_checksums.json")
     work = os.path.join(ROOT, "build", "golden_work")
     os.makedirs(work, exist_ok=True)
     rows = []
-    for kernel, size, reps, extra in CASES:
+    for kernel, size, reps, extra in cases:
         ck = run_case(a.exe, kernel, size, reps, extra, work)
         rows.append({"kernel": kernel, "size": size, "reps": reps, "flags": extra, "variant": "Base_Seq",
                      "checksum": ck})
         print(kernel, size, reps, extra, ck, file=sys.stderr)
     ver = subprocess.run([a.exe, "--help"], capture_output=True, text=True).stdout.splitlines()[:1]
-    json.dump({"source": "reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build, "
+    json.dump({"source": ("reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build with ENABLE_MPI=On against "
+                          "the one-rank in-process MPI stand-in oracle/mpi_stub (1 x 1 x 1 rank grid), " if a.mpi else
+                          "reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build, ") +
                          "g++ 13.3 -O3, glibc rand(), x87 long double",
                "command": "raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [flags]",
                "cases": rows}, open(a.out, "w"), indent=1)

@@ -1,0 +1,93 @@
+"""The one-rank MPI stand-in (oracle/mpi_stub: test infrastructure that lets the unmodified reference run its MPI-only
+Comm kernels here) must match messages the way MPI does on a self-communicator: by tag, oldest first, in any legal
+order of Irecv / Isend / Wait*.  The exchange goldens (tests/golden/ref_checksums_mpi1.json) rest on these rules."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "mpi_stub", "libmpistub.so")
+MPI_DOUBLE, MPI_BYTE, MPI_LONG_DOUBLE, MPI_SUM = 8, 1, 9, 1
+MPI_UNDEFINED, MPI_REQUEST_NULL = -32766, -1
+
+
+@pytest.fixture(scope="module")
+def mpi():
+    if not os.path.exists(SO):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
+    L = ctypes.CDLL(SO)
+    L.MPI_Wtime.restype = ctypes.c_double
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_rank_size_and_identity_collectives(mpi):
+    r, s = ctypes.c_int(-1), ctypes.c_int(-1)
+    mpi.MPI_Comm_rank(0, ctypes.byref(r)); mpi.MPI_Comm_size(0, ctypes.byref(s))
+    assert (r.value, s.value) == (0, 1)
+    a, b = np.arange(5, dtype=np.float64), np.zeros(5)
+    assert mpi.MPI_Allreduce(_p(a), _p(b), 5, MPI_DOUBLE, MPI_SUM, 0) == 0 and np.array_equal(a, b)
+    c = np.zeros(40, dtype=np.uint8)
+    assert mpi.MPI_Gather(_p(a), 40, MPI_BYTE, _p(c), 40, MPI_BYTE, 0, 0) == 0 and np.array_equal(c.view(np.float64), a)
+    assert mpi.MPI_Barrier(0) == 0 and mpi.MPI_Wtime() > 0.0
+
+
+def test_receives_posted_first_are_matched_by_tag(mpi):
+    """The suite's order: Irecv x N, Isend x N, Waitall (HALO_EXCHANGE_FUSED-Seq.cpp:35-116)."""
+    n = 26
+    recv = [np.full(4, -1.0) for _ in range(n)]
+    send = [np.full(4, float(t)) for t in range(n)]
+    rreq, sreq = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    for t in range(n):                                   # receive l carries tag 25 - l, like recv_tag = opposite neighbour
+        mpi.MPI_Irecv(_p(recv[t]), 4, MPI_DOUBLE, 0, n - 1 - t, 0, ctypes.byref(rreq, 4 * t))
+    for t in range(n):
+        mpi.MPI_Isend(_p(send[t]), 4, MPI_DOUBLE, 0, t, 0, ctypes.byref(sreq, 4 * t))
+    assert mpi.MPI_Waitall(n, rreq, None) == 0 and mpi.MPI_Waitall(n, sreq, None) == 0
+    assert all(r == MPI_REQUEST_NULL for r in rreq) and all(r == MPI_REQUEST_NULL for r in sreq)
+    for t in range(n):
+        assert np.all(recv[t] == float(n - 1 - t))
+
+
+def test_sends_before_receives_are_buffered_and_do_not_overtake(mpi):
+    first, second = np.full(3, 1.0), np.full(3, 2.0)
+    s1, s2, r1, r2 = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    mpi.MPI_Isend(_p(first), 3, MPI_DOUBLE, 0, 7, 0, ctypes.byref(s1))
+    mpi.MPI_Isend(_p(second), 3, MPI_DOUBLE, 0, 7, 0, ctypes.byref(s2))
+    first[:] = -9.0                                      # the payload was copied at Isend
+    mpi.MPI_Wait(ctypes.byref(s1), None)                 # a buffered send completes locally
+    a, b = np.zeros(3), np.zeros(3)
+    mpi.MPI_Irecv(_p(a), 3, MPI_DOUBLE, 0, 7, 0, ctypes.byref(r1))
+    mpi.MPI_Irecv(_p(b), 3, MPI_DOUBLE, 0, 7, 0, ctypes.byref(r2))
+    mpi.MPI_Wait(ctypes.byref(r1), None); mpi.MPI_Wait(ctypes.byref(r2), None); mpi.MPI_Wait(ctypes.byref(s2), None)
+    assert np.all(a == 1.0) and np.all(b == 2.0)
+
+
+def test_waitany_hands_out_every_completed_request_once(mpi):
+    """HALO_EXCHANGE-Seq.cpp:34-116 unpacks in MPI_Waitany order."""
+    n = 5
+    recv = [np.zeros(2) for _ in range(n)]
+    rreq = (ctypes.c_int * n)()
+    for t in range(n):
+        mpi.MPI_Irecv(_p(recv[t]), 2, MPI_DOUBLE, 0, 100 + t, 0, ctypes.byref(rreq, 4 * t))
+    sreq = ctypes.c_int()
+    for t in (3, 0, 4, 1, 2):
+        payload = np.full(2, float(t))
+        mpi.MPI_Isend(_p(payload), 2, MPI_DOUBLE, 0, 100 + t, 0, ctypes.byref(sreq))
+        mpi.MPI_Wait(ctypes.byref(sreq), None)
+    seen = []
+    for _ in range(n):
+        idx = ctypes.c_int(-1)
+        mpi.MPI_Waitany(n, rreq, ctypes.byref(idx), None)
+        seen.append(idx.value)
+    assert sorted(seen) == list(range(n))
+    idx = ctypes.c_int(0)
+    mpi.MPI_Waitany(n, rreq, ctypes.byref(idx), None)
+    assert idx.value == MPI_UNDEFINED
+    for t in range(n):
+        assert np.all(recv[t] == float(t))

@@ -10,6 +10,9 @@ import pytest
 import oracle
 
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums.json")))
+# the kernels the reference compiles only WITH MPI, from the unmodified sources linked against the one-rank MPI
+# stand-in of oracle/mpi_stub (oracle/build_ref_mpi.sh; generator: tests/golden/make_golden.py --mpi)
+GOLD_MPI1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums_mpi1.json")))
 
 
 def _iparams(kernel, flags):
@@ -27,6 +30,24 @@ def test_oracle_reproduces_reference_checksum(case):
     ref = np.longdouble(case["checksum"])
     # 20 printed digits of an 80-bit long double: allow 2 units in the 19th significant digit
     assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19) + np.longdouble(0), (got, ref)
+
+
+@pytest.mark.parametrize("case", GOLD_MPI1["cases"], ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}-{'_'.join(c['flags'][1::2])}")
+def test_oracle_reproduces_reference_exchange_checksums_on_one_rank(case):
+    """HALO_EXCHANGE, HALO_EXCHANGE_FUSED, HALO_SENDRECV: the oracle's in-process delivery against the reference's own
+    Irecv / pack / Isend / Waitall / unpack code run on a 1 x 1 x 1 rank grid."""
+    got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"]))
+    ref = np.longdouble(case["checksum"])
+    assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19), (got, ref)
+
+
+def test_mpi_stub_build_agrees_with_the_plain_build_on_the_pack_kernels():
+    """The two pack kernels exist in both reference builds: identical checksums, so the MPI-stub binary is the same suite."""
+    plain = {(c["kernel"], c["size"], c["reps"], tuple(c["flags"])): c["checksum"] for c in GOLD["cases"]}
+    both = [c for c in GOLD_MPI1["cases"] if (c["kernel"], c["size"], c["reps"], tuple(c["flags"])) in plain]
+    assert len(both) >= 3
+    for c in both:
+        assert c["checksum"] == plain[(c["kernel"], c["size"], c["reps"], tuple(c["flags"]))]
 
 
 def test_halo_exchange_single_rank_matches_any_rank_grid():
