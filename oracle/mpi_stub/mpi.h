@@ -1,15 +1,16 @@
 /*
- * mpi.h -- a ONE-RANK, in-process stand-in for the MPI the reference suite is written against.
+ * mpi.h -- an in-process / shared-memory stand-in for the MPI the reference suite is written against.
  *
  * TEST INFRASTRUCTURE ONLY (oracle/): this image has no MPI, and without MPI the reference compiles its
  * Comm_HALO_EXCHANGE / HALO_EXCHANGE_FUSED / HALO_SENDRECV kernels out (RAJAPerfSuite.hpp:177-181).  Linking the
  * UNMODIFIED reference sources against this stub (oracle/build_ref_mpi.sh) gives a reference binary that runs those
- * kernels on one rank, where every one of the 26 neighbours of the periodic rank grid is the rank itself -- the case
- * the P-rank result is equal to.  tests/golden/make_golden.py mints the exchange goldens from it.
+ * kernels: on one rank, where every one of the 26 neighbours of the periodic rank grid is the rank itself, and on P ranks
+ * -- P processes of the binary over a shared-memory arena (RPB_MPI_SIZE / RPB_MPI_RANK / RPB_MPI_SHM, see mpi_stub.c;
+ * the launcher is mpirun() in tests/golden/make_golden.py).  make_golden.py --mpi mints the exchange goldens from it.
  *
  * Only what the suite calls (grep MPI_ src/): Init/Finalize, Comm_rank/size, Barrier, Allreduce, Gather, Bcast,
- * Isend/Irecv, Wait/Waitall/Waitany.  A message is matched to a receive by (tag) exactly as MPI matches
- * (source, tag, comm) when source = dest = 0; sends are buffered, so any call order the standard allows works.
+ * Isend/Irecv, Wait/Waitall/Waitany.  A message is matched to a receive by (source, tag), oldest first, as MPI does;
+ * sends are buffered, so any call order the standard allows works.
  */
 #ifndef RPB_ORACLE_MPI_STUB_H
 #define RPB_ORACLE_MPI_STUB_H

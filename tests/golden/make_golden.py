@@ -49,23 +49,49 @@ for k in ["Algorithm_MEMCPY", "Algorithm_MEMSET"]:      # calibration streams: t
 CASES += [("Comm_HALO_PACKING", 0, 1, []), ("Comm_HALO_PACKING", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"])]
 
 
-# the kernels that exist only in an MPI build, on one rank (+ the two pack kernels as a cross-check of the binary)
+# the kernels that exist only in an MPI build: (kernel, size, reps, flags, ranks).  One rank = the in-process transport of
+# the stub (+ the two pack kernels as a cross-check of the binary); P ranks = P processes of the same binary over the stub's
+# shared-memory transport, rank grid given explicitly or left to the suite's default factorisation (RunParams.cpp:1211-1251)
 MPI_CASES = []
 for k in ["Comm_HALO_EXCHANGE_FUSED", "Comm_HALO_EXCHANGE", "Comm_HALO_SENDRECV"]:
-    MPI_CASES += [(k, 0, 1, []), (k, 0, 3, []), (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
-                  (k, 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1"]), (k, 8000, 2, []),
-                  (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "2"])]
-MPI_CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, []), ("Comm_HALO_PACKING_FUSED", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"]),
-              ("Comm_HALO_PACKING", 0, 1, [])]
+    MPI_CASES += [(k, 0, 1, [], 1), (k, 0, 3, [], 1), (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"], 1),
+                  (k, 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1"], 1), (k, 8000, 2, [], 1),
+                  (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "2"], 1)]
+    MPI_CASES += [(k, 27000, 2, [], 2), (k, 8000, 3, ["--halo_width", "2", "--halo_num_vars", "2"], 4),
+                  (k, 27000, 2, ["--halo_width", "2", "--halo_num_vars", "2", "--mpi_3d_division", "2", "2", "2"], 8),
+                  (k, 8000, 2, ["--mpi_3d_division", "3", "1", "2"], 6),
+                  (k, 1000, 1, ["--halo_width", "3", "--halo_num_vars", "1", "--mpi_3d_division", "1", "2", "1"], 2)]
+MPI_CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, [], 1), ("Comm_HALO_PACKING_FUSED", 27000, 2, ["--halo_width", "2", "--halo_num_vars", "5"], 1),
+              ("Comm_HALO_PACKING", 0, 1, [], 1)]
 
 
-def run_case(exe, kernel, size, reps, extra, workdir):
+def mpirun(nranks, cmd, timeout=600):
+    """P processes of `cmd` over the stub's shared-memory transport (oracle/mpi_stub/mpi_stub.c): one zero-filled arena
+    under /dev/shm, RPB_MPI_SIZE / RPB_MPI_RANK / RPB_MPI_SHM in the environment; rank 0 writes the reports."""
+    path = f"/dev/shm/rpb_mpi_{os.getpid()}"
+    with open(path, "wb") as f:
+        f.truncate(256 << 20)
+    try:
+        procs = [subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                                  env=dict(os.environ, OMP_NUM_THREADS="1", RPB_MPI_SIZE=str(nranks), RPB_MPI_RANK=str(r),
+                                           RPB_MPI_SHM=path)) for r in range(nranks)]
+        rcs = [p.wait(timeout=timeout) for p in procs]
+    finally:
+        os.unlink(path)
+    if any(rcs):
+        raise RuntimeError(f"{nranks}-rank run failed: {rcs}: {' '.join(cmd)}")
+
+
+def run_case(exe, kernel, size, reps, extra, workdir, ranks=1):
     out = os.path.join(workdir, "out")
     shutil.rmtree(out, ignore_errors=True)
     cmd = [exe, "--checkrun", str(reps), "--disable-warmup", "-k", kernel, "-v", "Base_Seq",
            "--outdir", out] + (["--size", str(size)] if size else []) + extra
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
-                   env=dict(os.environ, OMP_NUM_THREADS="1"))
+    if ranks > 1:
+        mpirun(ranks, cmd)
+    else:
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
     txt = open(os.path.join(out, "RAJAPerf-checksum.txt")).read()
     m = re.search(r"^Base_Seq-\S+\s+(\S+)", txt, re.M)
     if not m:
@@ -89,14 +115,18 @@ def main():
     work = os.path.join(ROOT, "build", "golden_work")
     os.makedirs(work, exist_ok=True)
     rows = []
-    for kernel, size, reps, extra in cases:
-        ck = run_case(a.exe, kernel, size, reps, extra, work)
+    for case in cases:
+        kernel, size, reps, extra = case[:4]
+        ranks = case[4] if len(case) > 4 else 1
+        ck = run_case(a.exe, kernel, size, reps, extra, work, ranks)
         rows.append({"kernel": kernel, "size": size, "reps": reps, "flags": extra, "variant": "Base_Seq",
                      "checksum": ck})
-        print(kernel, size, reps, extra, ck, file=sys.stderr)
+        if a.mpi:
+            rows[-1]["ranks"] = ranks        # the checksum is the report's average over the ranks
+        print(kernel, size, reps, extra, ranks, ck, file=sys.stderr)
     ver = subprocess.run([a.exe, "--help"], capture_output=True, text=True).stdout.splitlines()[:1]
     json.dump({"source": ("reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build with ENABLE_MPI=On against "
-                          "the one-rank in-process MPI stand-in oracle/mpi_stub (1 x 1 x 1 rank grid), " if a.mpi else
+                          "the MPI stand-in oracle/mpi_stub (one rank in process, or P processes over its shared-memory transport), " if a.mpi else
                           "reference raja-perf.exe (suite v2024.07.0, commit 9af20b3), CPU-only build, ") +
                          "g++ 13.3 -O3, glibc rand(), x87 long double",
                "command": "raja-perf.exe --checkrun R --disable-warmup -k K -v Base_Seq [--size S] [flags]",

@@ -91,3 +91,70 @@ def test_waitany_hands_out_every_completed_request_once(mpi):
     assert idx.value == MPI_UNDEFINED
     for t in range(n):
         assert np.all(recv[t] == float(t))
+
+
+_RANK_PROGRAM = r"""
+import ctypes, sys
+import numpy as np
+L = ctypes.CDLL(sys.argv[1])
+p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+L.MPI_Init(None, None)
+r, s = ctypes.c_int(), ctypes.c_int()
+L.MPI_Comm_rank(0, ctypes.byref(r)); L.MPI_Comm_size(0, ctypes.byref(s))
+r, s = r.value, s.value
+# ring: two messages with the same tag to the right neighbour (must not overtake), one with another tag to the left
+right, left = (r + 1) % s, (r - 1) % s
+a1, a2, b = np.full(4, 10.0 * r + 1), np.full(4, 10.0 * r + 2), np.full(2, 100.0 + r)
+req = (ctypes.c_int * 6)()
+ra1, ra2, rb = np.zeros(4), np.zeros(4), np.zeros(2)
+L.MPI_Irecv(p(ra1), 4, 8, left, 5, 0, ctypes.byref(req, 0))
+L.MPI_Irecv(p(ra2), 4, 8, left, 5, 0, ctypes.byref(req, 4))
+L.MPI_Irecv(p(rb), 2, 8, right, 6, 0, ctypes.byref(req, 8))
+L.MPI_Isend(p(a1), 4, 8, right, 5, 0, ctypes.byref(req, 12))
+L.MPI_Isend(p(a2), 4, 8, right, 5, 0, ctypes.byref(req, 16))
+L.MPI_Isend(p(b), 2, 8, left, 6, 0, ctypes.byref(req, 20))
+done = []
+for _ in range(3):
+    i = ctypes.c_int(-1)
+    L.MPI_Waitany(3, req, ctypes.byref(i), None)
+    done.append(i.value)
+L.MPI_Waitall(6, req, None)
+ok = sorted(done) == [0, 1, 2] and np.all(ra1 == 10.0 * left + 1) and np.all(ra2 == 10.0 * left + 2) and np.all(rb == 100.0 + right)
+# collectives: long double sum / max in rank order, gather of bytes, broadcast
+x = np.array([r + 0.25], dtype=np.longdouble); y = np.zeros(1, dtype=np.longdouble)
+L.MPI_Allreduce(p(x), p(y), 1, 9, 1, 0)
+ok = ok and y[0] == sum(q + 0.25 for q in range(s))
+L.MPI_Allreduce(p(x), p(y), 1, 9, 3, 0)
+ok = ok and y[0] == s - 1 + 0.25
+g = np.zeros(8 * s, dtype=np.uint8); mine = np.array([float(r)])
+L.MPI_Gather(p(mine), 8, 1, p(g), 8, 1, 0, 0)
+if r == 0:
+    ok = ok and g.view(np.float64).tolist() == [float(q) for q in range(s)]
+v = np.array([42.0 if r == 0 else -1.0])
+L.MPI_Bcast(p(v), 1, 8, 0, 0)
+ok = ok and v[0] == 42.0
+L.MPI_Barrier(0)
+L.MPI_Finalize()
+sys.exit(0 if ok else 3)
+"""
+
+
+@pytest.mark.parametrize("nranks", [2, 5])
+def test_shared_memory_transport_ring_and_collectives(mpi, nranks, tmp_path):
+    """P processes over the stub's shared-memory arena: tag + source matching without overtaking, Waitany, and the
+    collectives the suite's reports use (Executor.cpp:70-118)."""
+    import subprocess
+    import sys
+    prog = tmp_path / "rank.py"
+    prog.write_text(_RANK_PROGRAM)
+    arena = f"/dev/shm/rpb_mpi_test_{os.getpid()}_{nranks}"
+    with open(arena, "wb") as f:
+        f.truncate(64 << 20)
+    try:
+        procs = [subprocess.Popen([sys.executable, str(prog), SO],
+                                  env=dict(os.environ, RPB_MPI_SIZE=str(nranks), RPB_MPI_RANK=str(r), RPB_MPI_SHM=arena))
+                 for r in range(nranks)]
+        rcs = [p.wait(timeout=120) for p in procs]
+    finally:
+        os.unlink(arena)
+    assert rcs == [0] * nranks

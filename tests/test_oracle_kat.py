@@ -15,12 +15,22 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_che
 GOLD_MPI1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums_mpi1.json")))
 
 
-def _iparams(kernel, flags):
+def _iparams(kernel, flags, ranks=1):
+    flags = list(flags)
+    division = None
+    if "--mpi_3d_division" in flags:                       # the one option with three values
+        i = flags.index("--mpi_3d_division")
+        division = [int(v) for v in flags[i + 1:i + 4]]
+        del flags[i:i + 4]
     f = dict(zip(flags[0::2], flags[1::2]))
     if kernel == "Apps_LTIMES":
         return [int(f.get("--ltimes_num_d", 64)), int(f.get("--ltimes_num_g", 32)), int(f.get("--ltimes_num_m", 25))]
     if kernel.startswith("Comm_HALO"):
-        return [int(f.get("--halo_width", 1)), int(f.get("--halo_num_vars", 3)), 1, 1, 1]
+        if division is None:                               # the suite's default factorisation (RunParams.cpp:1211-1251)
+            from rajaperf_b200.dist import rank_grid
+            division = rank_grid(ranks)
+        assert division[0] * division[1] * division[2] == ranks
+        return [int(f.get("--halo_width", 1)), int(f.get("--halo_num_vars", 3))] + division
     return None
 
 
@@ -32,13 +42,38 @@ def test_oracle_reproduces_reference_checksum(case):
     assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19) + np.longdouble(0), (got, ref)
 
 
-@pytest.mark.parametrize("case", GOLD_MPI1["cases"], ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}-{'_'.join(c['flags'][1::2])}")
-def test_oracle_reproduces_reference_exchange_checksums_on_one_rank(case):
+@pytest.mark.parametrize("case", GOLD_MPI1["cases"],
+                         ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}-p{c['ranks']}-{'_'.join(x for x in c['flags'] if not x.startswith('--'))}")
+def test_oracle_reproduces_reference_exchange_checksums(case):
     """HALO_EXCHANGE, HALO_EXCHANGE_FUSED, HALO_SENDRECV: the oracle's in-process delivery against the reference's own
-    Irecv / pack / Isend / Waitall / unpack code run on a 1 x 1 x 1 rank grid."""
-    got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"]))
+    Irecv / pack / Isend / Waitall / unpack code, run on 1 rank (every neighbour is the rank itself) and on 2 / 4 / 6 / 8
+    ranks (P processes over the MPI stand-in's shared-memory transport; the report averages the P checksums)."""
+    got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"], case["ranks"]))
     ref = np.longdouble(case["checksum"])
-    assert abs(got - ref) <= abs(ref) * np.longdouble(2e-19), (got, ref)
+    tol = np.longdouble(2e-19) if case["ranks"] == 1 else np.longdouble(1e-18)      # + the rounding of the rank average
+    assert abs(got - ref) <= abs(ref) * tol, (got, ref)
+
+
+def test_reference_multi_rank_checksums_equal_its_one_rank_checksums():
+    """What SURVEY 8c derived on paper, now from the reference's own runs: every rank holds identical data, so the P-rank
+    result equals the periodic self-exchange of one rank, for any rank grid."""
+    one = {(c["kernel"], c["size"], c["reps"], _key(c["flags"])): np.longdouble(c["checksum"]) for c in GOLD_MPI1["cases"] if c["ranks"] == 1}
+    multi = [c for c in GOLD_MPI1["cases"] if c["ranks"] > 1]
+    hit = 0
+    for c in multi:
+        k = (c["kernel"], c["size"], c["reps"], _key(c["flags"]))
+        if k in one:
+            hit += 1
+            assert abs(np.longdouble(c["checksum"]) - one[k]) <= abs(one[k]) * np.longdouble(1e-18), c
+    assert len(multi) >= 15 and hit >= 9
+
+
+def _key(flags):
+    flags = list(flags)
+    if "--mpi_3d_division" in flags:
+        i = flags.index("--mpi_3d_division")
+        del flags[i:i + 4]
+    return tuple(flags)
 
 
 def test_mpi_stub_build_agrees_with_the_plain_build_on_the_pack_kernels():
