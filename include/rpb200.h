@@ -51,6 +51,8 @@ const char* rpb200_version(void);
  *       unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch (default 2);
  *   Algorithm_SCAN (large n, the TMA-staged kernel): unroll 9 = line-major result stores after a 4-lane transpose
  *       (opt-in, first measurement pending: tools/time_quick.py scan_line);
+ *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 9 = digit histograms with lane-private 16-bit counters (opt-in, first
+ *       measurement pending: tools/time_quick.py sort_hist);
  *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
  *   Apps_LTIMES: ctas_per_sm; unroll 5..8 = psi staged through a bulk-async ring, 10 = row-chunk A fragments, else line-major (default);
  *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.

@@ -143,6 +143,102 @@ sort_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n,
   }
 }
 
+// ---- the same histograms with LANE-PRIVATE counters (opt-in: tuning `unroll` 9 of Algorithm_SORT / Algorithm_SORTPAIRS;
+// written after the GPU budget of round 1 was spent: NOT YET MEASURED, tools/time_quick.py sort_hist is its first A/B) ---------
+// sort_hist_kernel is bound by its shared-memory atomics: 32 random bins per warp instruction fall on ~3.5 addresses of the
+// busiest bank (437 us for 2^27 keys against 165 us of DRAM time).  Here lane l of every warp counts in its own column: bin b
+// of digit d lives in the 16-bit half (b & 1) of word col[d][(b >> 1) * 32 + l], so the 32 atomics of a warp instruction hit
+// 32 different banks whatever the digits are.  A column is shared by the 32 warps of the CTA, hence a 16-bit counter may
+// receive 32 increments per "round" of one key per thread: the columns are folded into the 64-bit global histograms (and
+// cleared) every 2040 keys per thread, and at the end.  The top byte keeps the warp-uniform shortcut of hist_one.
+constexpr int HL_WARPS = 32, HL_BLOCK = HL_WARPS * 32, HL_DIGITS = NUM_PASSES - 1;
+constexpr int HL_COL_WORDS = (RADIX / 2) * 32;                       // words per digit: 128 bin pairs x 32 lanes
+constexpr int HL_FLUSH_KEYS = 2040;                                  // 32 warps x 2040 < 65536
+constexpr size_t HL_SMEM = sizeof(unsigned int) * (HL_DIGITS * HL_COL_WORDS + RADIX);
+
+__device__ __forceinline__ void hist_lane_one(unsigned int* col, unsigned int* s_top, unsigned long long k, bool ok, int lane)
+{
+  const unsigned int lo = (unsigned int)k, hi = (unsigned int)(k >> 32);
+  if (ok) {
+#pragma unroll
+    for (int d = 0; d < HL_DIGITS; ++d) {
+      const unsigned int b = d < 4 ? (lo >> (8 * d)) & 0xffu : (hi >> (8 * (d - 4))) & 0xffu;
+      atomicAdd(&col[d * HL_COL_WORDS + ((b >> 1) << 5) + lane], 1u << ((b & 1u) << 4));
+    }
+  }
+  const unsigned int d7 = hi >> 24;
+  const unsigned int d7_0 = __shfl_sync(0xffffffffu, d7, 0);
+  if (__all_sync(0xffffffffu, ok && d7 == d7_0)) {
+    if (lane == 0) atomicAdd(&s_top[d7], 32u);
+  } else if (ok) {
+    atomicAdd(&s_top[d7], 1u);
+  }
+}
+
+// fold the lane columns into the global histograms and clear them (whole CTA, between two barriers)
+__device__ __forceinline__ void hist_lane_flush(unsigned int* col, unsigned long long* __restrict__ g_hist)
+{
+  __syncthreads();
+  for (int e = threadIdx.x; e < HL_DIGITS * RADIX; e += HL_BLOCK) {
+    const int d = e >> 8, b = e & 0xff;
+    const unsigned int* row = col + d * HL_COL_WORDS + ((b >> 1) << 5);
+    const int sh = (b & 1) << 4;
+    unsigned int c = 0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) c += (row[(l + threadIdx.x) & 31] >> sh) & 0xffffu;     // rotated: no common bank
+    if (c) atomicAdd(&g_hist[e], (unsigned long long)c);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HL_DIGITS * HL_COL_WORDS; i += HL_BLOCK) col[i] = 0u;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(HL_BLOCK, 1)
+sort_hist_lanes_kernel(const unsigned long long* __restrict__ keys, int64_t n, unsigned long long* __restrict__ g_hist,
+                       int vector_ok)
+{
+  extern __shared__ __align__(16) unsigned int hl_smem[];
+  unsigned int* col = hl_smem;                                        // [HL_DIGITS][128][32]
+  unsigned int* s_top = hl_smem + HL_DIGITS * HL_COL_WORDS;           // [RADIX]
+  for (int i = threadIdx.x; i < HL_DIGITS * HL_COL_WORDS + RADIX; i += HL_BLOCK) hl_smem[i] = 0u;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nv = vector_ok ? n / 4 : 0;                          // whole 4-key vectors
+  // every thread of the CTA runs the same number of trips (the flush is a CTA barrier): round the trip space up per CTA
+  const int64_t trips = (nv + 2 * stride - 1) / (2 * stride);
+  int since_flush = 0;
+  for (int64_t it = 0; it < trips; ++it) {
+    const int64_t v0 = gtid + 2 * it * stride, v1 = v0 + stride;
+    const bool ok0 = v0 < nv, ok1 = v1 < nv;
+    dbl4 q0 = {0.0, 0.0, 0.0, 0.0}, q1 = {0.0, 0.0, 0.0, 0.0};
+    if (ok0) q0 = ldg256_stream(reinterpret_cast<const double*>(keys) + 4 * v0);
+    if (ok1) q1 = ldg256_stream(reinterpret_cast<const double*>(keys) + 4 * v1);
+    const double e0[4] = {q0.x, q0.y, q0.z, q0.w}, e1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hist_lane_one(col, s_top, key_encode((unsigned long long)__double_as_longlong(e0[j])), ok0, lane);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hist_lane_one(col, s_top, key_encode((unsigned long long)__double_as_longlong(e1[j])), ok1, lane);
+    since_flush += 8;
+    if (since_flush + 8 > HL_FLUSH_KEYS) { hist_lane_flush(col, g_hist); since_flush = 0; }     // CTA-uniform
+  }
+  const int64_t r0 = 4 * nv;                                          // scalar remainder (everything if unaligned)
+  const int64_t rtrips = (n - r0 + stride - 1) / stride;
+  for (int64_t it = 0; it < rtrips; ++it) {
+    const int64_t i = r0 + gtid + it * stride;
+    const bool ok = i < n;
+    hist_lane_one(col, s_top, ok ? key_encode(keys[i]) : 0ull, ok, lane);
+    if (++since_flush + 8 > HL_FLUSH_KEYS) { hist_lane_flush(col, g_hist); since_flush = 0; }
+  }
+  hist_lane_flush(col, g_hist);
+  for (int i = threadIdx.x; i < RADIX; i += HL_BLOCK) {
+    const unsigned int c = s_top[i];
+    if (c) atomicAdd(&g_hist[HL_DIGITS * RADIX + i], (unsigned long long)c);
+  }
+}
+
 // exclusive scan of each digit histogram in place: g_hist[p][b] = #keys with digit_p < b
 __global__ void __launch_bounds__(RADIX)
 sort_hist_scan_kernel(unsigned long long* __restrict__ g_hist)
@@ -370,7 +466,15 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
     int grid = ctx->sm_count * 4;
     int64_t need = (n + 511) / 512;
     if (need < grid) grid = (int)need;
-    sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist, rpb_aligned(keys, 32) ? 1 : 0);
+    if (ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll == 9) {          // opt-in: lane-private counters, one CTA per SM
+      int g1 = ctx->sm_count;
+      const int64_t need1 = (n + HL_BLOCK - 1) / HL_BLOCK;
+      if (need1 < g1) g1 = (int)need1;
+      RPB_CHECK(cudaFuncSetAttribute(sort_hist_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HL_SMEM));
+      sort_hist_lanes_kernel<<<g1, HL_BLOCK, HL_SMEM, st>>>((const unsigned long long*)keys, n, hist, rpb_aligned(keys, 32) ? 1 : 0);
+    } else {
+      sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist, rpb_aligned(keys, 32) ? 1 : 0);
+    }
     RPB_LAUNCH_CHECK();
     sort_hist_scan_kernel<<<NUM_PASSES, RADIX, 0, st>>>(hist);
     RPB_LAUNCH_CHECK();

@@ -105,6 +105,35 @@ if "scan_line" in which:
     ctx.reset_tuning("Algorithm_SCAN")
     del x, ya, yb
 
+if "sort_hist" in which:
+    # SORT / SORTPAIRS with the lane-private histogram kernel (tuning unroll 9; written after the GPU budget of round 1 was
+    # spent -- this section is its first measurement) against the default histogram: parity of the sorted output, then A/B/A/B
+    n = 1 << 27
+    x = torch.randint(0, 2**31 - 1, (n,), device="cuda").to(torch.float64).div_(2147483647.0)      # rand()/RAND_MAX
+    scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
+    for m_ in (n, 1000003, 4097):
+        outs = []
+        for var in (4, 9):
+            ctx.set_tuning("Algorithm_SORT", -1, -1, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, -1, var)
+            k = x[:m_].clone(); ctx.sort_keys(k, scratch, n=m_)
+            kb, vb = torch.empty(m_ + 1, **f64), torch.empty(m_ + 1, **f64)
+            k2, v2 = (kb[1:], vb[1:]) if m_ < n else (kb[:m_], vb[:m_])                # [1:]: key pointer not 32-byte aligned
+            k2.copy_(x[:m_]); v2.copy_(x[:m_])
+            ctx.sort_pairs(k2, v2, scratch, n=m_)
+            outs.append((k, k2, v2))
+        ok = all(bool(torch.equal(a, b)) for a, b in zip(outs[0], outs[1])) and bool((outs[0][0][1:] >= outs[0][0][:-1]).all())
+        print(f"sort lane-private histogram parity n={m_}: {'OK' if ok else 'FAILED'}", flush=True)
+        res[f"sort_hist parity {m_}"] = ok
+        del outs
+    y = torch.empty_like(x)
+    for rnd in range(2):
+        for var, label in ((4, "shared-bin histogram (default)"), (9, "lane-private histogram")):
+            ctx.set_tuning("Algorithm_SORT", -1, -1, var)
+            ms = time_ms(lambda: ctx.sort_keys(y, scratch), 5, 2, setup=lambda: y.copy_(x))
+            report(f"sort keys, {label} round {rnd}", 16 * n, ms, mkeys_per_s=n / ms / 1e3)
+    ctx.reset_tuning("Algorithm_SORT"); ctx.reset_tuning("Algorithm_SORTPAIRS")
+    del x, y, scratch
+
 if "ltimes_line" in which:
     # A fragments owned line-major (the default) against the row-chunk mapping (unroll 10): parity, then A/B/A/B
     nz0 = 37
