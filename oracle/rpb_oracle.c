@@ -7,7 +7,10 @@
  *
  * Parity pin: every orc_kat_* driver below reproduces the Base_Seq checksum the
  * reference's own build prints (tests/golden/ref_checksums.json, BASELINE.md
- * section 2) -- see tests/test_oracle_kat.py.
+ * section 2) -- see tests/test_oracle_kat.py.  The three kernels the reference
+ * compiles only with MPI (HALO_EXCHANGE, HALO_EXCHANGE_FUSED, HALO_SENDRECV) are
+ * pinned to tests/golden/ref_checksums_mpi1.json: the unmodified reference built
+ * against the MPI stand-in of oracle/mpi_stub, run on 1, 2, 4, 6 and 8 ranks.
  *
  * All file:line citations are relative to /root/reference/src.  Build with
  * -O2 -ffp-contract=off (no FMA contraction, no value-changing FP optimisation)

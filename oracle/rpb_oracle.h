@@ -12,7 +12,9 @@
  *
  * Parity pin: tests/test_oracle_kat.py checks every orc_kat_* driver against the
  * known-answer checksums minted from the reference's own Base_Seq build
- * (tests/golden/ref_checksums.json).
+ * (tests/golden/ref_checksums.json; the MPI-only exchange
+ * kernels: tests/golden/ref_checksums_mpi1.json, from the reference built against
+ * oracle/mpi_stub and run on 1-8 ranks).
  */
 #ifndef RPB_ORACLE_H
 #define RPB_ORACLE_H
