@@ -15,6 +15,26 @@ import oracle
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "rajaperf_b200", "suite", "raja-perf-b200.exe")
 GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_checksums.json")))["cases"]
+# the MPI-only exchange kernels, printed by the unmodified reference built against oracle/mpi_stub and run on 1-8 ranks
+GOLD_MPI = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_checksums_mpi1.json")))["cases"]
+
+
+def reference_exchange_golden(kernel, size, reps, halo_width, num_vars, division):
+    """The reference's own checksum for this exchange configuration, if one was minted (the result does not depend on the
+    rank grid, so a golden of any grid with the same number of ranks or of one rank qualifies), else None."""
+    want = ["--halo_width", str(halo_width), "--halo_num_vars", str(num_vars)]
+    ranks = division[0] * division[1] * division[2]
+    best = None
+    for c in GOLD_MPI:
+        flags = list(c["flags"])
+        if "--mpi_3d_division" in flags:
+            i = flags.index("--mpi_3d_division")
+            del flags[i:i + 4]
+        flags = flags or ["--halo_width", "1", "--halo_num_vars", "3"]
+        if c["kernel"] == kernel and c["size"] == size and c["reps"] == reps and flags == want and c["ranks"] in (ranks, 1):
+            if best is None or c["ranks"] == ranks:
+                best = c
+    return None if best is None else np.longdouble(best["checksum"])
 
 # parity class per kernel (SURVEY 8a): bit-exact => the 20 printed digits agree to the last place or two
 # of a long double; tolerance class => the suite's own 1e-7 absolute bound (test-raja-perf-suite.cpp:167)
@@ -129,6 +149,9 @@ def test_halo_exchange_fused_rank_grids_match_oracle(kernel, division, tmp_path)
     got = read_checksum(tmp_path)
     ref = oracle.kat("Comm_HALO_EXCHANGE_FUSED", 27000, 2, [2, 2] + list(division))
     assert abs(got - ref) <= abs(ref) * np.longdouble(1e-18), (got, ref)
+    gold = reference_exchange_golden(kernel, 27000, 2, 2, 2, division)      # the reference's own run (1 rank / 8 ranks)
+    assert gold is not None
+    assert abs(got - gold) <= abs(gold) * np.longdouble(4e-18), (got, gold)
 
 
 @pytest.mark.gpu
