@@ -25,6 +25,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref", "raja-perf-cuda.exe")
+REF_MPI = os.path.join(ROOT, "oracle", "_ref", "raja-perf-cuda-mpi1.exe")   # CUDA + MPI code paths over oracle/mpi_stub, one rank
 REF_CPU = os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe")      # the CPU-only build of the same sources
 OURS = os.path.join(ROOT, "rajaperf_b200", "suite", "raja-perf-b200.exe")
 CPU_REPS = 3            # reps of the Base_OpenMP / RAJA_OpenMP leg (a bounded sample: the CPU is ~50x slower)
@@ -39,13 +40,16 @@ GROUPS = [
     ("ltimes", ["Apps_LTIMES"], 128000000, 10, [], []),
     ("comm", ["Comm_HALO_PACKING", "Comm_HALO_PACKING_FUSED"], 1 << 24, 50, [], []),
     ("gemm", ["Polybench_GEMM"], 1000000, 10, [], []),
+    # the MPI-only kernels: the reference binary built against the MPI stand-in (oracle/build_ref_cuda_mpi.sh), ONE rank --
+    # every message is a self-send through its pinned host buffers; Base_B200 runs the same 1 x 1 x 1 rank grid
+    ("exchange", ["Comm_HALO_EXCHANGE", "Comm_HALO_EXCHANGE_FUSED", "Comm_HALO_SENDRECV"], 1 << 24, 50, [], []),
 ]
 # --fast: sizes still > the 126 MB L2 per dominant array, reference = Base_CUDA only (RAJA_CUDA where no Base_CUDA exists),
 # no OpenMP leg, Base_B200 through --graph only (plus the plain rep loop for the launch-bound Comm kernels)
 FAST = {"stream": 1 << 25, "algo": 1 << 25, "sort": 1 << 24, "mass": 31250000, "pa": 16000000, "ltimes": 64000000,
-        "gemm": 1000000, "comm": 1 << 24}
+        "gemm": 1000000, "comm": 1 << 24, "exchange": 1 << 24}
 QUICK = {"stream": 1 << 24, "algo": 1 << 24, "sort": 1 << 22, "mass": 12500000, "pa": 6400000, "ltimes": 25600000,
-         "gemm": 1000000, "comm": 1 << 21}
+         "gemm": 1000000, "comm": 1 << 21, "exchange": 1 << 21}
 
 
 def run(cmd, log, timeout, env=None):
@@ -148,15 +152,19 @@ def main():
         ref_variants = ["Base_CUDA", "RAJA_CUDA"] if (not a.fast or tag == "sort") else ["Base_CUDA"]
         common = ["-k"] + kernels + ["--size", str(size), "--checkrun", str(reps)] + both
         rdir, odir, gdir = (os.path.join(a.out, f"{tag}_{w}") for w in ("ref", "b200", "b200_graph"))
-        rc_r, t_r = run([REF] + common + ["-v"] + ref_variants + ref_only + ["--outdir", rdir], rdir + ".log", a.timeout)
-        if a.fast and tag != "comm":
+        ref_exe = REF_MPI if tag == "exchange" else REF
+        if not os.path.exists(ref_exe):
+            wall[tag] = {"skipped": f"{os.path.basename(ref_exe)} is not built"}
+            continue
+        rc_r, t_r = run([ref_exe] + common + ["-v"] + ref_variants + ref_only + ["--outdir", rdir], rdir + ".log", a.timeout)
+        if a.fast and tag not in ("comm", "exchange"):
             rc_o, t_o = None, 0.0
         else:
             rc_o, t_o = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--outdir", odir], odir + ".log", a.timeout)
         rc_g, t_g = run([OURS] + common + ["-v", "Base_B200", "-t", "default", "--graph", "--outdir", gdir], gdir + ".log", a.timeout)
         wall[tag] = {"reference_s": round(t_r, 1), "b200_s": round(t_o, 1), "b200_graph_s": round(t_g, 1), "rc": [rc_r, rc_o, rc_g]}
         cdir = os.path.join(a.out, f"{tag}_omp")
-        if not a.no_cpu and time.time() - t_begin < a.budget:
+        if not a.no_cpu and tag != "exchange" and time.time() - t_begin < a.budget:
             rc_c, t_c = run([cpu_exe, "-k"] + kernels + ["--size", str(size), "--checkrun", str(CPU_REPS)] + both +
                             ["-v", "Base_OpenMP", "RAJA_OpenMP", "--outdir", cdir], cdir + ".log", a.timeout, env=omp_env)
             wall[tag].update(openmp_s=round(t_c, 1), openmp_rc=rc_c)
