@@ -17,9 +17,11 @@ The ONE JSON line printed by rank 0 carries:
              the five kernels, D2H of the four output arrays + the DOT scalar, pipelined in chunks
   roofline   the dominant kernel of the step (largest share of device time) against the measured
              HBM copy bandwidth of MEASURED_PEAKS.json
-  cpu_baseline  the CPU restatement of the reference's Base_OpenMP Stream kernels (oracle/, test
-             infrastructure) timed on this box's host cores on the same workload
-  kernels    every kernel of the hot path at its BASELINE size: ms, GB/s, fraction of measured peak
+  cpu_baseline  the reference binary's own Base_OpenMP Stream kernels (oracle/_ref, built from /root/reference; the
+             OpenMP restatement in oracle/ when the binary is absent) timed on this box's host cores on the same workload
+  kernels    every kernel of the hot path at its BASELINE size: ms, GB/s, fraction of measured peak; at N = 1 each entry
+             also carries `cpu_openmp`: the reference binary's fastest Base_OpenMP / RAJA_OpenMP variant of that kernel on
+             this box's host threads, on a bounded sample (size, reps and thread count stated)
   halo_exchange  HALO_EXCHANGE_FUSED time per rep on the N-rank 3-D grid (512^3 cells per GPU)
 
 --impl reference times the CPU side alone (the reference arm of the comparison).
@@ -232,6 +234,75 @@ def cpu_stream_group_reference(n, steps, npasses=2):
     return gbs, dt / steps * 1e3, threads, "reference", sample
 
 
+# (kernels, --size, reps): bounded samples of every hot-path kernel for the reference's OpenMP variants -- sizes well past the
+# host's last-level cache, a few seconds of CPU work each (the CPU is ~50x slower than the B200, so the BASELINE sizes would
+# take minutes); SORT / SORTPAIRS exist as RAJA_OpenMP only (SORT.cpp:40-47)
+CPU_KERNEL_SAMPLES = [
+    (["Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Basic_INDEXLIST", "Algorithm_MEMCPY", "Algorithm_MEMSET"], 1 << 26, 3),
+    (["Algorithm_SORT", "Algorithm_SORTPAIRS"], 1 << 22, 2),
+    (["Apps_MASS3DPA"], 12500000, 3),
+    (["Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA"], 6400000, 3),
+    (["Apps_LTIMES"], 12800000, 3),
+    (["Comm_HALO_PACKING_FUSED"], 1 << 21, 10),
+    (["Polybench_GEMM"], 1000000, 2),
+]
+
+
+def _read_suite_csv(path):
+    """RAJAPerf-timing-Average.csv (title / variants / tunings / rows) -> {kernel: {"Variant-tuning": seconds}}."""
+    rows = [[c.strip() for c in l.rstrip("\n").split(",")] for l in open(path) if l.strip()]
+    names = [f"{v}-{t}" for v, t in zip(rows[1][1:], rows[2][1:])]
+    out = {}
+    for r in rows[3:]:
+        out[r[0]] = {}
+        for nm, cell in zip(names, r[1:]):
+            try:
+                out[r[0]][nm] = float(cell)
+            except ValueError:
+                pass
+    return out
+
+
+def cpu_kernels_reference(budget_s=75.0):
+    """The reference binary's Base_OpenMP / RAJA_OpenMP variants of every other hot-path kernel on this box's host cores
+    (north_star: the CPU figure sits next to the GPU one, core count stated).  Returns {kernel: {...}}; kernels whose run
+    fails or does not fit the time budget are simply absent."""
+    import shutil
+    import tempfile
+    out = {}
+    if not os.path.exists(REF_EXE):
+        return out
+    threads = os.cpu_count() or 1
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="cores")
+    t_begin = time.perf_counter()
+    for kernels, size, reps in CPU_KERNEL_SAMPLES:
+        if time.perf_counter() - t_begin > budget_s:
+            break
+        d = tempfile.mkdtemp(prefix="rpb_cpu_")
+        try:
+            subprocess.run([REF_EXE, "--checkrun", str(reps), "--disable-warmup", "-k"] + kernels +
+                           ["-v", "Base_OpenMP", "RAJA_OpenMP", "--size", str(size), "--outdir", d],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, timeout=60)
+            secs = _read_suite_csv(os.path.join(d, "RAJAPerf-timing-Average.csv"))
+            meta = {}
+            for line in open(os.path.join(d, "RAJAPerf-kernels.csv")):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 7 and f[0] in kernels:
+                    meta[f[0]] = (int(float(f[1])), int(float(f[2])), float(f[5]))       # problem size, reps, Bytes/rep
+            for k in kernels:
+                per = {nm: v for nm, v in secs.get(k, {}).items() if v > 0}
+                if k in meta and per:
+                    best = min(per, key=per.get)
+                    n_act, r, b = meta[k]
+                    ms = per[best] / r * 1e3
+                    out[k] = {"variant": best, "ms": ms, "gbs": b / ms / 1e6, "threads": threads, "size": n_act, "reps": r}
+        except Exception:
+            pass
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -363,6 +434,11 @@ def run_b200(args, rank, world, local_rank):
         ref = cpu_stream_group_reference(n_cpu, 3, npasses=1)
         gbs, ms, threads, kind, sample = ref if ref else cpu_stream_group(n_cpu, 3, 1)
         cpu = {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "ms_per_step": ms}
+        if not args.no_extras:
+            # the other kernels: the reference's OpenMP variants on bounded samples, reported next to the B200 numbers
+            for k, v in cpu_kernels_reference().items():
+                if k in kernels:
+                    kernels[k]["cpu_openmp"] = v
 
     if rank == 0:
         line = {
