@@ -1,0 +1,77 @@
+"""bench.py pieces that need no GPU: the reference arm's JSON line (the contract the driver parses), the parser of the
+suite's timing report, and the per-kernel cpu_openmp leg -- on tiny samples, against the reference binary when it is here
+(oracle/_ref/raja-perf.exe) and the OpenMP port otherwise."""
+import importlib.util
+import io
+import json
+import os
+import sys
+import types
+from contextlib import redirect_stdout
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_suite_timing_report_parser(bench, tmp_path):
+    p = tmp_path / "RAJAPerf-timing-Average.csv"
+    p.write_text("Mean Runtime Report (sec.)  ,  , \n"
+                 "Kernel          , Base_OpenMP , RAJA_OpenMP\n"
+                 "Kernel          , default  , default    \n"
+                 "Stream_TRIAD    , 0.000358 ,    0.038571\n"
+                 "Algorithm_SORT  , Not run ,    0.055839\n")
+    got = bench._read_suite_csv(str(p))
+    assert got == {"Stream_TRIAD": {"Base_OpenMP-default": 0.000358, "RAJA_OpenMP-default": 0.038571},
+                   "Algorithm_SORT": {"RAJA_OpenMP-default": 0.055839}}
+
+
+def test_reference_arm_prints_the_contract_line(bench, monkeypatch):
+    monkeypatch.setattr(bench, "STREAM_N", 1 << 20)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1)
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_reference_arm(args, rank=0)
+    line = json.loads(buf.getvalue().strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == "GB/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    # ranks other than 0 print nothing
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.run_reference_arm(args, rank=1)
+    assert buf.getvalue() == ""
+
+
+def test_cpu_openmp_leg_on_tiny_samples(bench, monkeypatch):
+    if not os.path.exists(bench.REF_EXE):
+        assert bench.cpu_kernels_reference() == {}          # no binary: the column is simply absent
+        return
+    monkeypatch.setattr(bench, "CPU_KERNEL_SAMPLES", [(["Algorithm_SCAN", "Algorithm_REDUCE_SUM"], 100000, 2),
+                                                      (["Algorithm_SORT"], 50000, 1), (["Apps_LTIMES"], 20480, 1)])
+    got = bench.cpu_kernels_reference()
+    assert set(got) == {"Algorithm_SCAN", "Algorithm_REDUCE_SUM", "Algorithm_SORT", "Apps_LTIMES"}
+    for k, v in got.items():
+        assert v["ms"] > 0 and v["gbs"] > 0 and v["threads"] >= 1 and v["variant"].split("-")[0] in ("Base_OpenMP", "RAJA_OpenMP")
+    assert got["Algorithm_SORT"]["variant"].startswith("RAJA_OpenMP")      # SORT has no Base_OpenMP (SORT.cpp:40-47)
+    assert got["Algorithm_SCAN"]["size"] == 100000 and got["Algorithm_SCAN"]["reps"] == 2
+    json.dumps(got)                                                         # goes into the bench line as is
+
+
+def test_measured_peak_falls_back_to_the_profiling_guide_number(bench, monkeypatch, tmp_path):
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    peak, src = bench.measured_peak()
+    assert peak == 6650.0 and "fallback" in src
+    (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6554.9}))
+    peak, src = bench.measured_peak()
+    assert peak == 6554.9 and "measured" in src
