@@ -11,7 +11,7 @@ REDUCE_SUM::REDUCE_SUM(const RunParams& params) : KernelBase(rajaperf::Algorithm
   setActualProblemSize(getTargetProblemSize());
   setItsPerRep(getActualProblemSize());
   setKernelsPerRep(1);
-  setBytesReadPerRep(1 * sizeof(Real_type) * getActualProblemSize());
+  setBytesReadPerRep(1 * sizeof(Real_type) * (1 + getActualProblemSize()));                      // REDUCE_SUM.cpp:31-32
   setBytesWrittenPerRep(1 * sizeof(Real_type));
   setFLOPsPerRep(getActualProblemSize());
   setVariantDefined(Base_B200);

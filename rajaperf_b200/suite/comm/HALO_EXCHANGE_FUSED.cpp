@@ -12,7 +12,7 @@ namespace comm {
 HALO_EXCHANGE_FUSED::HALO_EXCHANGE_FUSED(KernelID kid, const RunParams& params) : HALO_base(kid, params)
 {
   setDefaultReps(200);
-  setItsPerRep(m_num_vars * m_halo_elems * 2);
+  setItsPerRep(m_num_vars * m_halo_elems);                  // HALO_EXCHANGE_FUSED.cpp:32
   setKernelsPerRep(2);
   // HALO_EXCHANGE_FUSED.cpp:34-45: pack + unpack as in HALO_PACKING_FUSED plus the message itself
   // (one Real_type read by the sender and written at the receiver)

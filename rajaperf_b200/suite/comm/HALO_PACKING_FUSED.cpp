@@ -9,7 +9,7 @@ namespace comm {
 HALO_PACKING_FUSED::HALO_PACKING_FUSED(KernelID kid, const RunParams& params) : HALO_base(kid, params)
 {
   setDefaultReps(200);
-  setItsPerRep(m_num_vars * m_halo_elems * 2);
+  setItsPerRep(m_num_vars * m_halo_elems);                  // HALO_PACKING_FUSED.cpp:26: num_vars x (var_size - owned cells)
   setKernelsPerRep(2);
   // HALO_PACKING_FUSED.cpp:28-35: per packed element an Int_type index + a Real_type read + a Real_type
   // write, once for pack and once for unpack

@@ -11,8 +11,8 @@ DOT::DOT(const RunParams& params) : KernelBase(rajaperf::Stream_DOT, params)
   setActualProblemSize(getTargetProblemSize());
   setItsPerRep(getActualProblemSize());
   setKernelsPerRep(1);
-  setBytesReadPerRep(2 * sizeof(Real_type) * getActualProblemSize());
-  setBytesWrittenPerRep(0 * sizeof(Real_type) * getActualProblemSize());
+  setBytesReadPerRep(1 * sizeof(Real_type) + 2 * sizeof(Real_type) * getActualProblemSize());   // DOT.cpp:31-33: + the running dot
+  setBytesWrittenPerRep(1 * sizeof(Real_type));
   setFLOPsPerRep(2 * getActualProblemSize());
 
   setVariantDefined(Base_B200);

@@ -82,6 +82,30 @@ def mpirun(nranks, cmd, timeout=600):
         raise RuntimeError(f"{nranks}-rank run failed: {rcs}: {' '.join(cmd)}")
 
 
+# --dryrun tables: what the reference prints for (problem size, reps, iterations/rep, kernels/rep, bytes/rep, flops/rep) of
+# every hot-path kernel under these flag sets -- the kernel-class metadata the harness must reproduce (KernelBase.hpp:100-116)
+DRYRUN_KERNELS = ["Stream", "Algorithm_REDUCE_SUM", "Algorithm_SCAN", "Algorithm_SORT", "Algorithm_SORTPAIRS", "Algorithm_MEMCPY",
+                  "Algorithm_MEMSET", "Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA", "Apps_LTIMES", "Comm",
+                  "Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP", "Polybench_GEMM"]
+DRYRUN_FLAGS = [[], ["--size", "1234567"], ["--sizefact", "2.5", "--repfact", "0.3"],
+                ["--size", "27000", "--halo_width", "2", "--halo_num_vars", "5"], ["--repfact", "2", "--size", "50000"],
+                ["--size", "268435456"], ["--size", "100000", "--ltimes_num_d", "32", "--ltimes_num_g", "8", "--ltimes_num_m", "17"]]
+
+
+def dryrun_tables(exe):
+    out = []
+    for flags in DRYRUN_FLAGS:
+        txt = subprocess.run([exe, "--dryrun", "-k"] + DRYRUN_KERNELS + ["-v", "Base_Seq", "RAJA_Seq"] + flags,
+                             capture_output=True, text=True, check=True).stdout
+        rows = {}
+        for line in txt.splitlines():
+            if re.match(r"^(Stream|Algorithm|Apps|Comm|Basic|Polybench)_", line):
+                f = [x.strip() for x in line.split(",")]
+                rows[f[0]] = f[1:7]
+        out.append({"flags": flags, "rows": rows})
+    return out
+
+
 def run_case(exe, kernel, size, reps, extra, workdir, ranks=1):
     out = os.path.join(workdir, "out")
     shutil.rmtree(out, ignore_errors=True)
@@ -104,7 +128,16 @@ def main():
     ap.add_argument("--exe", default=os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe"))
     ap.add_argument("--out", default=None)
     ap.add_argument("--mpi", action="store_true", help="the MPI-only Comm kernels from the one-rank MPI-stub build")
+    ap.add_argument("--dryrun", action="store_true", help="the --dryrun tables of the MPI-stub build (all 23 kernels) -> ref_dryrun.json")
     a = ap.parse_args()
+    if a.dryrun:
+        exe = os.path.join(ROOT, "oracle", "_ref", "raja-perf-mpi1.exe")
+        out = a.out or os.path.join(ROOT, "tests", "golden", "ref_dryrun.json")
+        json.dump({"source": "reference raja-perf.exe --dryrun (suite v2024.07.0, CPU-only build against oracle/mpi_stub, one rank)",
+                   "columns": ["Problem size", "Reps", "Iterations/rep", "Kernels/rep", "Bytes/rep", "FLOPS/rep"],
+                   "tables": dryrun_tables(exe)}, open(out, "w"), indent=1)
+        print(f"wrote {out}", file=sys.stderr)
+        return
     cases = CASES
     if a.mpi:
         cases = MPI_CASES
