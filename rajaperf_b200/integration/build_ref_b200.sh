@@ -1,0 +1,24 @@
+#!/bin/bash
+# Authoring-container only: the reference suite WITH the Base_B200 variant integrated (apply_base_b200.py: a patched COPY of
+# /root/reference under /tmp, nothing is stored in this repo), built with the reference's own CMake for sm_100 and linked
+# against rajaperf_b200/lib/librpb200.so -> oracle/_ref/raja-perf-with-b200.exe.  On a B200:
+#   oracle/_ref/raja-perf-with-b200.exe -k Stream Algorithm_SCAN Apps_MASS3DPA -v Base_Seq Base_CUDA Base_B200 --checkrun 5
+# prints the reference's OWN checksum report (Base_B200 against Base_Seq, test/test-raja-perf-suite.cpp:124-167) and its own
+# timing report with the three variants side by side.  ~25 min on 8 cores.
+set -e
+HERE=$(cd "$(dirname "$0")" && pwd)
+ROOT=$(cd "$HERE/../.." && pwd)
+SRC=${SRC:-/tmp/ref_b200}
+BUILD=${BUILD:-/tmp/ref_b200_build}
+[ -d "$SRC/src" ] || python "$HERE/apply_base_b200.py" --dst "$SRC"
+mkdir -p "$BUILD" "$ROOT/oracle/_ref"
+cd "$BUILD"
+CC=/usr/bin/gcc CXX=/usr/bin/g++ cmake -G Ninja -DCMAKE_BUILD_TYPE=Release -DENABLE_OPENMP=On -DENABLE_CUDA=On \
+  -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DCMAKE_CUDA_HOST_COMPILER=/usr/bin/g++ \
+  "-DCMAKE_CUDA_ARCHITECTURES=90-virtual;100-real" -DENABLE_TESTS=Off \
+  "-DCMAKE_CXX_FLAGS=-I$ROOT/include" "-DCMAKE_CUDA_FLAGS=-I$ROOT/include" \
+  "-DCMAKE_CXX_STANDARD_LIBRARIES=-L$ROOT/rajaperf_b200/lib -lrpb200 -Wl,-rpath,\$ORIGIN/../../rajaperf_b200/lib" \
+  "$SRC" > cmake.log 2>&1
+ninja raja-perf.exe > ninja.log 2>&1
+cp bin/raja-perf.exe "$ROOT/oracle/_ref/raja-perf-with-b200.exe"
+echo "built $ROOT/oracle/_ref/raja-perf-with-b200.exe"

@@ -1,0 +1,73 @@
+//
+// HALO_PACKING_FUSED-B200.cpp -- the Base_B200 variant of Comm_HALO_PACKING_FUSED: the analogue of HALO_PACKING_FUSED-Cuda.cpp, added to the reference tree by
+// rajaperf_b200/integration/apply_base_b200.py.  The kernel is one call into librpb200.so (include/rpb200.h) per rep,
+// enqueued on the suite's CUDA stream between startTimer() and stopTimer(); data are the arrays setUp() allocated.
+//
+#include "HALO_PACKING_FUSED.hpp"
+
+#include "RAJA/RAJA.hpp"
+
+#if defined(RAJA_ENABLE_CUDA)
+
+#include "common/B200Utils.hpp"
+
+#include <iostream>
+#include <vector>
+
+namespace rajaperf
+{
+namespace comm
+{
+
+void HALO_PACKING_FUSED::runB200Variant(VariantID vid, size_t RAJAPERF_UNUSED_ARG(tune_idx))
+{
+  const Index_type run_reps = getRunReps();
+  auto res{getCudaResource()};
+  rpb200_stream_t stream = res.get_stream();
+  rpb200_ctx* ctx = getB200Context();
+
+  if ( vid != Base_B200 ) {
+    getCout() << "\n  HALO_PACKING_FUSED : Unknown B200 variant id = " << vid << std::endl;
+    return;
+  }
+
+  // the (buffer, list, var, len) tuples of HALO_PACKING_FUSED-Seq.cpp:43-61, 71-97 -- neighbour-major, variable-minor -- go to
+  // device memory ONCE (the reference rewrites them into pinned host memory every rep, HALO_PACKING_FUSED-Cuda.cpp:112-128)
+  const int num_neighbors = static_cast<int>(m_pack_index_lists.size());
+  std::vector<rpb200_halo_seg> pack_segs, unpack_segs;
+  for (int l = 0; l < num_neighbors; ++l) {
+    for (Index_type v = 0; v < m_num_vars; ++v) {
+      rpb200_halo_seg seg;
+      seg.var = m_vars[v]; seg.msg = l; seg.flags = 0;
+      seg.len = m_pack_index_list_lengths[l];
+      seg.list = m_pack_index_lists[l];
+      seg.buffer = m_pack_buffers[l] + v * seg.len;
+      pack_segs.push_back(seg);
+      seg.len = m_unpack_index_list_lengths[l];
+      seg.list = m_unpack_index_lists[l];
+      seg.buffer = m_unpack_buffers[l] + v * seg.len;
+      unpack_segs.push_back(seg);
+    }
+  }
+  rpb200_halo_worklist* pack_wl = nullptr;
+  rpb200_halo_worklist* unpack_wl = nullptr;
+  checkB200( rpb200_halo_worklist_create(ctx, pack_segs.data(), static_cast<int>(pack_segs.size()), &pack_wl),
+             "rpb200_halo_worklist_create" );
+  checkB200( rpb200_halo_worklist_create(ctx, unpack_segs.data(), static_cast<int>(unpack_segs.size()), &unpack_wl),
+             "rpb200_halo_worklist_create" );
+
+  startTimer();
+  for (RepIndex_type irep = 0; irep < run_reps; ++irep) {                 // 2 launches, no host synchronisation in between
+    checkB200( rpb200_halo_pack(ctx, pack_wl, stream), "rpb200_halo_pack" );
+    checkB200( rpb200_halo_unpack(ctx, unpack_wl, stream), "rpb200_halo_unpack" );
+  }
+  stopTimer();
+
+  rpb200_halo_worklist_destroy(pack_wl);
+  rpb200_halo_worklist_destroy(unpack_wl);
+}
+
+} // end namespace comm
+} // end namespace rajaperf
+
+#endif  // RAJA_ENABLE_CUDA
