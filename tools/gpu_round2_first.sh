@@ -15,4 +15,13 @@ timeout 200 ncu --set full --clock-control none --import-source on -k regex:"mas
 ncu -i gpurun_out/${TAG}_prof.ncu-rep --page raw --csv > gpurun_out/${TAG}_prof_raw.csv 2>/dev/null
 timeout 90 python tools/incumbent_suite.py --fast --groups exchange --timeout 40 --out gpurun_out/${TAG}_incumbent_exchange \
     > gpurun_out/${TAG}_incumbent_exchange.log 2>&1; echo "incumbent exchange rc=$?"; tail -6 gpurun_out/${TAG}_incumbent_exchange.log
+# 5. the reference's OWN driver with the Base_B200 variant integrated (rajaperf_b200/integration/): its checksum report
+#    compares Base_B200 with Base_Seq / Base_CUDA itself, at the suite's default sizes
+if [ -x oracle/_ref/raja-perf-with-b200.exe ]; then
+  timeout 120 oracle/_ref/raja-perf-with-b200.exe -k Stream Algorithm_REDUCE_SUM Algorithm_SCAN Algorithm_SORT Algorithm_SORTPAIRS \
+      Apps_MASS3DPA Apps_DIFFUSION3DPA Apps_CONVECTION3DPA Apps_LTIMES Comm_HALO_PACKING_FUSED \
+      -v Base_Seq Base_CUDA RAJA_CUDA Base_B200 --checkrun 5 --outdir gpurun_out/${TAG}_ref_with_b200 \
+      > gpurun_out/${TAG}_ref_with_b200.log 2>&1; echo "reference driver with Base_B200 rc=$?"
+  grep -E "^(Stream|Algorithm|Apps|Comm)_|Base_B200|Base_Seq" gpurun_out/${TAG}_ref_with_b200/RAJAPerf-checksum.txt | head -60
+fi
 TAG=$TAG bash tools/gpu_final.sh
