@@ -8,7 +8,8 @@
  * -- P processes of the binary over a shared-memory arena (RPB_MPI_SIZE / RPB_MPI_RANK / RPB_MPI_SHM, see mpi_stub.c;
  * the launcher is mpirun() in tests/golden/make_golden.py).  make_golden.py --mpi mints the exchange goldens from it.
  *
- * Only what the suite calls (grep MPI_ src/): Init/Finalize, Comm_rank/size, Barrier, Allreduce, Gather, Bcast,
+ * Only what the suite calls (grep MPI_ src/): Init/Finalize, Comm_rank/size, Barrier, Allreduce, Gather, Bcast (and
+ * Allgather, for the IPC-handle rendezvous of the Base_B200 exchange stub),
  * Isend/Irecv, Wait/Waitall/Waitany.  A message is matched to a receive by (source, tag), oldest first, as MPI does;
  * sends are buffered, so any call order the standard allows works.
  */
@@ -60,6 +61,7 @@ double MPI_Wtime(void);
 int MPI_Allreduce(const void* send, void* recv, int count, MPI_Datatype type, MPI_Op op, MPI_Comm comm);
 int MPI_Gather(const void* send, int scount, MPI_Datatype stype, void* recv, int rcount, MPI_Datatype rtype,
                int root, MPI_Comm comm);
+int MPI_Allgather(const void* send, int scount, MPI_Datatype stype, void* recv, int rcount, MPI_Datatype rtype, MPI_Comm comm);
 int MPI_Bcast(void* buf, int count, MPI_Datatype type, int root, MPI_Comm comm);
 int MPI_Isend(const void* buf, int count, MPI_Datatype type, int dest, int tag, MPI_Comm comm, MPI_Request* req);
 int MPI_Irecv(void* buf, int count, MPI_Datatype type, int source, int tag, MPI_Comm comm, MPI_Request* req);

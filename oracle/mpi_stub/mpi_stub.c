@@ -226,6 +226,19 @@ int MPI_Gather(const void* send, int scount, MPI_Datatype stype, void* recv, int
   return MPI_SUCCESS;
 }
 
+int MPI_Allgather(const void* send, int scount, MPI_Datatype stype, void* recv, int rcount, MPI_Datatype rtype, MPI_Comm comm)
+{
+  (void)rcount; (void)rtype; (void)comm;
+  const size_t bytes = (size_t)scount * type_bytes(stype);
+  if (g_size == 1) { memcpy(recv, send, bytes); return MPI_SUCCESS; }
+  if (bytes > SHM_SLOT_BYTES) die("Allgather larger than the collective slot");
+  memcpy(g_shm->coll[g_rank], send, bytes);
+  shm_barrier();
+  for (int r = 0; r < g_size; ++r) memcpy((char*)recv + (size_t)r * bytes, g_shm->coll[r], bytes);
+  shm_barrier();
+  return MPI_SUCCESS;
+}
+
 int MPI_Bcast(void* buf, int count, MPI_Datatype type, int root, MPI_Comm comm)
 {
   (void)comm;

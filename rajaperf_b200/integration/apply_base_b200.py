@@ -7,7 +7,7 @@
 Nothing is written under --src and no reference source is stored in this repo: the script copies the tree to --dst, makes
 the six `src/common` edits of INTEGRATION.md section 1 there by anchored text insertion (every anchor must match exactly
 once, or exactly the stated number of times -- otherwise the script stops: the reference changed), adds
-`setVariantDefined( Base_B200 )` + the `runB200Variant` declaration to the 14 kernel classes, drops in the stubs of
+`setVariantDefined( Base_B200 )` + the `runB200Variant` declaration to the 15 kernel classes, drops in the stubs of
 rajaperf_b200/integration/src/ (this repo's own files) and lists them in the group CMakeLists.  The result is the reference's
 own driver, reports and checksum comparison with one more variant: `raja-perf.exe -k Stream -v Base_Seq Base_CUDA Base_B200`.
 """
@@ -23,7 +23,7 @@ KERNELS = {
     "stream": ["ADD", "COPY", "DOT", "MUL", "TRIAD"],
     "algorithm": ["REDUCE_SUM", "SCAN", "SORT", "SORTPAIRS"],
     "apps": ["MASS3DPA", "DIFFUSION3DPA", "CONVECTION3DPA", "LTIMES"],
-    "comm": ["HALO_PACKING_FUSED"],
+    "comm": ["HALO_PACKING_FUSED", "HALO_EXCHANGE_FUSED"],      # the exchange compiles only in an MPI build (it is #if'ed out otherwise)
 }
 
 

@@ -12,13 +12,24 @@ SRC=${SRC:-/tmp/ref_b200}
 BUILD=${BUILD:-/tmp/ref_b200_build}
 [ -d "$SRC/src" ] || python "$HERE/apply_base_b200.py" --dst "$SRC"
 mkdir -p "$BUILD" "$ROOT/oracle/_ref"
+# MPI=1: also the MPI code paths (Comm_HALO_EXCHANGE_FUSED with its Base_B200 stub) against the MPI stand-in of
+# oracle/mpi_stub -> raja-perf-with-b200-mpi.exe; P ranks = P processes launched like tests/golden/make_golden.py:mpirun,
+# one GPU each (CUDA_VISIBLE_DEVICES per rank)
+MPI_FLAGS=()
+OUT=raja-perf-with-b200.exe
+if [ "${MPI:-0}" = "1" ]; then
+  /usr/bin/gcc -O2 -fPIC -std=gnu11 -pthread -c "$ROOT/oracle/mpi_stub/mpi_stub.c" -o "$BUILD/mpi_stub.o"
+  ar rcs "$BUILD/libmpistub.a" "$BUILD/mpi_stub.o"
+  MPI_FLAGS=(-DENABLE_MPI=On -DENABLE_FIND_MPI=Off "-DBLT_MPI_INCLUDES=$ROOT/oracle/mpi_stub" "-DBLT_MPI_LIBRARIES=$BUILD/libmpistub.a")
+  OUT=raja-perf-with-b200-mpi.exe
+fi
 cd "$BUILD"
 CC=/usr/bin/gcc CXX=/usr/bin/g++ cmake -G Ninja -DCMAKE_BUILD_TYPE=Release -DENABLE_OPENMP=On -DENABLE_CUDA=On \
   -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DCMAKE_CUDA_HOST_COMPILER=/usr/bin/g++ \
   "-DCMAKE_CUDA_ARCHITECTURES=90-virtual;100-real" -DENABLE_TESTS=Off \
   "-DCMAKE_CXX_FLAGS=-I$ROOT/include" "-DCMAKE_CUDA_FLAGS=-I$ROOT/include" \
   "-DCMAKE_CXX_STANDARD_LIBRARIES=-L$ROOT/rajaperf_b200/lib -lrpb200 -Wl,-rpath,\$ORIGIN/../../rajaperf_b200/lib" \
-  "$SRC" > cmake.log 2>&1
+  "${MPI_FLAGS[@]}" "$SRC" > cmake.log 2>&1
 ninja raja-perf.exe > ninja.log 2>&1
-cp bin/raja-perf.exe "$ROOT/oracle/_ref/raja-perf-with-b200.exe"
-echo "built $ROOT/oracle/_ref/raja-perf-with-b200.exe"
+cp bin/raja-perf.exe "$ROOT/oracle/_ref/$OUT"
+echo "built $ROOT/oracle/_ref/$OUT"

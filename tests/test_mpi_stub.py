@@ -130,6 +130,9 @@ g = np.zeros(8 * s, dtype=np.uint8); mine = np.array([float(r)])
 L.MPI_Gather(p(mine), 8, 1, p(g), 8, 1, 0, 0)
 if r == 0:
     ok = ok and g.view(np.float64).tolist() == [float(q) for q in range(s)]
+ag = np.zeros(s, dtype=np.float64)
+L.MPI_Allgather(p(mine), 8, 1, p(ag), 8, 1, 0)
+ok = ok and ag.tolist() == [float(q) for q in range(s)]
 v = np.array([42.0 if r == 0 else -1.0])
 L.MPI_Bcast(p(v), 1, 8, 0, 0)
 ok = ok and v[0] == 42.0
