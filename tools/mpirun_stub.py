@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Launch P ranks of a binary linked against the MPI stand-in (oracle/mpi_stub): the `mpirun` of this repo's reference builds.
+
+    python tools/mpirun_stub.py -n 8 [--gpu-per-rank] -- oracle/_ref/raja-perf-with-b200-mpi.exe \
+        -k Comm_HALO_EXCHANGE_FUSED -v Base_Seq Base_CUDA Base_B200 --checkrun 5 --size 2097152
+
+One zero-filled arena under /dev/shm carries the messages (RPB_MPI_SHM), RPB_MPI_SIZE / RPB_MPI_RANK tell a process who it
+is; with --gpu-per-rank rank r sees only GPU r mod <number of GPUs> (CUDA_VISIBLE_DEVICES), the binding a real launcher
+would do.  Rank 0's output is shown, the others' is dropped unless --all-output.  Exit code: the first non-zero one.
+"""
+import argparse
+import os
+import subprocess
+import sys
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-n", type=int, required=True)
+    ap.add_argument("--gpu-per-rank", action="store_true")
+    ap.add_argument("--all-output", action="store_true")
+    ap.add_argument("--arena-mb", type=int, default=1024)
+    ap.add_argument("--timeout", type=int, default=900)
+    ap.add_argument("cmd", nargs=argparse.REMAINDER)
+    a = ap.parse_args()
+    cmd = a.cmd[1:] if a.cmd and a.cmd[0] == "--" else a.cmd
+    if not cmd:
+        ap.error("no command")
+    ngpu = 0
+    if a.gpu_per_rank:
+        try:
+            ngpu = len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.strip().splitlines())
+        except OSError:
+            ngpu = 0
+        if ngpu == 0:
+            sys.exit("--gpu-per-rank: no GPU visible")
+    path = f"/dev/shm/rpb_mpi_{os.getpid()}"
+    with open(path, "wb") as f:
+        f.truncate(a.arena_mb << 20)
+    try:
+        procs = []
+        for r in range(a.n):
+            env = dict(os.environ, RPB_MPI_SIZE=str(a.n), RPB_MPI_RANK=str(r), RPB_MPI_SHM=path)
+            env.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // a.n)))
+            if ngpu:
+                env["CUDA_VISIBLE_DEVICES"] = str(r % ngpu)
+            quiet = r != 0 and not a.all_output
+            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL if quiet else None,
+                                          stderr=subprocess.DEVNULL if quiet else None))
+        rcs = [p.wait(timeout=a.timeout) for p in procs]
+    finally:
+        os.unlink(path)
+    bad = [rc for rc in rcs if rc]
+    sys.exit(bad[0] if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
