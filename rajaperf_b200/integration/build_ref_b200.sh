@@ -4,7 +4,8 @@
 # against rajaperf_b200/lib/librpb200.so -> oracle/_ref/raja-perf-with-b200.exe.  On a B200:
 #   oracle/_ref/raja-perf-with-b200.exe -k Stream Algorithm_SCAN Apps_MASS3DPA -v Base_Seq Base_CUDA Base_B200 --checkrun 5
 # prints the reference's OWN checksum report (Base_B200 against Base_Seq, test/test-raja-perf-suite.cpp:124-167) and its own
-# timing report with the three variants side by side.  ~25 min on 8 cores.
+# timing report with the three variants side by side.  ~25 min on 8 cores.  The run path of librpb200.so is absolute
+# ($ROOT/rajaperf_b200/lib: /root/repo/... exists on the GPU box too, as a symlink to the snapshot).
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
 ROOT=$(cd "$HERE/../.." && pwd)
@@ -28,7 +29,7 @@ CC=/usr/bin/gcc CXX=/usr/bin/g++ cmake -G Ninja -DCMAKE_BUILD_TYPE=Release -DENA
   -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DCMAKE_CUDA_HOST_COMPILER=/usr/bin/g++ \
   "-DCMAKE_CUDA_ARCHITECTURES=90-virtual;100-real" -DENABLE_TESTS=Off \
   "-DCMAKE_CXX_FLAGS=-I$ROOT/include" "-DCMAKE_CUDA_FLAGS=-I$ROOT/include" \
-  "-DCMAKE_CXX_STANDARD_LIBRARIES=-L$ROOT/rajaperf_b200/lib -lrpb200 -Wl,-rpath,\$ORIGIN/../../rajaperf_b200/lib" \
+  "-DCMAKE_CXX_STANDARD_LIBRARIES=-L$ROOT/rajaperf_b200/lib -lrpb200 -Wl,-rpath,$ROOT/rajaperf_b200/lib" \
   "${MPI_FLAGS[@]}" "$SRC" > cmake.log 2>&1
 ninja raja-perf.exe > ninja.log 2>&1
 cp bin/raja-perf.exe "$ROOT/oracle/_ref/$OUT"
