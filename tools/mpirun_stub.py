@@ -5,8 +5,8 @@
         -k Comm_HALO_EXCHANGE_FUSED -v Base_Seq Base_CUDA Base_B200 --checkrun 5 --size 2097152
 
 One zero-filled arena under /dev/shm carries the messages (RPB_MPI_SHM), RPB_MPI_SIZE / RPB_MPI_RANK tell a process who it
-is; with --gpu-per-rank rank r sees only GPU r mod <number of GPUs> (CUDA_VISIBLE_DEVICES), the binding a real launcher
-would do.  Rank 0's output is shown, the others' is dropped unless --all-output.  Exit code: the first non-zero one.
+is; with --gpu-per-rank device 0 of rank r is GPU r mod <number of GPUs> (CUDA_VISIBLE_DEVICES is the GPU list rotated by r,
+so the peers stay visible for CUDA IPC), the binding a real launcher would do.  Rank 0's output is shown, the others' is dropped unless --all-output.  Exit code: the first non-zero one.
 """
 import argparse
 import os
@@ -42,8 +42,8 @@ def main():
         for r in range(a.n):
             env = dict(os.environ, RPB_MPI_SIZE=str(a.n), RPB_MPI_RANK=str(r), RPB_MPI_SHM=path)
             env.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // a.n)))
-            if ngpu:
-                env["CUDA_VISIBLE_DEVICES"] = str(r % ngpu)
+            if ngpu:      # rotated list: device 0 is this rank's GPU, the others stay visible (CUDA IPC needs the peer's device)
+                env["CUDA_VISIBLE_DEVICES"] = ",".join(str((r + i) % ngpu) for i in range(ngpu))
             quiet = r != 0 and not a.all_output
             procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL if quiet else None,
                                           stderr=subprocess.DEVNULL if quiet else None))
