@@ -11,7 +11,21 @@
  *     the caller (the kernel object's setUp/tearDown, KernelBase.cpp:359-377);
  *   - `stream` is a cudaStream_t passed as an opaque pointer (NULL = legacy default
  *     stream); every call is asynchronous on that stream, nothing synchronises;
- *   - return 0 on success, otherwise a cudaError_t value (or RPB200_EINVAL);
+ *   - STREAMS: one context serves any number of streams CONCURRENTLY.  Everything a kernel writes
+ *     besides the caller's arrays (reduction partials and tickets, scan / index-list look-back
+ *     descriptors, tickets and epochs, PA basis tables) exists once per (context, stream) -- the
+ *     reference likewise gives every reducer its own scratch, GPUUtils.hpp:250-330 -- and is
+ *     attached to a stream at its first call (no allocation for the first 4 streams; see
+ *     rpb200_stream_attach).  The three Apps_*3DPA kernels keep their basis tables in
+ *     __constant__ memory, one set per DEVICE: calls on different streams are safe but
+ *     serialise (an event orders each call behind the device's previous PA call).
+ *     Caller-provided scratch (SORT) and halo plans are the caller's to keep to one stream at
+ *     a time.  Look-back epochs live in device memory, so every entry point may be captured
+ *     into a CUDA graph and the graph replayed any number of times;
+ *   - DEVICE: a context belongs to the device it was created for; the calling thread's
+ *     current device must be that device at every call (checked: RPB200_EDEVICE).
+ *     rpb200_create() leaves the caller's current device unchanged;
+ *   - return 0 on success, otherwise a cudaError_t value (or one of the RPB200_E* codes);
  *     no exceptions, no CPU fallback: without a usable sm_100 device
  *     rpb200_create() fails and nothing else may be called;
  *   - all file:line citations are relative to /root/reference/src.
@@ -28,6 +42,8 @@ extern "C" {
 
 #define RPB200_EINVAL (-22)
 #define RPB200_ETIMEDOUT (-110)
+#define RPB200_EDEVICE (-19)            /* the current CUDA device is not the context's            */
+#define RPB200_ENOSLOT (-24)            /* more than 64 streams attached to one context            */
 
 typedef struct rpb200_ctx rpb200_ctx;   /* per-device context (scratch, SM count, tunings) */
 typedef void* rpb200_stream_t;          /* cudaStream_t */
@@ -40,19 +56,25 @@ void        rpb200_destroy(rpb200_ctx* ctx);
 const char* rpb200_error_string(int err);
 int         rpb200_sm_count(const rpb200_ctx* ctx);
 const char* rpb200_version(void);
+/* Optional.  attach: give `stream` its scratch set NOW (allocating one if the 4 pre-allocated sets are taken, and sizing
+ * its look-back state to the largest rpb200_scan_reserve / rpb200_indexlist_reserve so far; synchronises) -- required only
+ * before CAPTURING calls on a stream that is the 5th or later stream of the context, since a capture may not allocate.
+ * detach: the stream is about to be destroyed; its set is kept for the next stream that attaches (at most 64 attached
+ * streams per context: RPB200_ENOSLOT).                                                                               */
+int rpb200_stream_attach(rpb200_ctx* ctx, rpb200_stream_t stream);
+int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
 
 /* Launch tuning, the analogue of the reference's block-size tunings
  * (GPUUtils.hpp:345-373).  kernel = full kernel name ("Stream_TRIAD");
  * <=0 keeps the current value of that field (ctas_per_sm: < 0).  Meaning of the fields:
  *   Stream_*, Stream_DOT, Algorithm_REDUCE_SUM, Algorithm_SCAN (small n), Basic_INDEXLIST (small n):
  *       threads per CTA, persistent CTAs per SM (0 = one tile per CTA), independent vectors per thread;
- *   Comm_HALO_PACKING_FUSED / Comm_HALO_EXCHANGE_FUSED: block_size 256 = contiguous chunk ranges per CTA,
- *       192 = the same with pack launches walking the list backwards (default), 128 = round-robin; ctas_per_sm; unroll 4 = L2 eviction-priority hints on; for the exchange
- *       unroll 1 = ONE fused launch per rep, 2 / 4 = pack launch + unpack launch (default 2);
- *   Algorithm_SCAN (large n, the TMA-staged kernel): unroll 9 = line-major result stores after a 4-lane transpose
- *       (opt-in, first measurement pending: tools/time_quick.py scan_line);
- *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 9 = digit histograms with lane-private 16-bit counters (opt-in, first
- *       measurement pending: tools/time_quick.py sort_hist);
+ *   Comm_HALO_PACKING_FUSED / Comm_HALO_EXCHANGE_FUSED, two-launch forms: block_size 256 = contiguous chunk ranges per CTA,
+ *       192 = the same with pack launches walking the list backwards (default), 128 = round-robin; ctas_per_sm; unroll 4 = L2
+ *       eviction-priority hints on.  One-launch forms (rpb200_halo_plan_pack_unpack, rpb200_halo_exchange): ctas_per_sm;
+ *       exchange unroll 1 = ONE launch per rep over the item list, 2 / 4 = pack launch + unpack launch;
+ *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 8 = digit histograms in shared bins instead of the lane-private 16-bit
+ *       counters (default since round 2: profiles/r02_a_optin.log);
  *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
  *   Apps_LTIMES: ctas_per_sm; unroll 5..8 = psi staged through a bulk-async ring, 10 = row-chunk A fragments, else line-major (default);
  *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.
@@ -86,8 +108,9 @@ int rpb200_reduce_sum(rpb200_ctx*, const double* x, int64_t n, double init, doub
 /* algorithm/SCAN-Cuda.cpp:34-188 + common/CudaGridScan.hpp: exclusive prefix sum,
  * single pass (decoupled look-back), no per-call memset.                            */
 int rpb200_scan_exclusive(rpb200_ctx*, const double* x, double* y, int64_t n, rpb200_stream_t);
-/* Optional: grow the context's look-back state for n elements now (synchronises), so that later
- * rpb200_scan_exclusive calls never allocate -- required before capturing them into a CUDA graph.  */
+/* Optional: grow the look-back state of every scratch set of the context for n elements now (synchronises), so that
+ * later rpb200_scan_exclusive calls never allocate -- required before capturing them into a CUDA graph.  The look-back
+ * epoch is read from device memory by the kernel, so a captured scan replays correctly any number of times.  */
 int rpb200_scan_reserve(rpb200_ctx*, int64_t n);
 /* algorithm/SORT-Cuda.cpp:35-43 (RAJA::sort -> cub::DeviceRadixSort::SortKeys):
  * ascending in-place sort of n doubles (IEEE total order on non-NaN values, -0 < +0).
@@ -164,6 +187,12 @@ int rpb200_halo_worklist_update(rpb200_halo_worklist*, const rpb200_halo_seg* h_
 void rpb200_halo_worklist_destroy(rpb200_halo_worklist*);
 int rpb200_halo_pack  (rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t);
 int rpb200_halo_unpack(rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t);
+/* pack(`pack`) and unpack(`unpack`) of one rep in ONE launch, for callers whose two lists touch DISJOINT memory -- true of
+ * HALO_PACKING_FUSED (HALO_PACKING_FUSED-Seq.cpp:43-61 reads owned cells into the pack buffers, :71-97 writes ghost cells
+ * from the unpack buffers), where the result then equals pack followed by unpack.  The first call for a (pack, unpack) pair
+ * builds and uploads the merged item list (synchronises: make it before capturing into a graph); see
+ * rpb200_halo_plan_pack_unpack below for what the item order buys.                                                      */
+int rpb200_halo_pack_unpack(rpb200_ctx*, rpb200_halo_worklist* pack, rpb200_halo_worklist* unpack, rpb200_stream_t);
 
 /* (2) HALO_base: the 26-neighbour periodic decomposition and its index lists
  *     (comm/HALO_base.cpp:31-35 grid dims, :82-116 offsets, :118-166 extents, :169-291
@@ -187,6 +216,13 @@ int  rpb200_halo_plan_bind(rpb200_halo_plan*, double* const* vars, double* const
                            double* const* unpack_buffers);
 int  rpb200_halo_plan_pack(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_plan_unpack(rpb200_halo_plan*, rpb200_stream_t);
+/* One rep of HALO_PACKING_FUSED in ONE launch.  The pack (HALO_PACKING_FUSED-Seq.cpp:43-61: owned cells -> pack buffers) and
+ * the unpack (:71-97: unpack buffers -> ghost cells) touch disjoint cells and disjoint buffers, so the result does not
+ * depend on how their work interleaves; the launch walks an item list that keeps chunk c of pack(-x), pack(+x), unpack(-x),
+ * unpack(+x) of a variable adjacent -- those four touch the same one or two 32-byte sectors per grid row, so the strided
+ * faces cost one DRAM burst per row instead of four (csrc/halo.cu: halo_items_kernel).  Same result as pack then unpack.
+ * Tuning Comm_HALO_PACKING_FUSED `unroll` 2 = run the two launches instead; 3 = x-face items first instead of mixed in.  */
+int  rpb200_halo_plan_pack_unpack(rpb200_halo_plan*, rpb200_stream_t);
 
 /* (3) HALO_EXCHANGE_FUSED over NVLink peer memory (replaces MPI_Irecv / MPI_Isend /
  *     MPI_Waitall on host-pinned buffers, HALO_EXCHANGE_FUSED-Cuda.cpp:109-196).
@@ -225,7 +261,9 @@ int  rpb200_halo_sendrecv_put(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_sendrecv_wait(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_recv_buffer(rpb200_halo_plan*, int l, const double** d_ptr, int64_t* len);
 int  rpb200_halo_exchange(rpb200_halo_plan*, rpb200_stream_t);
-/* 0, or RPB200_ETIMEDOUT if an unpack CTA gave up waiting for a flag (synchronises)        */
+/* 0, or RPB200_ETIMEDOUT if an unpack CTA gave up waiting for a message (synchronises).  The wait is bounded in wall-clock
+ * time (%globaltimer; 2 s, RPB200_HALO_TIMEOUT_MS overrides); a message that did not arrive is NOT unpacked and the rep's
+ * epoch is NOT committed: the caller must treat a non-zero status as fatal for the plan (the suite stubs abort).        */
 int  rpb200_halo_exchange_status(rpb200_halo_plan*);
 
 /* CUDA IPC plumbing so one-process-per-GPU ranks can map each other's buffers

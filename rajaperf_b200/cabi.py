@@ -36,6 +36,8 @@ SIGNATURES = {
     "rpb200_error_string": (c_char_p, [c_int]),
     "rpb200_sm_count": (c_int, [_P]),
     "rpb200_version": (c_char_p, []),
+    "rpb200_stream_attach": (c_int, [_P, _P]),
+    "rpb200_stream_detach": (c_int, [_P, _P]),
     "rpb200_set_tuning": (c_int, [_P, c_char_p, c_int, c_int, c_int]),
     "rpb200_reset_tuning": (c_int, [_P, c_char_p]),
     "rpb200_stream_copy": (c_int, [_P, _P, _P, c_int64, _P]),
@@ -63,6 +65,7 @@ SIGNATURES = {
     "rpb200_halo_worklist_destroy": (None, [_P]),
     "rpb200_halo_pack": (c_int, [_P, _P, _P]),
     "rpb200_halo_unpack": (c_int, [_P, _P, _P]),
+    "rpb200_halo_pack_unpack": (c_int, [_P, _P, _P, _P]),
     "rpb200_halo_grid_dims": (None, [c_int64, POINTER(c_int64)]),
     "rpb200_halo_plan_create": (c_int, [_P, POINTER(c_int64), c_int64, c_int, c_int, POINTER(c_int), POINTER(_P)]),
     "rpb200_halo_plan_destroy": (None, [_P]),
@@ -72,6 +75,7 @@ SIGNATURES = {
     "rpb200_halo_plan_bind": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(_P)]),
     "rpb200_halo_plan_pack": (c_int, [_P, _P]),
     "rpb200_halo_plan_unpack": (c_int, [_P, _P]),
+    "rpb200_halo_plan_pack_unpack": (c_int, [_P, _P]),
     "rpb200_halo_exchange_window": (c_int, [_P, POINTER(_P), POINTER(_P), POINTER(c_size_t), POINTER(c_ubyte)]),
     "rpb200_halo_exchange_connect": (c_int, [_P, c_int, POINTER(c_ubyte)]),
     "rpb200_halo_exchange_connect_ptrs": (c_int, [_P, c_int, POINTER(_P)]),
@@ -181,6 +185,20 @@ class Context:
         """Built-in launch shape of `kernel` (None: of every kernel) again."""
         check(self.lib.rpb200_reset_tuning(self.h, kernel.encode() if kernel else None), f"reset_tuning({kernel})")
 
+    def stream_attach(self, stream=None):
+        """Give a stream (default: torch's current one) its scratch set now (rpb200.h: needed before capturing on the 5th+
+        stream of a context)."""
+        check(self.lib.rpb200_stream_attach(self.h, _stream() if stream is None else stream), "stream_attach")
+
+    def stream_detach(self, stream=None):
+        check(self.lib.rpb200_stream_detach(self.h, _stream() if stream is None else stream), "stream_detach")
+
+    def scan_reserve(self, n: int):
+        check(self.lib.rpb200_scan_reserve(self.h, n), "scan_reserve")
+
+    def indexlist_reserve(self, n: int):
+        check(self.lib.rpb200_indexlist_reserve(self.h, n), "indexlist_reserve")
+
     # ---- Stream --------------------------------------------------------------------------
     def stream_copy(self, c, a, n=None):
         n = a.numel() if n is None else n
@@ -273,6 +291,10 @@ class Context:
     def halo_unpack(self, wl):
         check(self.lib.rpb200_halo_unpack(self.h, wl.h, _stream()), "halo_unpack")
 
+    def halo_pack_unpack(self, pack_wl, unpack_wl):
+        """pack + unpack of one rep in ONE launch (the two lists must touch disjoint memory: rpb200.h)."""
+        check(self.lib.rpb200_halo_pack_unpack(self.h, pack_wl.h, unpack_wl.h, _stream()), "halo_pack_unpack")
+
     def halo_plan(self, grid_dims, halo_width=1, num_vars=3, rank=0, rank_dims=(1, 1, 1)):
         return HaloPlan(self, grid_dims, halo_width, num_vars, rank, rank_dims)
 
@@ -363,6 +385,10 @@ class HaloPlan:
 
     def unpack(self):
         check(self.lib.rpb200_halo_plan_unpack(self.h, _stream()), "halo_plan_unpack")
+
+    def pack_unpack(self):
+        """One rep of HALO_PACKING_FUSED in ONE launch (pack and unpack items interleaved)."""
+        check(self.lib.rpb200_halo_plan_pack_unpack(self.h, _stream()), "halo_plan_pack_unpack")
 
     def window(self, vars_, want_handle=True):
         """Allocate this rank's receive window; returns (device pointer, bytes, ipc handle bytes).

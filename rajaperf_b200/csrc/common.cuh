@@ -35,27 +35,54 @@ enum rpb_kernel_id {
   RPB_K_COUNT
 };
 
+#define RPB_MAX_PARTIALS 8192
+#define RPB_MAX_STREAMS 64        // distinct streams one context can serve at the same time
+#define RPB_PREALLOC_STREAMS 4    // scratch sets allocated by rpb200_create (no allocation on the first call of a stream)
+
+// Everything a kernel writes besides the caller's arrays, ONE SET PER (context, stream): calls on different streams of one
+// context never share a ticket, a partial, a look-back descriptor or an epoch (the reference gives every reducer its own
+// scratch, GPUUtils.hpp:250-330).  All state is left re-armed by the kernel that used it, so nothing is cleared between calls,
+// and the look-back epochs live in DEVICE memory (read at kernel start, committed by the last CTA to retire): a captured
+// graph holding one scan replays correctly any number of times.
+struct rpb_scratch {
+  cudaStream_t  stream;            // the stream this set is attached to
+  int           attached;
+  void*         d_fixed;           // one allocation: partials | tickets | epochs | basis tables
+  double*       d_partials;        // 2 x RPB_MAX_PARTIALS doubles (DOT, REDUCE_SUM)
+  unsigned int* d_ticket;          // [0] DOT [1] REDUCE_SUM
+  unsigned int* d_scan_ticket;     // [0..1] scan.cu [2..3] scan_tma.cu [4..5] indexlist.cu [6..7] indexlist_tma.cu
+  unsigned long long* d_epoch;     // [0] scan [1] indexlist: epoch of the LAST COMPLETED call
+  double*       d_basis_tables;    // 64 doubles: PA basis tables built per call by a 1-CTA prologue
+  void*         d_scan_state;      // look-back descriptors, grown lazily (rpb200_scan_reserve pre-sizes)
+  size_t        scan_state_bytes;
+  void*         d_ilist_state;
+  size_t        ilist_state_bytes;
+};
+
 struct rpb200_ctx {
   int device;
   int sm_count;
   rpb_tuning tune[RPB_K_COUNT];
-  // reductions: per-CTA partials + a ticket counter (self-resetting)
-  double*       d_partials;      // RPB_MAX_PARTIALS doubles
-  unsigned int* d_ticket;        // 1 counter per reduction kernel kind (2)
-  // scan: per-tile look-back state, epoch-tagged so no memset is needed per call
-  void*         d_scan_state;    // allocated lazily, grows with n
-  size_t        scan_state_bytes;
-  unsigned int  scan_epoch;
-  unsigned int* d_scan_ticket;   // dynamic tile counter, reset by the last tile
-  // diffusion: effective basis tables (48 doubles) built per call by a 1-CTA prologue
-  double*       d_basis_tables;
-  // indexlist: 8-byte look-back descriptors, epoch-tagged like the scan's
-  void*         d_ilist_state;
-  size_t        ilist_state_bytes;
-  unsigned int  ilist_epoch;
+  rpb_scratch slot[RPB_MAX_STREAMS];
+  int         last_slot;           // the slot of the previous call (the common case: one stream)
+  size_t      scan_reserve_bytes;  // rpb200_scan_reserve / rpb200_indexlist_reserve: minimum state size of every slot
+  size_t      ilist_reserve_bytes;
+  volatile int lock;               // slot table spin lock (the reference drives a context from one host thread)
 };
 
-#define RPB_MAX_PARTIALS 8192
+// The scratch set of (ctx, stream); attaches a free set on the first call of a stream (allocating it if it is not one of
+// the pre-allocated ones -- illegal while the stream is being captured: rpb200_stream_attach() it beforehand).
+// Also checks that the calling thread's current device is the context's.  nullptr + *err on failure.
+rpb_scratch* rpb_get_scratch(rpb200_ctx* ctx, cudaStream_t st, int* err);
+int rpb_grow_state(void** d_state, size_t* bytes, size_t need, cudaStream_t st);
+
+#define RPB_SCRATCH(sc, ctx, st)                                        \
+  rpb_scratch* sc;                                                      \
+  { int rpb_se_ = 0; sc = rpb_get_scratch((ctx), (st), &rpb_se_); if (!sc) return rpb_se_; }
+
+// entry points that need no scratch still refuse to launch on another device than the context's
+#define RPB_CHECK_DEVICE(ctx)                                           \
+  do { int rpb_d_ = -1; RPB_CHECK(cudaGetDevice(&rpb_d_)); if (rpb_d_ != (ctx)->device) return RPB200_EDEVICE; } while (0)
 
 // ---------------------------------------------------------------------------------
 // 256-bit / 128-bit global accesses.  sm_100a has LDG/STG.256 (ld.global.v4.f64).

@@ -39,6 +39,118 @@ static void default_tunings(rpb200_ctx* c)
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }
 
+// ---- per-stream scratch ---------------------------------------------------------------
+namespace {
+struct slot_lock {
+  rpb200_ctx* c;
+  explicit slot_lock(rpb200_ctx* ctx) : c(ctx) { while (__sync_lock_test_and_set(&c->lock, 1)) { } }
+  ~slot_lock() { __sync_lock_release(&c->lock); }
+};
+
+constexpr size_t FIXED_PARTIALS = sizeof(double) * RPB_MAX_PARTIALS * 2;
+constexpr size_t FIXED_BYTES = FIXED_PARTIALS + 256 /* tickets */ + 256 /* epochs */ + 512 /* basis tables */;
+
+int slot_alloc(rpb_scratch* sc)
+{
+  if (sc->d_fixed) return 0;
+  RPB_CHECK(cudaMalloc(&sc->d_fixed, FIXED_BYTES));
+  cudaError_t e = cudaMemset(sc->d_fixed, 0, FIXED_BYTES);
+  if (e != cudaSuccess) { cudaFree(sc->d_fixed); sc->d_fixed = nullptr; return (int)e; }
+  char* p = (char*)sc->d_fixed;
+  sc->d_partials = (double*)p;
+  sc->d_ticket = (unsigned int*)(p + FIXED_PARTIALS);
+  sc->d_scan_ticket = sc->d_ticket + 8;
+  sc->d_epoch = (unsigned long long*)(p + FIXED_PARTIALS + 256);
+  sc->d_basis_tables = (double*)(p + FIXED_PARTIALS + 512);
+  return 0;
+}
+void slot_free(rpb_scratch* sc)
+{
+  cudaFree(sc->d_fixed);
+  cudaFree(sc->d_scan_state);
+  cudaFree(sc->d_ilist_state);
+  memset(sc, 0, sizeof(*sc));
+}
+}  // namespace
+
+// grows only; fresh memory is zeroed once: epoch 0 is never used, so fresh descriptors read "not ready"
+int rpb_grow_state(void** d_state, size_t* bytes, size_t need, cudaStream_t st)
+{
+  if (need <= *bytes) return 0;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+    return (int)cudaErrorStreamCaptureUnsupported;      // rpb200_scan_reserve / rpb200_indexlist_reserve before capturing
+  RPB_CHECK(cudaStreamSynchronize(st));
+  if (*d_state) RPB_CHECK(cudaFree(*d_state));
+  *d_state = nullptr; *bytes = 0;
+  const size_t cap_bytes = need + need / 2 + 4096;
+  RPB_CHECK(cudaMalloc(d_state, cap_bytes));
+  RPB_CHECK(cudaMemset(*d_state, 0, cap_bytes));
+  *bytes = cap_bytes;
+  return 0;
+}
+
+rpb_scratch* rpb_get_scratch(rpb200_ctx* ctx, cudaStream_t st, int* err)
+{
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { *err = (int)e; return nullptr; }
+  if (dev != ctx->device) { *err = RPB200_EDEVICE; return nullptr; }
+  slot_lock guard(ctx);
+  rpb_scratch* sc = &ctx->slot[ctx->last_slot];
+  if (sc->attached && sc->stream == st) return sc;
+  int free_ready = -1, free_any = -1;
+  for (int i = 0; i < RPB_MAX_STREAMS; ++i) {
+    rpb_scratch* c = &ctx->slot[i];
+    if (c->attached) {
+      if (c->stream == st) { ctx->last_slot = i; return c; }
+    } else if (c->d_fixed) {
+      if (free_ready < 0) free_ready = i;
+    } else if (free_any < 0) {
+      free_any = i;
+    }
+  }
+  const int i = free_ready >= 0 ? free_ready : free_any;
+  if (i < 0) { *err = RPB200_ENOSLOT; return nullptr; }
+  sc = &ctx->slot[i];
+  if (!sc->d_fixed) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) {
+      *err = (int)cudaErrorStreamCaptureUnsupported;
+      return nullptr;
+    }
+    const int rc = slot_alloc(sc);
+    if (rc != 0) { *err = rc; return nullptr; }
+  }
+  sc->stream = st;
+  sc->attached = 1;
+  ctx->last_slot = i;
+  return sc;
+}
+
+extern "C" int rpb200_stream_attach(rpb200_ctx* ctx, rpb200_stream_t s)
+{
+  if (!ctx) return RPB200_EINVAL;
+  RPB_SCRATCH(sc, ctx, rpb_stream(s));
+  int rc = rpb_grow_state(&sc->d_scan_state, &sc->scan_state_bytes, ctx->scan_reserve_bytes, nullptr);
+  if (rc == 0) rc = rpb_grow_state(&sc->d_ilist_state, &sc->ilist_state_bytes, ctx->ilist_reserve_bytes, nullptr);
+  return rc;
+}
+
+extern "C" int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t s)
+{
+  if (!ctx) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  slot_lock guard(ctx);
+  for (int i = 0; i < RPB_MAX_STREAMS; ++i)
+    if (ctx->slot[i].attached && ctx->slot[i].stream == st) {
+      ctx->slot[i].attached = 0;      // memory is kept for the next stream that attaches; its state is re-armed
+      ctx->slot[i].stream = nullptr;
+      return 0;
+    }
+  return RPB200_EINVAL;
+}
+
 extern "C" int rpb200_create(int device, rpb200_ctx** out)
 {
   if (!out) return RPB200_EINVAL;
@@ -46,7 +158,8 @@ extern "C" int rpb200_create(int device, rpb200_ctx** out)
   int ndev = 0;
   RPB_CHECK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return (int)cudaErrorInvalidDevice;
-  RPB_CHECK(cudaSetDevice(device));
+  int prev = -1;
+  RPB_CHECK(cudaGetDevice(&prev));
   cudaDeviceProp prop;
   RPB_CHECK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -58,17 +171,12 @@ extern "C" int rpb200_create(int device, rpb200_ctx** out)
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   default_tunings(c);
-  cudaError_t e;
-  if ((e = cudaMalloc(&c->d_partials, sizeof(double) * RPB_MAX_PARTIALS * 2)) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_ticket, sizeof(unsigned int) * 8)) != cudaSuccess ||
-      (e = cudaMemset(c->d_ticket, 0, sizeof(unsigned int) * 8)) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_scan_ticket, sizeof(unsigned int) * 8)) != cudaSuccess ||
-      (e = cudaMemset(c->d_scan_ticket, 0, sizeof(unsigned int) * 8)) != cudaSuccess ||
-      (e = cudaMalloc(&c->d_basis_tables, sizeof(double) * 64)) != cudaSuccess) {
-    rpb200_destroy(c);
-    return (int)e;
-  }
-  c->scan_epoch = 0;
+  // the caller's current device is left as it was (a host holding contexts for several GPUs selects the device itself
+  // before each call; every entry point checks it and returns RPB200_EDEVICE on a mismatch)
+  cudaError_t e = cudaSetDevice(device);
+  for (int i = 0; e == cudaSuccess && i < RPB_PREALLOC_STREAMS; ++i) e = (cudaError_t)slot_alloc(&c->slot[i]);
+  cudaSetDevice(prev);
+  if (e != cudaSuccess) { rpb200_destroy(c); return (int)e; }
   *out = c;
   return 0;
 }
@@ -76,13 +184,11 @@ extern "C" int rpb200_create(int device, rpb200_ctx** out)
 extern "C" void rpb200_destroy(rpb200_ctx* c)
 {
   if (!c) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  cudaFree(c->d_partials);
-  cudaFree(c->d_ticket);
-  cudaFree(c->d_scan_ticket);
-  cudaFree(c->d_scan_state);
-  cudaFree(c->d_basis_tables);
-  cudaFree(c->d_ilist_state);
+  for (int i = 0; i < RPB_MAX_STREAMS; ++i) slot_free(&c->slot[i]);
+  if (prev >= 0) cudaSetDevice(prev);
   free(c);
 }
 
@@ -90,6 +196,9 @@ extern "C" const char* rpb200_error_string(int err)
 {
   if (err == 0) return "success";
   if (err == RPB200_EINVAL) return "rpb200: invalid argument";
+  if (err == RPB200_ETIMEDOUT) return "rpb200: timed out waiting for a halo message";
+  if (err == RPB200_EDEVICE) return "rpb200: the current CUDA device is not the context's device";
+  if (err == RPB200_ENOSLOT) return "rpb200: too many streams attached to one context (rpb200_stream_detach)";
   return cudaGetErrorString((cudaError_t)err);
 }
 

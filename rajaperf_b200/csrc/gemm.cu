@@ -168,6 +168,7 @@ extern "C" int rpb200_polybench_gemm(rpb200_ctx* ctx, const double* A, const dou
 {
   (void)beta;     // dead in the reference body as well (POLYBENCH_GEMM.hpp:32-39)
   if (!ctx || ni < 0 || nj < 0 || nk < 0) return RPB200_EINVAL;
+  RPB_CHECK_DEVICE(ctx);
   if (ni == 0 || nj == 0) return 0;
   if (!C || (nk > 0 && (!A || !B))) return RPB200_EINVAL;
   if (ni > 0x7fffffffll || nj > 0x7fffffffll || nk > 0x7fffffffll) return RPB200_EINVAL;

@@ -15,6 +15,7 @@
 //                                                      release/acquire flags replace MPI_Waitall
 #include "common.cuh"
 
+#include <algorithm>
 #include <math.h>
 #include <new>
 #include <stdlib.h>
@@ -106,8 +107,9 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
             const int* __restrict__ chunk_seg, const long long* __restrict__ seg_first_chunk, int total_chunks,
             const halo_msg* __restrict__ msgs, unsigned int* __restrict__ msg_done,
             unsigned long long* __restrict__ d_epoch, unsigned int* __restrict__ unpack_done,
-            int* __restrict__ error, int chunk_lo, int commit, int reverse)
+            int* __restrict__ error, int chunk_lo, int commit, int reverse, unsigned long long timeout_ns)
 {
+  __shared__ int s_ok;
   // reverse (pack launches): walk the chunks from the end of the work list, so that the strided x faces -- first in the
   // list -- are packed LAST and are the most recently used L2 lines when the unpack, which walks forward, starts with
   // the ghost cells that share those lines (LIFO reuse across the two launches).
@@ -126,6 +128,7 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   const int c_end = STRIDED ? total_chunks : min(c_begin + per, total_chunks);
   const int c_step = STRIDED ? (int)gridDim.x : 1;
   int waited_msg = -1;
+  bool timed_out = false;
   const unsigned long long pol_keep = HINT ? policy_keep() : 0ull, pol_once = HINT ? policy_once() : 0ull;
 
   const int c_flip = chunk_lo + total_chunks - 1;          // reverse: chunk c stands for chunk c_flip - c
@@ -139,15 +142,22 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
     if (MODE == 2 && seg.msg != waited_msg) {      // first chunk of a message this CTA touches: acquire it
       if (threadIdx.x == 0) {
         const unsigned long long* f = msgs[seg.msg].my_flag;
-        unsigned int spins = 0;
+        unsigned long long t0 = 0, t1 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        int ok = 1;
         while (ld_acquire_sys(f) < epoch) {
           __nanosleep(40);
-          if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }   // > 1 s: give up loudly
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          if (t1 - t0 > timeout_ns) { atomicExch(error, RPB200_ETIMEDOUT); ok = 0; break; }   // wall-clock bound: give up loudly
         }
+        s_ok = ok;
       }
+      __syncthreads();
+      timed_out = timed_out || (s_ok == 0);
       __syncthreads();
       waited_msg = seg.msg;
     }
+    if (MODE == 2 && timed_out) continue;          // a message that did not arrive is NOT unpacked (and the epoch not committed)
 
     const int* __restrict__ list = seg.list + i0;
     double* __restrict__ buf = seg.buffer + i0;
@@ -224,133 +234,213 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
   if (MODE == 2 && commit) {
     __syncthreads();
     if (threadIdx.x == 0) {
+      __threadfence();
       const unsigned int prev = atomicAdd(unpack_done, 1u);
-      if (prev == gridDim.x - 1) {       // every CTA has read the epoch and finished: commit it
+      if (prev == gridDim.x - 1) {       // every CTA has read the epoch and finished: commit it (unless a message timed out)
         *unpack_done = 0u;
-        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
+        __threadfence();
+        int err = 0;
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(err) : "l"(error) : "memory");
+        if (err == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
       }
     }
   }
 }
 
-// HALO_EXCHANGE_FUSED as ONE launch: every CTA first packs its share of the chunks (storing into the peers'
-// windows and crediting / releasing the messages it completes), then turns to its share of the unpack chunks,
-// acquiring each message's flag the first time it touches it.  The grid is sized to be fully co-resident, and the
-// pack phase never waits, so every rank's flags are eventually released: no deadlock.  Compared with the
-// pack-launch + unpack-launch pair this overlaps the tail of the (NVLink-bound) packing with the first unpacks
-// and removes one launch.  Pack reads owned cells, unpack writes ghost cells: the two phases never alias.
-struct halo_side {
-  const rpb200_halo_seg* segs_g0; const rpb200_halo_seg* segs_g1;
-  const int* chunk_seg; const long long* seg_first_chunk; int total_chunks;
+// ------------------------------------------------------------------------------------------------------------------
+// The ITEM-LIST kernel: HALO_PACKING_FUSED as ONE launch (pack and unpack items interleaved), and HALO_EXCHANGE_FUSED as ONE
+// launch (all pack items, signal, then wait + unpack items).
+//
+// Why.  ncu on the two-launch form (profiles/r01_halo_l2_forward_vs_backward.csv): 320 MB of DRAM traffic per rep for 190 MB
+// of algorithmic bytes, at half of the DRAM bandwidth.  The waste is all in the +-x faces.  A cell of the -x / +x face is one
+// 8-byte word per (j, k) row of the variable, 4112 bytes from the next one: every access is its own DRAM burst (64 bytes
+// fetched for 8 used), and the pack launch (owned cells i = 1, i = nx) and the unpack launch (ghost cells i = 0, i = nx + 1)
+// each pay it, the unpack as a read-modify-write of a partial sector.  But in memory the four cells
+//      (nx, j, k)  (nx+1, j, k)  (0, j+1, k)  (1, j+1, k)      =  +x owned, +x ghost, -x ghost, -x owned
+// are CONSECUTIVE (the end of row j and the start of row j + 1): 32 bytes, one sector when j is even, two adjacent sectors
+// when j is odd.  So element n of the four tuples  pack(-x), pack(+x), unpack(-x), unpack(+x)  of one variable touch the same
+// one or two sectors.  An item list that puts chunk c of those four tuples NEXT TO EACH OTHER, dealt round-robin to
+// neighbouring CTAs, turns four DRAM bursts (one of them a read-modify-write) into one burst read + one write-back: the other
+// three accesses hit the line in L2 while it is still there.  The same adjacency serves the index lists: the items of the
+// three variables of one (neighbour, chunk) sit together, so a list chunk is fetched from DRAM once and hit twice.
+// Pack and unpack of HALO_PACKING_FUSED touch disjoint cells (owned / ghost) and disjoint buffers
+// (HALO_PACKING_FUSED-Seq.cpp:43-97), so any interleaving computes the reference's result.
+//
+// Dealing is round-robin (item i -> CTA i mod grid), which spreads the slow strided items and the streaming items evenly
+// over every CTA; the list order mixes the two kinds so that the burst-bound x-face work overlaps the bandwidth-bound rest.
+// A thread keeps the index loads of its NEXT item in flight while it gathers / scatters the current one.
+struct halo_item { int seg; int chunk; };            // seg: tuple index, bit 30 set = unpack side
+constexpr int ITEM_UNPACK = 1 << 30;
+constexpr int ITEMS_MAX_SEGS = 128;                  // tuples per side kept in shared memory (26 neighbours x <= 4 variables)
+
+struct halo_items_args {
+  const rpb200_halo_seg* psegs[2];                   // pack tuples, generation 0 / 1 (the same array for HALO_PACKING_FUSED)
+  const rpb200_halo_seg* usegs[2];
+  const halo_item* items;
+  int n_items, n_pack_items, npsegs, nusegs;         // XCHG: items [0, n_pack_items) are the pack phase
+  const halo_msg* pmsgs; const halo_msg* umsgs;
+  unsigned int* msg_done; unsigned long long* d_epoch; unsigned int* unpack_done; int* error;
+  unsigned long long timeout_ns;
 };
 
-__global__ void __launch_bounds__(HALO_BLOCK)
-halo_exchange_kernel(halo_side P, halo_side U, const halo_msg* __restrict__ pmsgs, const halo_msg* __restrict__ umsgs,
-                     unsigned int* __restrict__ msg_done, unsigned long long* __restrict__ d_epoch,
-                     unsigned int* __restrict__ unpack_done, int* __restrict__ error)
+template <bool XCHG>
+__global__ void __launch_bounds__(HALO_BLOCK, 4)
+halo_items_kernel(const __grid_constant__ halo_items_args A)
 {
   constexpr int EPT = HALO_CHUNK / HALO_BLOCK;
+  __shared__ rpb200_halo_seg s_seg[2][ITEMS_MAX_SEGS];
+  __shared__ unsigned int s_credit[NNB];
+  __shared__ int s_ok;
   unsigned long long epoch = 0;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
-  epoch += 1;
-  const bool odd = (epoch & 1ull) != 0;
-  const rpb200_halo_seg* __restrict__ psegs = odd ? P.segs_g1 : P.segs_g0;
-  const rpb200_halo_seg* __restrict__ usegs = odd ? U.segs_g1 : U.segs_g0;
-  const int step = (int)gridDim.x;
-
-  // ---- phase 1: pack + signal
-  for (int c = blockIdx.x; c < P.total_chunks; c += step) {
-    const int s = __ldg(P.chunk_seg + c);
-    const rpb200_halo_seg seg = psegs[s];
-    const int64_t i0 = ((int64_t)c - __ldg(P.seg_first_chunk + s)) * HALO_CHUNK;
-    const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
-    const int* __restrict__ list = seg.list + i0;
-    double* __restrict__ buf = seg.buffer + i0;
-    const double* __restrict__ var = seg.var;
-    int idx[EPT]; double v[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; idx[k] = (i < cnt) ? __ldg(list + i) : -1; }
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+  if (XCHG) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(A.d_epoch) : "memory");
+    epoch += 1;
   }
-  if ((int)blockIdx.x < P.total_chunks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      int c = blockIdx.x;
-      while (c < P.total_chunks) {
-        const int m = psegs[__ldg(P.chunk_seg + c)].msg;
-        int run = 1;
-        while (c + run * step < P.total_chunks && psegs[__ldg(P.chunk_seg + c + run * step)].msg == m) ++run;
-        const halo_msg hm = pmsgs[m];
-        const unsigned int prev = atomicAdd(msg_done + m, (unsigned int)run);
-        if (prev + run == hm.chunks) {
-          msg_done[m] = 0u;
-          st_release_sys(hm.remote_flag, epoch);
-        }
-        c += run * step;
-      }
-    }
+  const int gen = XCHG ? (int)(epoch & 1ull) : 0;
+  {
+    const rpb200_halo_seg* __restrict__ ps = A.psegs[gen];
+    const rpb200_halo_seg* __restrict__ us = A.usegs[gen];
+    for (int i = threadIdx.x; i < A.npsegs; i += HALO_BLOCK) s_seg[0][i] = ps[i];
+    for (int i = threadIdx.x; i < A.nusegs; i += HALO_BLOCK) s_seg[1][i] = us[i];
+    if (threadIdx.x < NNB) s_credit[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) s_ok = 1;
   }
+  __syncthreads();
 
-  // ---- phase 2: wait + unpack
-  int waited_msg = -1;
-  for (int c = blockIdx.x; c < U.total_chunks; c += step) {
-    const int s = __ldg(U.chunk_seg + c);
-    const rpb200_halo_seg seg = usegs[s];
-    const int64_t i0 = ((int64_t)c - __ldg(U.seg_first_chunk + s)) * HALO_CHUNK;
-    const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
-    if (seg.msg != waited_msg) {
-      if (threadIdx.x == 0) {
-        const unsigned long long* f = umsgs[seg.msg].my_flag;
-        unsigned int spins = 0;
-        while (ld_acquire_sys(f) < epoch) {
-          __nanosleep(40);
-          if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }
-        }
-      }
-      __syncthreads();
-      waited_msg = seg.msg;
+  const int G = (int)gridDim.x;
+  int idx[EPT], nidx[EPT];
+  // the index loads of item `it` (or nothing past the end of this CTA's share)
+  auto fetch = [&](int it, int end, int (&dst)[EPT], halo_item& h) {
+    if (it < end) {
+      h = A.items[it];
+      const rpb200_halo_seg& seg = s_seg[(h.seg & ITEM_UNPACK) ? 1 : 0][h.seg & (ITEM_UNPACK - 1)];
+      const int64_t i0 = (int64_t)h.chunk * HALO_CHUNK;
+      const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
+      const int* __restrict__ list = seg.list + i0;
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; dst[k] = (i < cnt) ? __ldg(list + i) : -1; }
     }
-    const int* __restrict__ list = seg.list + i0;
-    const double* __restrict__ buf = seg.buffer + i0;
+  };
+  auto move = [&](const halo_item h, const int (&ix)[EPT]) {
+    const bool unpack = (h.seg & ITEM_UNPACK) != 0;
+    const rpb200_halo_seg& seg = s_seg[unpack ? 1 : 0][h.seg & (ITEM_UNPACK - 1)];
+    double* __restrict__ buf = seg.buffer + (int64_t)h.chunk * HALO_CHUNK;
     double* __restrict__ var = seg.var;
-    int idx[EPT]; double v[EPT];
+    double v[EPT];
+    if (!unpack) {
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; idx[k] = (i < cnt) ? __ldg(list + i) : -1; }
+      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = var[ix[k]];
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+    } else {
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) var[idx[k]] = v[k];
+      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) var[ix[k]] = v[k];
+    }
+  };
+
+  // ---- phase 1: every item (HALO_PACKING_FUSED) / the pack items (exchange)
+  const int end1 = XCHG ? A.n_pack_items : A.n_items;
+  {
+    halo_item h, nh;
+    fetch((int)blockIdx.x, end1, idx, h);
+    for (int it = blockIdx.x; it < end1; it += G) {
+      fetch(it + G, end1, nidx, nh);
+      move(h, idx);
+      if (XCHG && threadIdx.x == 0) s_credit[s_seg[0][h.seg].msg] += 1u;     // only thread 0 touches s_credit between barriers
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
+      h = nh;
+    }
+  }
+  if (!XCHG) return;
+
+  // all remote stores of this CTA -> barrier -> ONE system fence -> credit every message it touched; whoever completes a
+  // message publishes the epoch to the destination's flag (release at system scope)
+  __syncthreads();
+  if (threadIdx.x == 0) __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < NNB && s_credit[threadIdx.x] != 0u) {
+    const int m = threadIdx.x;
+    const halo_msg hm = A.pmsgs[m];
+    const unsigned int mine = s_credit[m];
+    const unsigned int prev = atomicAdd(A.msg_done + m, mine);
+    if (prev + mine == hm.chunks) {
+      A.msg_done[m] = 0u;                // re-armed for the next rep (stream-ordered launches)
+      st_release_sys(hm.remote_flag, epoch);
+    }
+  }
+
+  // ---- phase 2: wait + unpack.  The grid is fully co-resident and phase 1 never waits, so every rank's flags are
+  // eventually released.  A message that does not arrive within the time-out is NOT unpacked and the epoch is NOT committed.
+  int waited_msg = -1;
+  bool failed = false;
+  {
+    halo_item h, nh;
+    const int first = A.n_pack_items + (int)blockIdx.x;
+    fetch(first, A.n_items, idx, h);
+    for (int it = first; it < A.n_items; it += G) {
+      fetch(it + G, A.n_items, nidx, nh);
+      const int m = s_seg[1][h.seg & (ITEM_UNPACK - 1)].msg;
+      if (m != waited_msg) {
+        if (threadIdx.x == 0) {
+          const unsigned long long* f = A.umsgs[m].my_flag;
+          unsigned long long t0 = 0, t1 = 0;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          int ok = 1;
+          while (ld_acquire_sys(f) < epoch) {
+            __nanosleep(40);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > A.timeout_ns) { atomicExch(A.error, RPB200_ETIMEDOUT); ok = 0; break; }
+          }
+          s_ok = ok;
+        }
+        __syncthreads();
+        failed = failed || (s_ok == 0);
+        __syncthreads();
+        waited_msg = m;
+      }
+      if (!failed) move(h, idx);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
+      h = nh;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(unpack_done, 1u);
-    if (prev == gridDim.x - 1) {         // every CTA has read the epoch and finished: commit it
-      *unpack_done = 0u;
-      asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
+    __threadfence();                     // this CTA's time-out report (if any) is visible before its retirement is counted
+    const unsigned int prev = atomicAdd(A.unpack_done, 1u);
+    if (prev == gridDim.x - 1) {         // every CTA has read the epoch and finished
+      *A.unpack_done = 0u;
+      __threadfence();
+      int err = 0;
+      asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(err) : "l"(A.error) : "memory");
+      if (err == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(A.d_epoch), "l"(epoch) : "memory");
     }
   }
 }
 
 // HALO_SENDRECV's receive side: wait for the 26 messages of this rep, then commit the epoch
-__global__ void halo_wait_kernel(const halo_msg* __restrict__ umsgs, unsigned long long* __restrict__ d_epoch, int* __restrict__ error)
+__global__ void halo_wait_kernel(const halo_msg* __restrict__ umsgs, unsigned long long* __restrict__ d_epoch, int* __restrict__ error,
+                                 unsigned long long timeout_ns)
 {
   unsigned long long epoch = 0;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(epoch) : "l"(d_epoch) : "memory");
   epoch += 1;
+  int ok = 1;
   if (threadIdx.x < NNB) {
     const unsigned long long* f = umsgs[threadIdx.x].my_flag;
-    unsigned int spins = 0;
+    unsigned long long t0 = 0, t1 = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while (ld_acquire_sys(f) < epoch) {
       __nanosleep(40);
-      if (++spins > (1u << 25)) { atomicExch(error, RPB200_ETIMEDOUT); break; }
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > timeout_ns) { atomicExch(error, RPB200_ETIMEDOUT); ok = 0; break; }
     }
   }
-  __syncwarp();
-  if (threadIdx.x == 0) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
+  ok = __all_sync(0xffffffffu, ok);      // a rep with a missing message is not committed
+  if (threadIdx.x == 0 && ok) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(d_epoch), "l"(epoch) : "memory");
 }
 
 struct worklist_dev {
@@ -363,11 +453,14 @@ struct worklist_dev {
   std::vector<int64_t> lens;
   std::vector<int> flags;
   std::vector<long long> first;     // host copy: first chunk of every tuple
+  std::vector<rpb200_halo_seg> h_segs;   // host copy of the tuples as built (geometry: len, msg, flags, var)
+  // item list of the one-launch pack+unpack kernel, cached on the PACK list for the unpack list it was merged with
+  void* d_items = nullptr; int n_items = 0; const void* merged_with = nullptr; int merged_mix = -1;
 };
 
 int worklist_free(worklist_dev& w)
 {
-  cudaFree(w.d_segs); cudaFree(w.d_chunk_seg); cudaFree(w.d_first);
+  cudaFree(w.d_segs); cudaFree(w.d_chunk_seg); cudaFree(w.d_first); cudaFree(w.d_items);
   if (w.h_stage) cudaFreeHost(w.h_stage);
   w = worklist_dev();
   return 0;
@@ -409,6 +502,7 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   if (chunks > 0x7fffffffll) return RPB200_EINVAL;
   w.total_chunks = chunks;
   w.first = first;
+  w.h_segs = segs;
   const size_t nb = sizeof(rpb200_halo_seg) * (size_t)(nsegs > 0 ? nsegs : 1);
   RPB_CHECK(cudaMalloc(&w.d_segs, nb));
   RPB_CHECK(cudaMallocHost(&w.h_stage, nb));
@@ -420,6 +514,19 @@ int worklist_build(worklist_dev& w, const rpb200_halo_seg* h_segs, int nsegs)
   }
   if (!map.empty()) RPB_CHECK(cudaMemcpy(w.d_chunk_seg, map.data(), sizeof(int) * map.size(), cudaMemcpyHostToDevice));
   return 0;
+}
+
+// how long an unpack CTA waits for a message before it reports RPB200_ETIMEDOUT (wall clock, %globaltimer);
+// RPB200_HALO_TIMEOUT_MS overrides the 2 s default
+unsigned long long halo_timeout_ns()
+{
+  static unsigned long long ns = 0;
+  if (ns == 0) {
+    const char* e = getenv("RPB200_HALO_TIMEOUT_MS");
+    const long ms = e ? atol(e) : 2000;
+    ns = (unsigned long long)(ms > 0 ? ms : 2000) * 1000000ull;
+  }
+  return ns;
 }
 
 struct exchange_args {
@@ -457,7 +564,7 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
 #define RPB_HALO_LAUNCH(H, S)                                                                                  \
   halo_kernel<PACK, MODE, H, S><<<(int)grid, HALO_BLOCK, 0, st>>>(                                             \
       w.d_segs, x.other_gen ? x.other_gen->d_segs : w.d_segs, w.d_chunk_seg, w.d_first, (int)chunk_hi,         \
-      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error, (int)chunk_lo, commit, reverse)
+      x.msgs, x.msg_done, x.d_epoch, x.unpack_done, x.error, (int)chunk_lo, commit, reverse, halo_timeout_ns())
   if (hint && strided) RPB_HALO_LAUNCH(true, true);
   else if (hint) RPB_HALO_LAUNCH(true, false);
   else if (strided) RPB_HALO_LAUNCH(false, true);
@@ -531,6 +638,8 @@ struct rpb200_halo_plan {
   unsigned long long* d_epoch = nullptr;   // committed exchange epoch (device): reps done so far
   unsigned int* d_unpack_done = nullptr;
   bool connected = false;
+  // item lists of the one-launch kernels (halo_items_kernel): HALO_PACKING_FUSED merged, exchange pack-then-unpack
+  halo_item* d_items_xchg = nullptr;   int n_items_xchg = 0, n_pack_items_xchg = 0;
 };
 
 extern "C" int rpb200_halo_chunk(void) { return HALO_CHUNK; }
@@ -601,6 +710,7 @@ extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
   cudaFree(p->d_window);
   cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_send_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
   cudaFree(p->d_epoch); cudaFree(p->d_unpack_done);
+  cudaFree(p->d_items_xchg);
   delete p;
 }
 
@@ -684,6 +794,182 @@ extern "C" int rpb200_halo_plan_neighbor(const rpb200_halo_plan* p, int l, int* 
   return 0;
 }
 
+// ---- item lists of the one-launch kernels ------------------------------------------------------------------------
+// Built from the geometry of two work lists alone.  The X TUPLES are the strided tuples (cells not adjacent in the variable)
+// of the greatest strided length -- for HALO_base's lists the -x and +x faces of every variable.  Chunk c of every X tuple
+// goes into one GROUP of adjacent items, the tuples of one variable next to each other (see halo_items_kernel); every other
+// tuple contributes groups {chunk c of the tuples of one message}.
+static int64_t plan_chunks(int64_t len) { return (len + HALO_CHUNK - 1) / HALO_CHUNK; }
+
+static int64_t x_tuple_len(const worklist_dev& a, const worklist_dev& b)
+{
+  int64_t m = 0;
+  for (const worklist_dev* w : {&a, &b})
+    for (const rpb200_halo_seg& s : w->h_segs) if ((s.flags & SEG_STRIDED) && s.len > m) m = s.len;
+  return m >= HALO_CHUNK ? m : 0;                       // short strided tuples (edges) are not worth a group of their own
+}
+static bool is_x_tuple(const rpb200_halo_seg& s, int64_t xlen) { return xlen > 0 && (s.flags & SEG_STRIDED) && s.len == xlen; }
+
+// the X tuples of both lists, ordered (variable, side, message): {pack(-x), pack(+x), unpack(-x), unpack(+x)} per variable
+struct x_ref { const double* var; int side; int msg; int seg; };
+static std::vector<x_ref> x_tuples(const worklist_dev& pw, const worklist_dev& uw, int64_t xlen, bool want_pack, bool want_unpack)
+{
+  std::vector<x_ref> x;
+  if (want_pack) for (int i = 0; i < pw.nsegs; ++i) if (is_x_tuple(pw.h_segs[i], xlen)) x.push_back(x_ref{pw.h_segs[i].var, 0, pw.h_segs[i].msg, i});
+  if (want_unpack) for (int i = 0; i < uw.nsegs; ++i) if (is_x_tuple(uw.h_segs[i], xlen)) x.push_back(x_ref{uw.h_segs[i].var, 1, uw.h_segs[i].msg, i | ITEM_UNPACK});
+  // variables in order of first appearance (not of address), then side, then message
+  std::vector<const double*> order;
+  for (const x_ref& r : x) { bool seen = false; for (const double* v : order) seen = seen || v == r.var; if (!seen) order.push_back(r.var); }
+  auto rank = [&](const double* v) { size_t k = 0; while (k < order.size() && order[k] != v) ++k; return k; };
+  std::stable_sort(x.begin(), x.end(), [&](const x_ref& a, const x_ref& b) {
+    const size_t ra = rank(a.var), rb = rank(b.var);
+    if (ra != rb) return ra < rb;
+    if (a.side != b.side) return a.side < b.side;
+    return a.msg < b.msg;
+  });
+  return x;
+}
+
+// mix: spread the X groups evenly among the streaming groups (Bresenham), so that the burst-bound and the bandwidth-bound
+// traffic are in flight together; otherwise X groups first.
+static void merge_groups(const std::vector<std::vector<halo_item>>& xg, const std::vector<std::vector<halo_item>>& sg, bool mix,
+                         std::vector<halo_item>& out)
+{
+  size_t ix = 0, is = 0;
+  const size_t nx = xg.size(), ns = sg.size();
+  while (ix < nx || is < ns) {
+    bool take_x;
+    if (!mix) take_x = ix < nx;
+    else if (ix >= nx) take_x = false;
+    else if (is >= ns) take_x = true;
+    else take_x = (ix + 1) * ns <= (is + 1) * nx;      // keep ix / nx and is / ns level
+    const std::vector<halo_item>& g = take_x ? xg[ix++] : sg[is++];
+    out.insert(out.end(), g.begin(), g.end());
+  }
+}
+
+// streaming groups of one list: for every message (run of consecutive tuples with the same msg), chunk-major
+static void stream_groups(const worklist_dev& w, int64_t xlen, int bit, std::vector<std::vector<halo_item>>& sg)
+{
+  int i = 0;
+  while (i < w.nsegs) {
+    int j = i;
+    int64_t maxc = 0;
+    while (j < w.nsegs && w.h_segs[j].msg == w.h_segs[i].msg) { if (!is_x_tuple(w.h_segs[j], xlen)) maxc = std::max(maxc, plan_chunks(w.h_segs[j].len)); ++j; }
+    for (int64_t c = 0; c < maxc; ++c) {
+      std::vector<halo_item> g;
+      for (int t = i; t < j; ++t)
+        if (!is_x_tuple(w.h_segs[t], xlen) && c < plan_chunks(w.h_segs[t].len)) g.push_back(halo_item{t | bit, (int)c});
+      if (!g.empty()) sg.push_back(g);
+    }
+    i = j;
+  }
+}
+
+// HALO_PACKING_FUSED: pack and unpack items interleaved
+static void build_items_merged(const worklist_dev& pw, const worklist_dev& uw, bool mix, std::vector<halo_item>& items)
+{
+  const int64_t xlen = x_tuple_len(pw, uw);
+  std::vector<std::vector<halo_item>> xg, sg, sp, su;
+  const std::vector<x_ref> x = x_tuples(pw, uw, xlen, true, true);
+  for (int64_t c = 0; c < plan_chunks(xlen) && !x.empty(); ++c) {
+    std::vector<halo_item> g;
+    for (const x_ref& r : x) g.push_back(halo_item{r.seg, (int)c});
+    xg.push_back(g);
+  }
+  stream_groups(pw, xlen, 0, sp);
+  stream_groups(uw, xlen, ITEM_UNPACK, su);
+  for (size_t k = 0; k < sp.size() || k < su.size(); ++k) {        // pack group, unpack group, pack group, ...
+    if (k < sp.size()) sg.push_back(sp[k]);
+    if (k < su.size()) sg.push_back(su[k]);
+  }
+  items.clear();
+  merge_groups(xg, sg, mix, items);
+}
+
+// HALO_EXCHANGE_FUSED: all pack items, then all unpack items.  The X tuples are packed LAST (ascending chunks) and unpacked
+// FIRST (descending chunks): the ghost cells share their L2 lines with the owned cells read a moment earlier (LIFO reuse
+// across the signal), and the -x / +x chunks of one variable stay adjacent so that they share their DRAM bursts.
+static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, std::vector<halo_item>& items, int* n_pack)
+{
+  const int64_t xlen = x_tuple_len(pw, uw);
+  std::vector<std::vector<halo_item>> sp, su;
+  stream_groups(pw, xlen, 0, sp);
+  stream_groups(uw, xlen, ITEM_UNPACK, su);
+  const std::vector<x_ref> xp = x_tuples(pw, uw, xlen, true, false), xu = x_tuples(pw, uw, xlen, false, true);
+  items.clear();
+  for (const auto& g : sp) items.insert(items.end(), g.begin(), g.end());
+  for (int64_t c = 0; c < plan_chunks(xlen) && !xp.empty(); ++c)
+    for (const x_ref& r : xp) items.push_back(halo_item{r.seg, (int)c});
+  *n_pack = (int)items.size();
+  for (int64_t c = plan_chunks(xlen) - 1; c >= 0 && !xu.empty(); --c)
+    for (size_t k = xu.size(); k-- > 0;) items.push_back(halo_item{xu[k].seg, (int)c});
+  for (const auto& g : su) items.insert(items.end(), g.begin(), g.end());
+}
+
+static int upload_items(const std::vector<halo_item>& items, halo_item** d_items)
+{
+  cudaFree(*d_items); *d_items = nullptr;
+  if (items.empty()) return 0;
+  RPB_CHECK(cudaMalloc(d_items, sizeof(halo_item) * items.size()));
+  RPB_CHECK(cudaMemcpy(*d_items, items.data(), sizeof(halo_item) * items.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+template <bool XCHG>
+static int launch_items(const rpb200_ctx* ctx, int kid, const halo_items_args& A, cudaStream_t st)
+{
+  if (A.n_items == 0) return 0;
+  int resident = 0;             // XCHG: the grid must be fully co-resident (phase 2 spins on flags other ranks' phase 1 releases)
+  RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_items_kernel<XCHG>, HALO_BLOCK, 0));
+  if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
+  int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
+  if (cps > resident) cps = resident;
+  int64_t grid = (int64_t)ctx->sm_count * cps;
+  const int64_t most = XCHG ? (A.n_pack_items > A.n_items - A.n_pack_items ? A.n_pack_items : A.n_items - A.n_pack_items) : A.n_items;
+  if (grid > most) grid = most;
+  if (grid < 1) grid = 1;
+  halo_items_kernel<XCHG><<<(int)grid, HALO_BLOCK, 0, st>>>(A);
+  RPB_LAUNCH_CHECK();
+  return 0;
+}
+
+// The one-launch pack + unpack over two work lists; the item list is built on the first call for a (pack, unpack) pair and
+// cached on the pack list.
+static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev& uw, cudaStream_t st)
+{
+  const int unroll = ctx->tune[RPB_K_HALO_PACKING_FUSED].unroll;
+  const bool two_launches = unroll == 2 || unroll == 4 || pw.nsegs > ITEMS_MAX_SEGS || uw.nsegs > ITEMS_MAX_SEGS;
+  if (two_launches) {                              // tuning `unroll` 2 / 4: the two-launch form (without / with L2 hints)
+    const int rc = worklist_launch<true, 0>(ctx, RPB_K_HALO_PACKING_FUSED, pw, exchange_args(), st);
+    return rc != 0 ? rc : worklist_launch<false, 0>(ctx, RPB_K_HALO_PACKING_FUSED, uw, exchange_args(), st);
+  }
+  const int mix = unroll == 3 ? 0 : 1;             // tuning `unroll` 3: X groups first instead of mixed in
+  if (pw.merged_with != (const void*)&uw || pw.merged_mix != mix) {
+    std::vector<halo_item> items;
+    build_items_merged(pw, uw, mix != 0, items);
+    halo_item* d = (halo_item*)pw.d_items;
+    const int rc = upload_items(items, &d);
+    pw.d_items = d;
+    if (rc != 0) { pw.merged_with = nullptr; return rc; }
+    pw.n_items = (int)items.size(); pw.merged_with = &uw; pw.merged_mix = mix;
+  }
+  halo_items_args A;
+  memset(&A, 0, sizeof(A));
+  A.psegs[0] = A.psegs[1] = pw.d_segs;
+  A.usegs[0] = A.usegs[1] = uw.d_segs;
+  A.items = (const halo_item*)pw.d_items; A.n_items = pw.n_items; A.n_pack_items = 0;
+  A.npsegs = pw.nsegs; A.nusegs = uw.nsegs;
+  return launch_items<false>(ctx, RPB_K_HALO_PACKING_FUSED, A, st);
+}
+
+extern "C" int rpb200_halo_pack_unpack(rpb200_ctx* ctx, rpb200_halo_worklist* pack, rpb200_halo_worklist* unpack, rpb200_stream_t s)
+{
+  if (!ctx || !pack || !unpack || pack == unpack) return RPB200_EINVAL;
+  RPB_CHECK_DEVICE(ctx);
+  return worklist_pack_unpack(ctx, pack->w, unpack->w, rpb_stream(s));
+}
+
 // neighbour-major, variable-minor segments (HALO_PACKING_FUSED-Seq.cpp:43-61, 71-97)
 static int plan_segments(const rpb200_halo_plan* p, bool pack, double* const* vars, double* const* buffers,
                          std::vector<rpb200_halo_seg>& segs)
@@ -721,6 +1007,15 @@ extern "C" int rpb200_halo_plan_bind(rpb200_halo_plan* p, double* const* vars, d
   if (rc != 0) { worklist_free(p->pack_wl); worklist_free(p->unpack_wl); return rc; }
   p->bound = true;
   return 0;
+}
+
+// HALO_PACKING_FUSED, one rep in ONE launch: the pack of HALO_PACKING_FUSED-Seq.cpp:43-61 and the unpack of :71-97 touch
+// disjoint cells and buffers, so their items may interleave (halo_items_kernel)
+extern "C" int rpb200_halo_plan_pack_unpack(rpb200_halo_plan* p, rpb200_stream_t s)
+{
+  if (!p || !p->bound) return RPB200_EINVAL;
+  RPB_CHECK_DEVICE(p->ctx);
+  return worklist_pack_unpack(p->ctx, p->pack_wl, p->unpack_wl, rpb_stream(s));
 }
 
 extern "C" int rpb200_halo_plan_pack(rpb200_halo_plan* p, rpb200_stream_t s)
@@ -809,6 +1104,15 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
   }
   RPB_CHECK(cudaMemcpy(p->d_pack_msgs, pm.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
   RPB_CHECK(cudaMemcpy(p->d_unpack_msgs, um.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
+  cudaFree(p->d_items_xchg); p->d_items_xchg = nullptr; p->n_items_xchg = 0;
+  if (!p->vars.empty() && NNB * p->nvars <= ITEMS_MAX_SEGS) {
+    std::vector<halo_item> items;
+    int n_pack = 0;
+    build_items_xchg(p->xpack_wl[0], p->xunpack_wl[0], items, &n_pack);
+    const int rc = upload_items(items, &p->d_items_xchg);
+    if (rc != 0) return rc;
+    p->n_items_xchg = (int)items.size(); p->n_pack_items_xchg = n_pack;
+  }
   p->connected = true;
   return 0;
 }
@@ -893,22 +1197,19 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
     const int rc = rpb200_halo_exchange_pack(p, s);
     return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
   }
-  int resident = 0;             // CTAs of the fused kernel that fit one SM: the grid must be fully co-resident
-  RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_exchange_kernel, HALO_BLOCK, 0));
-  if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
-  int cps = t.ctas_per_sm > 0 ? t.ctas_per_sm : 4;
-  if (cps > resident) cps = resident;
-  const worklist_dev& pw = p->xpack_wl[0]; const worklist_dev& uw = p->xunpack_wl[0];
-  int64_t grid = (int64_t)p->ctx->sm_count * cps;
-  const int64_t most = pw.total_chunks > uw.total_chunks ? pw.total_chunks : uw.total_chunks;
-  if (grid > most) grid = most;
-  if (grid < 1) return 0;
-  halo_side P{pw.d_segs, p->xpack_wl[1].d_segs, pw.d_chunk_seg, pw.d_first, (int)pw.total_chunks};
-  halo_side U{uw.d_segs, p->xunpack_wl[1].d_segs, uw.d_chunk_seg, uw.d_first, (int)uw.total_chunks};
-  halo_exchange_kernel<<<(int)grid, HALO_BLOCK, 0, rpb_stream(s)>>>(P, U, p->d_pack_msgs, p->d_unpack_msgs, p->d_msg_done,
-                                                                    p->d_epoch, p->d_unpack_done, p->d_error);
-  RPB_LAUNCH_CHECK();
-  return 0;
+  if (!p->d_items_xchg) {       // more tuples than the item kernel keeps in shared memory: two launches
+    const int rc = rpb200_halo_exchange_pack(p, s);
+    return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
+  }
+  halo_items_args A;
+  memset(&A, 0, sizeof(A));
+  A.psegs[0] = p->xpack_wl[0].d_segs; A.psegs[1] = p->xpack_wl[1].d_segs;
+  A.usegs[0] = p->xunpack_wl[0].d_segs; A.usegs[1] = p->xunpack_wl[1].d_segs;
+  A.items = p->d_items_xchg; A.n_items = p->n_items_xchg; A.n_pack_items = p->n_pack_items_xchg;
+  A.npsegs = p->xpack_wl[0].nsegs; A.nusegs = p->xunpack_wl[0].nsegs;
+  A.pmsgs = p->d_pack_msgs; A.umsgs = p->d_unpack_msgs; A.msg_done = p->d_msg_done; A.d_epoch = p->d_epoch;
+  A.unpack_done = p->d_unpack_done; A.error = p->d_error; A.timeout_ns = halo_timeout_ns();
+  return launch_items<true>(p->ctx, RPB_K_HALO_EXCHANGE_FUSED, A, rpb_stream(s));
 }
 
 // ---- HALO_SENDRECV (comm/HALO_SENDRECV-Seq.cpp:34-52): transport only -----------------------------------
@@ -955,7 +1256,7 @@ extern "C" int rpb200_halo_sendrecv_put(rpb200_halo_plan* p, rpb200_stream_t s)
 extern "C" int rpb200_halo_sendrecv_wait(rpb200_halo_plan* p, rpb200_stream_t s)
 {
   if (!p || !p->connected || !p->send_bound) return RPB200_EINVAL;
-  halo_wait_kernel<<<1, 32, 0, rpb_stream(s)>>>(p->d_unpack_msgs, p->d_epoch, p->d_error);
+  halo_wait_kernel<<<1, 32, 0, rpb_stream(s)>>>(p->d_unpack_msgs, p->d_epoch, p->d_error, halo_timeout_ns());
   RPB_LAUNCH_CHECK();
   return 0;
 }

@@ -37,18 +37,29 @@ __device__ __forceinline__ void il_st(unsigned long long* p, unsigned long long 
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// 30-bit descriptor tag of a 64-bit call counter: never 0 (fresh, zeroed state reads "not ready"); a stale descriptor could
+// only alias after 2^30 - 1 further calls that all left it untouched
+__device__ __forceinline__ unsigned long long il_tag(unsigned long long epoch)
+{ return (epoch % 0x3fffffffull + 1ull) << 34; }
+
 __global__ void __launch_bounds__(IL_BLOCK)
 indexlist_kernel(const double* __restrict__ x, int* __restrict__ list, int64_t n, long long* __restrict__ d_len,
                  unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket,
-                 unsigned long long epoch, unsigned int num_tiles, int vector_ok)
+                 unsigned long long* d_epoch, unsigned int num_tiles, int vector_ok)
 {
   __shared__ int s_out[IL_TILE];
   __shared__ unsigned int s_warp[IL_BLOCK / 32];
   __shared__ unsigned int s_prefix;
   __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_epoch;
 
+  // this call's epoch = 1 + the last completed call's, in DEVICE memory (committed by the last CTA to retire): a captured
+  // launch replays with a fresh tag; read once per CTA before the first barrier, so every read happens-before the commit
+  if (threadIdx.x == 0) s_epoch = *(volatile unsigned long long*)d_epoch + 1ull;
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned long long tag = (epoch & 0x3fffffffull) << 34;
+  const unsigned long long tag = il_tag(epoch);
 
   for (;;) {
     if (threadIdx.x == 0) s_tile = atomicAdd(&ticket[0], 1u);
@@ -57,7 +68,7 @@ indexlist_kernel(const double* __restrict__ x, int* __restrict__ list, int64_t n
     if (tile >= num_tiles) {
       if (threadIdx.x == 0) {       // the last CTA to draw a terminating ticket re-arms the counters
         const unsigned int gone = atomicAdd(&ticket[1], 1u);
-        if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; }
+        if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; *d_epoch = epoch; }
       }
       break;
     }
@@ -148,29 +159,24 @@ indexlist_kernel(const double* __restrict__ x, int* __restrict__ list, int64_t n
   }
 }
 
-int il_grow_state(rpb200_ctx* ctx, size_t need, cudaStream_t st)
-{
-  if (need <= ctx->ilist_state_bytes) return 0;
-  RPB_CHECK(cudaStreamSynchronize(st));
-  if (ctx->d_ilist_state) RPB_CHECK(cudaFree(ctx->d_ilist_state));
-  ctx->d_ilist_state = nullptr; ctx->ilist_state_bytes = 0;
-  const size_t cap = need + need / 2 + 4096;
-  RPB_CHECK(cudaMalloc(&ctx->d_ilist_state, cap));
-  RPB_CHECK(cudaMemset(ctx->d_ilist_state, 0, cap));     // epoch 0 is never used: fresh words read "not ready"
-  ctx->ilist_state_bytes = cap;
-  ctx->ilist_epoch = 0;
-  return 0;
-}
-
 }  // namespace
 
 int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n, long long* d_len, unsigned long long* d_desc,
-                          size_t desc_bytes, unsigned int* d_ticket, unsigned long long tag, cudaStream_t st, int* handled);   // indexlist_tma.cu
+                          size_t desc_bytes, unsigned int* d_ticket, unsigned long long* d_epoch, cudaStream_t st, int* handled);   // indexlist_tma.cu
 
 extern "C" int rpb200_indexlist_reserve(rpb200_ctx* ctx, int64_t n)
 {
   if (!ctx || n < 0) return RPB200_EINVAL;
-  return il_grow_state(ctx, IL_DESC_BYTES * (size_t)((n + IL_TILE - 1) / IL_TILE + 1), nullptr);
+  RPB_CHECK_DEVICE(ctx);
+  const size_t need = IL_DESC_BYTES * (size_t)((n + IL_TILE - 1) / IL_TILE + 1);
+  if (need > ctx->ilist_reserve_bytes) ctx->ilist_reserve_bytes = need;
+  for (int i = 0; i < RPB_MAX_STREAMS; ++i) {      // every existing scratch set; later ones: rpb200_stream_attach / first use
+    rpb_scratch* sc = &ctx->slot[i];
+    if (!sc->d_fixed) continue;
+    const int rc = rpb_grow_state(&sc->d_ilist_state, &sc->ilist_state_bytes, ctx->ilist_reserve_bytes, sc->attached ? sc->stream : nullptr);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 extern "C" int rpb200_indexlist(rpb200_ctx* ctx, const double* x, int* list, int64_t n, int64_t* d_len,
@@ -179,28 +185,29 @@ extern "C" int rpb200_indexlist(rpb200_ctx* ctx, const double* x, int* list, int
   if (!ctx || n < 0 || !d_len || (n > 0 && (!x || !list))) return RPB200_EINVAL;
   if (n > 0x7fffffffll) return RPB200_EINVAL;          // Int_type index list (RPTypes.hpp:81)
   cudaStream_t st = rpb_stream(s);
+  RPB_SCRATCH(sc, ctx, st);
   if (n == 0) { RPB_CHECK(cudaMemsetAsync(d_len, 0, sizeof(int64_t), st)); return 0; }
   const unsigned int tiles = (unsigned int)((n + IL_TILE - 1) / IL_TILE);
-  { const int rc = il_grow_state(ctx, IL_DESC_BYTES * ((size_t)tiles + 1), st); if (rc != 0) return rc; }
-  if (++ctx->ilist_epoch >= 0x3fffffffu) {             // 30-bit tag about to wrap: start over from clean state
-    RPB_CHECK(cudaMemsetAsync(ctx->d_ilist_state, 0, ctx->ilist_state_bytes, st));
-    ctx->ilist_epoch = 1;
+  {
+    size_t need = IL_DESC_BYTES * ((size_t)tiles + 1);
+    if (need < ctx->ilist_reserve_bytes) need = ctx->ilist_reserve_bytes;
+    const int rc = rpb_grow_state(&sc->d_ilist_state, &sc->ilist_state_bytes, need, st);
+    if (rc != 0) return rc;
   }
+  unsigned long long* d_epoch = sc->d_epoch + 1;
   static_assert(sizeof(long long) == sizeof(int64_t), "Index_type");
   {   // large, aligned problems: the TMA-staged warp-specialised kernel (separate ticket pair: [6], [7])
     int handled = 0;
-    const int rc = rpb_indexlist_tma_try(ctx, x, list, n, (long long*)d_len, (unsigned long long*)ctx->d_ilist_state,
-                                         ctx->ilist_state_bytes, ctx->d_scan_ticket + 6,
-                                         ((unsigned long long)ctx->ilist_epoch & 0x3fffffffull) << 34, st, &handled);
+    const int rc = rpb_indexlist_tma_try(ctx, x, list, n, (long long*)d_len, (unsigned long long*)sc->d_ilist_state,
+                                         sc->ilist_state_bytes, sc->d_scan_ticket + 6, d_epoch, st, &handled);
     if (rc != 0) return rc;
     if (handled) return 0;
   }
   const int cps = ctx->tune[RPB_K_INDEXLIST].ctas_per_sm > 0 ? ctx->tune[RPB_K_INDEXLIST].ctas_per_sm : 2;
   int grid = ctx->sm_count * cps;
   if ((unsigned int)grid > tiles) grid = (int)tiles;
-  indexlist_kernel<<<grid, IL_BLOCK, 0, st>>>(x, list, n, (long long*)d_len, (unsigned long long*)ctx->d_ilist_state,
-                                              ctx->d_scan_ticket + 4, (unsigned long long)ctx->ilist_epoch, tiles,
-                                              rpb_aligned(x, 32) ? 1 : 0);
+  indexlist_kernel<<<grid, IL_BLOCK, 0, st>>>(x, list, n, (long long*)d_len, (unsigned long long*)sc->d_ilist_state,
+                                              sc->d_scan_ticket + 4, d_epoch, tiles, rpb_aligned(x, 32) ? 1 : 0);
   RPB_LAUNCH_CHECK();
   return 0;
 }

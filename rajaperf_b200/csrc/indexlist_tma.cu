@@ -55,6 +55,7 @@ struct il_smem {
   unsigned int tile_id[IT_STAGES];
   unsigned int lb_tile[IT_SLOTS];                           // tile of the sequence number a look-back warp is handed
   unsigned int arrived[IT_SLOTS];
+  unsigned long long epoch;                                 // this call's epoch, read once per CTA
 };
 
 // IT_LBW = descriptors per lane per look-back round; dstride = distance between descriptors in 8-byte words
@@ -62,12 +63,17 @@ struct il_smem {
 template <int IT_LBW>
 __global__ void __launch_bounds__(IT_THREADS, 1)
 indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict__ list, long long rows,
-                     unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long tag,
+                     unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long* d_epoch,
                      unsigned int num_tiles, int dstride, unsigned int backoff_ns, int num_lb, int evict_first)
 {
   extern __shared__ unsigned char smem_raw[];
   il_smem& S = *reinterpret_cast<il_smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // this call's epoch = 1 + the last COMPLETED call's, kept in device memory and committed by the last producer to retire
+  // (a captured launch replays with a fresh tag).  Thread 0 reads it before the barrier below and broadcasts it through
+  // shared memory: no producer draws a ticket before every warp of its CTA can see S.epoch, so every read of *d_epoch
+  // happens-before the commit.
+  if (threadIdx.x == 0) S.epoch = *(volatile unsigned long long*)d_epoch + 1ull;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < IT_STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], IT_WARPS); }
@@ -76,6 +82,8 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  const unsigned long long epoch = S.epoch;
+  const unsigned long long tag = (epoch % 0x3fffffffull + 1ull) << 34;      // 30-bit tag, never 0 (indexlist.cu: il_tag)
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer (one lane)
@@ -105,7 +113,7 @@ indexlist_tma_kernel(const __grid_constant__ CUtensorMap x_map, int* __restrict_
         }
       }
       const unsigned int gone = atomicAdd(&ticket[1], 1u);     // the last CTA to retire re-arms the ticket
-      if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; }
+      if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; *d_epoch = epoch; }
     }
     return;
   }
@@ -273,7 +281,7 @@ __global__ void indexlist_tail_kernel(const double* __restrict__ x, int* __restr
 
 // handled = 1 if the call was served here, 0 if the caller should use the register-staged kernel
 int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n, long long* d_len, unsigned long long* d_desc,
-                          size_t desc_bytes, unsigned int* d_ticket, unsigned long long tag, cudaStream_t st, int* handled)
+                          size_t desc_bytes, unsigned int* d_ticket, unsigned long long* d_epoch, cudaStream_t st, int* handled)
 {
   *handled = 0;
   static int disabled = -1;
@@ -305,9 +313,9 @@ int rpb_indexlist_tma_try(rpb200_ctx* ctx, const double* x, int* list, int64_t n
   else RPB_CHECK(cudaFuncSetAttribute(indexlist_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = ctx->sm_count;
   if (grid > tiles) grid = (int)tiles;
-  if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
-  else if (lbw == 2) indexlist_tma_kernel<2><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
-  else indexlist_tma_kernel<1><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, tag, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
+  if (lbw == 4) indexlist_tma_kernel<4><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, d_epoch, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
+  else if (lbw == 2) indexlist_tma_kernel<2><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, d_epoch, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
+  else indexlist_tma_kernel<1><<<grid, IT_THREADS, smem, st>>>(map, list, (long long)rows, d_desc, d_ticket, d_epoch, (unsigned int)tiles, ds, (unsigned int)backoff, nlb, rpb_tma::tma_evict_first());
   RPB_LAUNCH_CHECK();
   indexlist_tail_kernel<<<1, 32, 0, st>>>(x, list, (long long)rows * IT_IPT, (int)(n - rows * IT_IPT), d_desc + (tiles - 1) * ds, d_len);
   RPB_LAUNCH_CHECK();

@@ -281,6 +281,7 @@ extern "C" int rpb200_ltimes(rpb200_ctx* ctx, double* phi, const double* ell, co
                              rpb200_stream_t s)
 {
   if (!ctx || num_d <= 0 || num_g <= 0 || num_m <= 0 || num_z < 0) return RPB200_EINVAL;
+  RPB_CHECK_DEVICE(ctx);
   if (num_z == 0) return 0;
   if (!phi || !ell || !psi) return RPB200_EINVAL;
   cudaStream_t st = rpb_stream(s);

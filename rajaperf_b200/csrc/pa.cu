@@ -17,6 +17,9 @@
 // live in __constant__ memory (refreshed per call by a stream-ordered device-to-device copy), so
 // each FMA takes its basis operand from the constant bank instead of a shared-memory load.
 // The kernels are HBM-bound by design: algorithmic traffic only (X, D read once, Y read+written).
+// The __constant__ tables are module-level state, one set per DEVICE: calls on one stream are ordered by the stream, and a
+// call that arrives on another stream than the device's previous PA call is ordered behind it with an event (pa_order
+// below), so PA calls on different streams of one device are safe -- they serialise instead of racing on the tables.
 //
 // Memory pipeline: all three kernels are PERSISTENT and stage their element tensors with bulk-async
 // copies (cp.async.bulk + mbarrier, the TMA engine: no registers, no LSU queue) into a shared-memory
@@ -768,18 +771,55 @@ cudaError_t launch_mass(const rpb200_ctx* ctx, const double* D, const double* X,
 
 }  // namespace
 
+// ---- one set of __constant__ tables per device: order a call behind the previous PA call on another stream ------------
+namespace {
+struct pa_device_state { cudaStream_t last; cudaEvent_t done; int have_event; int recorded; };
+pa_device_state g_pa[64];
+volatile int g_pa_lock = 0;
+struct pa_lock { pa_lock() { while (__sync_lock_test_and_set(&g_pa_lock, 1)) { } } ~pa_lock() { __sync_lock_release(&g_pa_lock); } };
+
+bool pa_capturing(cudaStream_t st)
+{
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  return st != nullptr && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+}
+// before the tables are refreshed on `st`
+int pa_order_begin(const rpb200_ctx* ctx, cudaStream_t st)
+{
+  if (ctx->device < 0 || ctx->device >= 64 || pa_capturing(st)) return 0;   // captured calls: ordered by the graph's author
+  pa_lock guard;
+  pa_device_state& P = g_pa[ctx->device];
+  if (P.recorded && P.last != st) RPB_CHECK(cudaStreamWaitEvent(st, P.done, 0));
+  return 0;
+}
+// after the kernel that reads the tables has been enqueued on `st`
+int pa_order_end(const rpb200_ctx* ctx, cudaStream_t st)
+{
+  if (ctx->device < 0 || ctx->device >= 64 || pa_capturing(st)) return 0;
+  pa_lock guard;
+  pa_device_state& P = g_pa[ctx->device];
+  if (!P.have_event) { RPB_CHECK(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming)); P.have_event = 1; }
+  RPB_CHECK(cudaEventRecord(P.done, st));
+  P.last = st;
+  P.recorded = 1;
+  return 0;
+}
+}  // namespace
+
 extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* Bt, const double* D,
                                const double* X, double* Y, int64_t NE, rpb200_stream_t s)
 {
   if (!ctx || NE < 0 || (NE > 0 && (!B || !Bt || !D || !X || !Y))) return RPB200_EINVAL;
   if (NE == 0) return 0;
   if (!rpb_aligned(X, 32) || !rpb_aligned(Y, 32)) return RPB200_EINVAL;   // 512-byte elements
-  cudaStream_t st = rpb_stream(s);
-  mass_tables_kernel<<<1, 32, 0, st>>>(B, Bt, ctx->d_basis_tables);
-  RPB_LAUNCH_CHECK();
-  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, ctx->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
-  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, ctx->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16)) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  RPB_SCRATCH(sc, ctx, st);
+  mass_tables_kernel<<<1, 32, 0, st>>>(B, Bt, sc->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  { const int rc_ = pa_order_begin(ctx, st); if (rc_ != 0) return rc_; }
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_B, sc->d_basis_tables, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_mass_Bt, sc->d_basis_tables + 20, 20 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   // elements per CTA / threads / CTAs per SM / D stages: 8/32/11/1 with line-major accesses is the best of the sweeps in
   // profiles/r01_pa_variants.md
   switch (ctx->tune[RPB_K_MASS3DPA].unroll) {
@@ -826,7 +866,7 @@ extern "C" int rpb200_mass3dpa(rpb200_ctx* ctx, const double* B, const double* B
       break;
   }
   RPB_LAUNCH_CHECK();
-  return 0;
+  return pa_order_end(ctx, st);
 }
 
 extern "C" int rpb200_convection3dpa(rpb200_ctx* ctx, const double* Basis, const double* tBasis,
@@ -835,11 +875,13 @@ extern "C" int rpb200_convection3dpa(rpb200_ctx* ctx, const double* Basis, const
 {
   if (!ctx || NE < 0 || (NE > 0 && (!Basis || !tBasis || !dBasis || !D || !X || !Y))) return RPB200_EINVAL;
   if (NE == 0) return 0;
-  cudaStream_t st = rpb_stream(s);
-  conv_tables_kernel<<<1, 32, 0, st>>>(Basis, tBasis, dBasis, ctx->d_basis_tables);
-  RPB_LAUNCH_CHECK();
-  RPB_CHECK(cudaMemcpyToSymbolAsync(c_conv, ctx->d_basis_tables, 36 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16) || !rpb_aligned(X, 16) || !rpb_aligned(Y, 16)) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  RPB_SCRATCH(sc, ctx, st);
+  conv_tables_kernel<<<1, 32, 0, st>>>(Basis, tBasis, dBasis, sc->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  { const int rc_ = pa_order_begin(ctx, st); if (rc_ != 0) return rc_; }
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_conv, sc->d_basis_tables, 36 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   // tuning field `unroll` selects the launch shape {elements per CTA, threads, ring stages, CTAs per SM}
   // (sweep: profiles/r01_pa_variants.md)
 #define RPB_CONV(E, B, S, M) RPB_CHECK((launch_ring_kernel<E, B, S, M, 192>(convection3dpa_kernel<E, B, S, M>, ctx, D, X, Y, NE, st)))
@@ -856,7 +898,7 @@ extern "C" int rpb200_convection3dpa(rpb200_ctx* ctx, const double* Basis, const
   }
 #undef RPB_CONV
   RPB_LAUNCH_CHECK();
-  return 0;
+  return pa_order_end(ctx, st);
 }
 
 extern "C" int rpb200_diffusion3dpa(rpb200_ctx* ctx, const double* Basis, const double* dBasis,
@@ -865,15 +907,17 @@ extern "C" int rpb200_diffusion3dpa(rpb200_ctx* ctx, const double* Basis, const 
 {
   if (!ctx || NE < 0 || (NE > 0 && (!Basis || !dBasis || !D || !X || !Y))) return RPB200_EINVAL;
   if (NE == 0) return 0;
-  cudaStream_t st = rpb_stream(s);
-  diffusion_tables_kernel<<<1, 32, 0, st>>>(Basis, dBasis, ctx->d_basis_tables);
-  RPB_LAUNCH_CHECK();
-  RPB_CHECK(cudaMemcpyToSymbolAsync(c_diff, ctx->d_basis_tables, 48 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (!rpb_aligned(D, 16) || !rpb_aligned(X, 16) || !rpb_aligned(Y, 16)) return RPB200_EINVAL;
+  cudaStream_t st = rpb_stream(s);
+  RPB_SCRATCH(sc, ctx, st);
+  diffusion_tables_kernel<<<1, 32, 0, st>>>(Basis, dBasis, sc->d_basis_tables);
+  RPB_LAUNCH_CHECK();
+  { const int rc_ = pa_order_begin(ctx, st); if (rc_ != 0) return rc_; }
+  RPB_CHECK(cudaMemcpyToSymbolAsync(c_diff, sc->d_basis_tables, 48 * sizeof(double), 0, cudaMemcpyDeviceToDevice, st));
   if (symmetric)
     RPB_CHECK((launch_ring_kernel<8, 128, 2, 3, 384>(diffusion3dpa_kernel<8, 128, 2, 3, true>, ctx, D, X, Y, NE, st)));
   else
     RPB_CHECK((launch_ring_kernel<8, 128, 2, 3, 384>(diffusion3dpa_kernel<8, 128, 2, 3, false>, ctx, D, X, Y, NE, st)));
   RPB_LAUNCH_CHECK();
-  return 0;
+  return pa_order_end(ctx, st);
 }

@@ -37,8 +37,16 @@ template <int VPT>   // vectors (of 4 doubles) per thread
 __global__ void __launch_bounds__(512)
 scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
             tile_desc* __restrict__ desc, unsigned int* __restrict__ ticket,
-            unsigned long long epoch, unsigned int num_tiles, int vector_ok, int dstride)
+            unsigned long long* d_epoch, unsigned int num_tiles, int vector_ok, int dstride)
 {
+  // the epoch of this call = 1 + the epoch of the last completed call, kept in DEVICE memory and committed by the last
+  // CTA to retire: a captured launch replays with a fresh epoch every time (no host-side counter frozen into the graph)
+  // (read by ONE thread before the first barrier and broadcast through shared memory, so that every read of the epoch
+  // happens-before any CTA's terminating ticket, hence before the commit)
+  __shared__ unsigned long long s_epoch;
+  if (threadIdx.x == 0) s_epoch = *(volatile unsigned long long*)d_epoch + 1ull;
+  __syncthreads();
+  const unsigned long long epoch = s_epoch;
   // dstride: distance between tile descriptors in 16-byte units (see scan_tma.cu)
   constexpr int IPT = VPT * 4;
   __shared__ double s_warp[32];
@@ -57,7 +65,7 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
       // for the next call (no CTA can draw again after that)
       if (threadIdx.x == 0) {
         const unsigned int gone = atomicAdd(&ticket[1], 1u);
-        if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; }
+        if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; *d_epoch = epoch; }
       }
       break;
     }
@@ -150,29 +158,24 @@ scan_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
 }  // namespace
 
 int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, void* d_desc, size_t desc_bytes,
-                     unsigned int* d_ticket, unsigned long long epoch, cudaStream_t st, int* handled);   // scan_tma.cu
-
-static int scan_grow_state(rpb200_ctx* ctx, size_t need, cudaStream_t st)
-{
-  if (need <= ctx->scan_state_bytes) return 0;
-  // grows only; fresh memory is zeroed once so no stale word can alias a live epoch
-  RPB_CHECK(cudaStreamSynchronize(st));
-  if (ctx->d_scan_state) RPB_CHECK(cudaFree(ctx->d_scan_state));
-  ctx->d_scan_state = nullptr; ctx->scan_state_bytes = 0;
-  size_t cap = need + need / 2 + 4096;
-  RPB_CHECK(cudaMalloc(&ctx->d_scan_state, cap));
-  RPB_CHECK(cudaMemset(ctx->d_scan_state, 0, cap));
-  ctx->scan_state_bytes = cap;
-  ctx->scan_epoch = 0;
-  return 0;
-}
+                     unsigned int* d_ticket, unsigned long long* d_epoch, cudaStream_t st, int* handled);   // scan_tma.cu
 
 extern "C" int rpb200_scan_reserve(rpb200_ctx* ctx, int64_t n)
 {
   if (!ctx || n < 0) return RPB200_EINVAL;
+  RPB_CHECK_DEVICE(ctx);
   // the smallest tile any tuning can select (32 threads x 4 doubles) bounds the tile count
   const size_t tiles = (size_t)((n + 127) / 128);
-  return scan_grow_state(ctx, 2 * sizeof(tile_desc) * tiles, nullptr);
+  const size_t need = 2 * sizeof(tile_desc) * tiles;
+  if (need > ctx->scan_reserve_bytes) ctx->scan_reserve_bytes = need;
+  // every scratch set that exists is grown now; sets attached later are sized by rpb200_stream_attach / on first use
+  for (int i = 0; i < RPB_MAX_STREAMS; ++i) {
+    rpb_scratch* sc = &ctx->slot[i];
+    if (!sc->d_fixed) continue;
+    const int rc = rpb_grow_state(&sc->d_scan_state, &sc->scan_state_bytes, ctx->scan_reserve_bytes, sc->attached ? sc->stream : nullptr);
+    if (rc != 0) return rc;
+  }
+  return 0;
 }
 
 extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y, int64_t n,
@@ -181,6 +184,7 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   if (!ctx || n < 0 || (n > 0 && (!x || !y))) return RPB200_EINVAL;
   if (n == 0) return 0;
   cudaStream_t st = rpb_stream(s);
+  RPB_SCRATCH(sc, ctx, st);
   rpb_tuning t = ctx->tune[RPB_K_SCAN];
   if (t.block_size > 512) t.block_size = 512;
   if (t.block_size < 32) t.block_size = 32;
@@ -194,27 +198,28 @@ extern "C" int rpb200_scan_exclusive(rpb200_ctx* ctx, const double* x, double* y
   // the TMA path spreads its descriptors one per 128-byte line (8192-element tiles)
   size_t need = 2 * sizeof(tile_desc) * (size_t)tiles;        // descriptors one per 32-byte sector
   { const size_t spread = 128 * (size_t)((n + 8191) / 8192 + 1); if (spread > need) need = spread; }
-  { const int rc = scan_grow_state(ctx, need, st); if (rc != 0) return rc; }
-  const unsigned long long epoch = ++ctx->scan_epoch;
+  if (need < ctx->scan_reserve_bytes) need = ctx->scan_reserve_bytes;
+  { const int rc = rpb_grow_state(&sc->d_scan_state, &sc->scan_state_bytes, need, st); if (rc != 0) return rc; }
+  unsigned long long* d_epoch = sc->d_epoch + 0;
 
   // large, aligned problems: the TMA-staged warp-specialised kernel (separate ticket pair: [2], [3])
   {
     int handled = 0;
-    const int rc = rpb_scan_tma_try(ctx, x, y, n, ctx->d_scan_state, ctx->scan_state_bytes, ctx->d_scan_ticket + 2, epoch, st, &handled);
+    const int rc = rpb_scan_tma_try(ctx, x, y, n, sc->d_scan_state, sc->scan_state_bytes, sc->d_scan_ticket + 2, d_epoch, st, &handled);
     if (rc != 0) return rc;
     if (handled) return 0;
   }
 
   int grid = ctx->sm_count * (t.ctas_per_sm > 0 ? t.ctas_per_sm : 4);
   if ((unsigned int)grid > tiles) grid = (int)tiles;
-  tile_desc* desc = (tile_desc*)ctx->d_scan_state;
+  tile_desc* desc = (tile_desc*)sc->d_scan_state;
   const int vok = aligned ? 1 : 0;   // unaligned sub-ranges take the bounds-checked scalar path
   int ds = 2;                        // one descriptor per 32-byte sector when the state allows it
-  while (ds > 1 && sizeof(tile_desc) * (size_t)tiles * ds > ctx->scan_state_bytes) ds >>= 1;
+  while (ds > 1 && sizeof(tile_desc) * (size_t)tiles * ds > sc->scan_state_bytes) ds >>= 1;
   switch (vpt) {
-    case 4: scan_kernel<4><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
-    case 2: scan_kernel<2><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
-    default: scan_kernel<1><<<grid, t.block_size, 0, st>>>(x, y, n, desc, ctx->d_scan_ticket, epoch, tiles, vok, ds); break;
+    case 4: scan_kernel<4><<<grid, t.block_size, 0, st>>>(x, y, n, desc, sc->d_scan_ticket, d_epoch, tiles, vok, ds); break;
+    case 2: scan_kernel<2><<<grid, t.block_size, 0, st>>>(x, y, n, desc, sc->d_scan_ticket, d_epoch, tiles, vok, ds); break;
+    default: scan_kernel<1><<<grid, t.block_size, 0, st>>>(x, y, n, desc, sc->d_scan_ticket, d_epoch, tiles, vok, ds); break;
   }
   RPB_LAUNCH_CHECK();
   return 0;

@@ -57,44 +57,22 @@ struct scan_smem {
   double woff[2][ST_WARPS];                               // exclusive prefix of every warp's segment
   unsigned int tile_id[ST_STAGES];
   unsigned int arrived[2];                                // compute warps done with A(k): the last one publishes
+  unsigned long long epoch;                               // this call's epoch (*d_epoch + 1), read once per CTA
 };
 
-// 4 x 4 transpose of 32-byte pieces inside every aligned group of four lanes: on entry lane 4G + r holds the four pieces
-// m[0..3] of row r; on exit lane 4G + q holds piece q of the rows 0..3 of its group (m[j] = piece q of row j).  Two
-// butterfly stages (lane ^ 1 on piece bit 0, lane ^ 2 on piece bit 1), 16 32-bit shuffles each.
-__device__ __forceinline__ void exchange_piece(dbl4& keep_if_set, dbl4& keep_if_clear, bool set, int mask)
-{
-  // every lane sends the piece it does not keep and receives its partner's piece into that slot
-  const double sx = set ? keep_if_clear.x : keep_if_set.x, sy = set ? keep_if_clear.y : keep_if_set.y;
-  const double sz = set ? keep_if_clear.z : keep_if_set.z, sw = set ? keep_if_clear.w : keep_if_set.w;
-  const double rx = __shfl_xor_sync(0xffffffffu, sx, mask), ry = __shfl_xor_sync(0xffffffffu, sy, mask);
-  const double rz = __shfl_xor_sync(0xffffffffu, sz, mask), rw = __shfl_xor_sync(0xffffffffu, sw, mask);
-  keep_if_clear.x = set ? rx : keep_if_clear.x; keep_if_clear.y = set ? ry : keep_if_clear.y;
-  keep_if_clear.z = set ? rz : keep_if_clear.z; keep_if_clear.w = set ? rw : keep_if_clear.w;
-  keep_if_set.x = set ? keep_if_set.x : rx; keep_if_set.y = set ? keep_if_set.y : ry;
-  keep_if_set.z = set ? keep_if_set.z : rz; keep_if_set.w = set ? keep_if_set.w : rw;
-}
-__device__ __forceinline__ void transpose4_pieces(dbl4 (&m)[4], int lane)
-{
-  const bool b0 = lane & 1, b1 = lane & 2;
-  // lane ^ 1 on piece bit 0: an odd lane keeps the odd slots (m[1], m[3]) and receives into the even ones, and vice versa
-  exchange_piece(m[1], m[0], b0, 1);
-  exchange_piece(m[3], m[2], b0, 1);
-  // lane ^ 2 on piece bit 1
-  exchange_piece(m[2], m[0], b1, 2);
-  exchange_piece(m[3], m[1], b1, 2);
-}
-
-// LINE_ST (opt-in, tuning `unroll` 9 of Algorithm_SCAN; written after the GPU budget of round 1 was spent: NOT YET MEASURED):
-// a thread owns one 128-byte row of y, so each of its four 256-bit stores puts ONE sector into a line of its own -- 32 lines
-// per warp instruction, the request pattern that cost MASS3DPA 10 % and LTIMES 3 % (profiles/r01_pa_variants.md).  With
-// LINE_ST every aligned group of four lanes transposes its 4 x 4 pieces first, so a warp instruction stores 8 whole lines.
-template <int LB, int BACKOFF, bool LINE_ST = false>
+// (A line-major variant of the result stores -- a 4 x 4 piece transpose inside every group of four lanes, then whole-line
+// stores -- was written in round 1 and first run in round 2: 6074 GB/s against 6210 for the row-per-thread stores below, and
+// its transpose was wrong (profiles/r02_a_optin.log).  Deleted: the 32 extra shuffles per tile cost more than the store
+// pattern gains once the loads come through TMA.)
+template <int LB, int BACKOFF>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ y, long long rows,
-                tile_desc* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long epoch,
+                tile_desc* __restrict__ desc, unsigned int* __restrict__ ticket, unsigned long long* d_epoch,
                 unsigned int num_tiles, unsigned long long* __restrict__ dbg, int dstride)
 {
+  // epoch of this call = 1 + the last COMPLETED call's, in device memory (committed below by the last CTA to retire), so a
+  // captured launch draws a fresh epoch at every replay
+  // (read by thread 0 before the first barrier, broadcast through shared memory: every read happens-before the commit)
   // dstride: distance between tile descriptors in 16-byte units (2 = one per 32-byte sector: the polls
   // of a look-back round spread over more L2 lines/slices; 5860 -> 6146 GB/s at 2^27, profiles/r01_widened.md)
   // dbg (optional, RPB200_SCAN_DEBUG=1): per CTA {tiles, clk waiting for TMA, clk waiting for agg_ready,
@@ -108,10 +86,12 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_STAGES; ++s) mbar_init(&S.full[s], 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&S.agg_ready[s], ST_WARPS); mbar_init(&S.prefix_ready[s], 1); S.arrived[s] = 0u; }
+    S.epoch = *(volatile unsigned long long*)d_epoch + 1ull;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
+  const unsigned long long epoch = S.epoch;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer + look-back warp
@@ -217,7 +197,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
     }
     if (lane == 0) {
       const unsigned int gone = atomicAdd(&ticket[1], 1u);
-      if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; }
+      if (gone == gridDim.x - 1) { ticket[0] = 0u; ticket[1] = 0u; *d_epoch = epoch; }
     }
     return;
   }
@@ -275,18 +255,7 @@ scan_tma_kernel(const __grid_constant__ CUtensorMap x_map, double* __restrict__ 
     mbar_wait(&S.prefix_ready[slot], (k >> 1) & 1);
     const double off = S.woff[slot][cw] + lane_excl;
     const long long grow = (long long)tile * ST_ROWS + row;
-    if constexpr (LINE_ST) {
-      dbl4 m[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) { m[q].x = off + v[4 * q]; m[q].y = off + v[4 * q + 1]; m[q].z = off + v[4 * q + 2]; m[q].w = off + v[4 * q + 3]; }
-      transpose4_pieces(m, lane);                            // every lane takes part, also for rows past the end
-      const int q = lane & 3;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {                          // piece q of row (group base + j)
-        const long long r = grow - q + j;
-        if (r < rows) stg256_stream(y + r * ST_IPT + 4 * q, m[j]);
-      }
-    } else if (grow < rows) {
+    if (grow < rows) {
       double* yp = y + grow * ST_IPT;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -315,7 +284,7 @@ __global__ void scan_tail_kernel(const double* __restrict__ x, double* __restric
 
 // Returns 1 if the call was handled here, 0 if the caller should use the register-staged kernel, < 0 / cudaError on failure.
 int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, void* d_desc, size_t desc_bytes,
-                     unsigned int* d_ticket, unsigned long long epoch, cudaStream_t st, int* handled)
+                     unsigned int* d_ticket, unsigned long long* d_epoch, cudaStream_t st, int* handled)
 {
   *handled = 0;
   static int disabled = -1;
@@ -353,14 +322,9 @@ int rpb_scan_tma_try(rpb200_ctx* ctx, const double* x, double* y, int64_t n, voi
     want_dbg = (e && atoi(e)) ? 1 : 0;
     if (want_dbg) { RPB_CHECK(cudaMalloc(&dbg, 8 * sizeof(unsigned long long) * 1024)); RPB_CHECK(cudaMemset(dbg, 0, 8 * 8 * 1024)); }
   }
-#define ST_LAUNCH(LB, BO, LS)                                                                                              \
-  do {                                                                                                                     \
-    RPB_CHECK(cudaFuncSetAttribute(scan_tma_kernel<LB, BO, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    scan_tma_kernel<LB, BO, LS><<<grid, ST_THREADS, smem, st>>>(map, y, (long long)rows, (tile_desc*)d_desc, d_ticket, epoch, \
-                                                               (unsigned int)tiles, dbg, ds);                                 \
-  } while (0)
-  if (ctx->tune[RPB_K_SCAN].unroll == 9) ST_LAUNCH(1, 0, true);      // opt-in: line-major stores (see the kernel's comment)
-  else ST_LAUNCH(1, 0, false);
+  RPB_CHECK(cudaFuncSetAttribute(scan_tma_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  scan_tma_kernel<1, 0><<<grid, ST_THREADS, smem, st>>>(map, y, (long long)rows, (tile_desc*)d_desc, d_ticket, d_epoch,
+                                                        (unsigned int)tiles, dbg, ds);
   RPB_LAUNCH_CHECK();
   if (want_dbg) {
     static int printed = 0;

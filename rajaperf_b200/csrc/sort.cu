@@ -11,6 +11,12 @@
 //     every pass reads and writes each key exactly once (16 B/key/pass, 32 B for pairs);
 //   * keys are first reordered by digit in shared memory, so the global scatter is made of
 //     contiguous runs;
+//   * UNIFORM TILES: a tile whose 8192 keys all carry the same digit in this pass (the suite's keys are rand()/RAND_MAX in
+//     [0, 1]: their top byte is 0x3f for 99.997 % of them, so ~78 % of the tiles of the last pass; any pass of clustered
+//     or already sorted data) needs no ranking at all -- its keys keep their order and move as one block to
+//     base[digit] + prefix.  A warp vote per round and one shared-memory word per warp detect it; the tile then skips the
+//     8-ballot match (45 % of a pass's instructions), the warp-count scan and the shared-memory reorder, and streams
+//     its keys out of the registers they were loaded into;
 //   * look-back descriptors carry a pass-parity code, so they are never cleared between passes or
 //     between calls of the same size; tiles are dealt by atomic ticket (no reliance on CTA order);
 //   * caller-provided scratch, no allocation, no host synchronisation; stable (pairs well-defined).
@@ -143,8 +149,9 @@ sort_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n,
   }
 }
 
-// ---- the same histograms with LANE-PRIVATE counters (opt-in: tuning `unroll` 9 of Algorithm_SORT / Algorithm_SORTPAIRS;
-// written after the GPU budget of round 1 was spent: NOT YET MEASURED, tools/time_quick.py sort_hist is its first A/B) ---------
+// ---- the same histograms with LANE-PRIVATE counters (the default since round 2: bit-exact at 2^27 / 1000003 / 4097 keys and
+// 7.818 ms against 7.863 ms for the whole keys sort at 2^27, profiles/r02_a_optin.log; tuning `unroll` 8 selects the
+// shared-bin kernel above) ---------
 // sort_hist_kernel is bound by its shared-memory atomics: 32 random bins per warp instruction fall on ~3.5 addresses of the
 // busiest bank (437 us for 2^27 keys against 165 us of DRAM time).  Here lane l of every warp counts in its own column: bin b
 // of digit d lives in the 16-bit half (b & 1) of word col[d][(b >> 1) * 32 + l], so the 32 atomics of a warp instruction hit
@@ -288,7 +295,6 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
                      unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket,
                      unsigned int num_tiles, unsigned int parity)
 {
-  using pos_t = typename std::conditional<PAIRS, unsigned short, int>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);            // [TILE]
   unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_keys + SORT_TILE);               // [WARPS][RADIX]
@@ -330,36 +336,63 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
     }
   }
 
-  // ---- rank inside the warp chunk (stable): match-any on the digit
-  unsigned short rank[SORT_IPT];
-  unsigned int* my_cnt = s_cnt + warp * RADIX;
+  // ---- uniform tile?  every key of the tile has the digit of the tile's first key (full tiles only: the padding of the
+  // last tile carries digit 0xff).  One vote per warp, one word per warp in shared memory, one barrier.
+  __shared__ unsigned int s_wdigit[SORT_WARPS];
+  {
+    const unsigned int d0 = __shfl_sync(0xffffffffu, key_digit(key[0], shift), 0);
+    bool same = full;
 #pragma unroll
-  for (int r = 0; r < SORT_IPT; ++r) {
-    const unsigned int d = key_digit(key[r], shift);
-    const unsigned int peers = match_digit(d);
-    const int leader = __ffs(peers) - 1;
-    unsigned int before = 0;
-    if (lane == leader) { before = my_cnt[d]; my_cnt[d] = before + __popc(peers); }
-    before = __shfl_sync(0xffffffffu, before, leader);
-    rank[r] = (unsigned short)(before + __popc(peers & lt_mask));
-    __syncwarp();
+    for (int r = 0; r < SORT_IPT; ++r) same = same && (key_digit(key[r], shift) == d0);
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) s_wdigit[warp] = same ? d0 : 0xffffffffu;
   }
   __syncthreads();
+  unsigned int udigit = s_wdigit[0];
+#pragma unroll
+  for (int w = 1; w < SORT_WARPS; ++w) udigit = (s_wdigit[w] == udigit) ? udigit : 0xffffffffu;
+  const bool uniform = udigit != 0xffffffffu;             // CTA-uniform
+
+  // ---- rank inside the warp chunk (stable): match-any on the digit.  Two 16-bit ranks per register.
+  unsigned int rank2[SORT_IPT / 2];
+  unsigned int* my_cnt = s_cnt + warp * RADIX;
+  if (!uniform) {
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+      const unsigned int d = key_digit(key[r], shift);
+      const unsigned int peers = match_digit(d);
+      const int leader = __ffs(peers) - 1;
+      unsigned int before = 0;
+      if (lane == leader) { before = my_cnt[d]; my_cnt[d] = before + __popc(peers); }
+      before = __shfl_sync(0xffffffffu, before, leader);
+      const unsigned int rk = before + __popc(peers & lt_mask);
+      rank2[r >> 1] = (r & 1) ? (rank2[r >> 1] | (rk << 16)) : rk;
+      __syncwarp();
+    }
+    __syncthreads();
+  }
 
   // ---- per digit: scan the warp counts, publish the tile count, look back
   unsigned int my_total = 0;
   if (threadIdx.x < RADIX) {
     const int b = threadIdx.x;
-    unsigned int run = 0;
+    if (uniform) {
+      my_total = ((unsigned int)b == udigit) ? (unsigned int)SORT_TILE : 0u;
+    } else {
+      unsigned int run = 0;
 #pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w) { const unsigned int c = s_cnt[w * RADIX + b]; s_cnt[w * RADIX + b] = run; run += c; }
-    my_total = run;
+      for (int w = 0; w < SORT_WARPS; ++w) { const unsigned int c = s_cnt[w * RADIX + b]; s_cnt[w * RADIX + b] = run; run += c; }
+      my_total = run;
+    }
     const unsigned long long code_agg = 2ull * parity, code_inc = 2ull * parity + 1ull;
     if (tile + 1 < num_tiles)     // nobody looks at the last tile
       st_desc(desc + (size_t)tile * RADIX + b, ((unsigned long long)my_total << 2) | (tile == 0 ? code_inc : code_agg));
   }
-  // tile-local exclusive scan of the 256 digit totals (positions in the reordered tile)
-  {
+  // tile-local exclusive scan of the 256 digit totals (positions in the reordered tile; a uniform tile is not reordered:
+  // every bin starts at 0, only the one digit is used)
+  if (uniform) {
+    if (threadIdx.x < RADIX) s_bin_start[threadIdx.x] = 0u;
+  } else {
     unsigned int inc = my_total;            // threads >= RADIX hold 0
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
@@ -391,14 +424,34 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   }
   __syncthreads();
 
-  // ---- reorder by digit in shared memory
-  pos_t pos[SORT_IPT];
+  if (uniform) {
+    // ---- the tile moves as one block, in order, straight from the registers it was loaded into
+    const long long delta = s_delta[udigit];
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+      const int p = chunk + r * 32;
+      keys_out[p + delta] = LAST ? key_decode(key[r]) : key[r];
+    }
+    if (PAIRS) {
+      unsigned long long v[SORT_IPT];
+#pragma unroll
+      for (int r = 0; r < SORT_IPT; ++r)
+        asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(v[r]) : "l"(vals_in + tile_base + chunk + r * 32));
+#pragma unroll
+      for (int r = 0; r < SORT_IPT; ++r) vals_out[chunk + r * 32 + delta] = v[r];
+    }
+    return;
+  }
+
+  // ---- reorder by digit in shared memory (positions: two 16-bit values per register)
+  unsigned int pos2[SORT_IPT / 2];
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
     const unsigned int d = key_digit(key[r], shift);
-    pos[r] = (pos_t)(s_bin_start[d] + my_cnt[d] + rank[r]);
-    s_keys[pos[r]] = key[r];
-    if (PAIRS) s_digit[pos[r]] = (unsigned char)d;
+    const unsigned int ps = s_bin_start[d] + my_cnt[d] + ((rank2[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
+    pos2[r >> 1] = (r & 1) ? (pos2[r >> 1] | (ps << 16)) : ps;
+    s_keys[ps] = key[r];
+    if (PAIRS) s_digit[ps] = (unsigned char)d;
   }
   // pairs: the values are requested only now, when the key registers are dead (the kernel stays at
   // 64 registers = 2 CTAs per SM); their latency hides behind the key write-out
@@ -428,7 +481,7 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   if (PAIRS) {
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) s_keys[pos[r]] = val[r];
+    for (int r = 0; r < SORT_IPT; ++r) s_keys[(pos2[r >> 1] >> ((r & 1) * 16)) & 0xffffu] = val[r];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
@@ -444,6 +497,7 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
 {
   if (!ctx || n < 0 || (n > 0 && (!keys || (PAIRS && !vals)))) return RPB200_EINVAL;
   if (n <= 1) return 0;
+  RPB_CHECK_DEVICE(ctx);
   const sort_scratch_layout L = make_layout(n, PAIRS ? 1 : 0);
   if (!scratch || scratch_bytes < L.total || !rpb_aligned(scratch, 256)) return RPB200_EINVAL;
   if (L.tiles > 0x7ffffff0ll) return RPB200_EINVAL;
@@ -466,7 +520,7 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
     int grid = ctx->sm_count * 4;
     int64_t need = (n + 511) / 512;
     if (need < grid) grid = (int)need;
-    if (ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll == 9) {          // opt-in: lane-private counters, one CTA per SM
+    if (ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll != 8) {          // default: lane-private counters, one CTA per SM (tuning `unroll` 8: shared bins)
       int g1 = ctx->sm_count;
       const int64_t need1 = (n + HL_BLOCK - 1) / HL_BLOCK;
       if (need1 < g1) g1 = (int)need1;

@@ -93,6 +93,7 @@ static int launch_ew(rpb200_ctx* ctx, int kid, double* out, const double* in0, c
 {
   if (!ctx || n < 0 || (n > 0 && (!out || !in0))) return RPB200_EINVAL;
   if (n == 0) return 0;
+  RPB_CHECK_DEVICE(ctx);
   cudaStream_t st = rpb_stream(s);
   constexpr bool two = (OP == OP_ADD || OP == OP_TRIAD);
   if (two && !in1) return RPB200_EINVAL;
@@ -289,8 +290,9 @@ static int launch_reduce(rpb200_ctx* ctx, int kid, const double* a, const double
 {
   if (!ctx || !d_out || n < 0 || (n > 0 && (!a || (NIN == 2 && !b)))) return RPB200_EINVAL;
   cudaStream_t st = rpb_stream(s);
-  unsigned int* ticket = ctx->d_ticket + (NIN == 2 ? 0 : 1);
-  double* partials = ctx->d_partials + (NIN == 2 ? 0 : RPB_MAX_PARTIALS);
+  RPB_SCRATCH(sc, ctx, st);                    // this stream's partials + ticket: concurrent streams never share them
+  unsigned int* ticket = sc->d_ticket + (NIN == 2 ? 0 : 1);
+  double* partials = sc->d_partials + (NIN == 2 ? 0 : RPB_MAX_PARTIALS);
   rpb_tuning t = ctx->tune[kid];
   if (!rpb_aligned(a, 32) || (NIN == 2 && !rpb_aligned(b, 32))) {
     int64_t blocks = (n + 255) / 256;

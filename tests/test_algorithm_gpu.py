@@ -131,6 +131,82 @@ def test_sort_negative_zero_denormal_inf_keys(ctx):
     assert np.all(sgn[:-1] >= sgn[1:])
 
 
+def _adversarial_keys(kind, n, rng):
+    """Key sets aimed at the parts of the onesweep pass: uniform tiles (every key of an 8192-key tile shares the pass's digit:
+    the tile skips ranking and moves as one block), tiles that are ALMOST uniform, and the look-back across runs of both."""
+    if kind == "all_equal":                      # every tile uniform in every pass
+        return np.full(n, 0.37)
+    if kind == "sorted":                         # high passes: long runs of uniform tiles with different digits
+        return np.sort(rng.random(n))
+    if kind == "reversed":
+        return np.sort(rng.random(n))[::-1].copy()
+    if kind == "suite_like":                     # rand()/RAND_MAX in [0, 1]: top byte 0x3f except for a handful of tiny keys
+        return rng.integers(0, 2**31 - 1, n).astype(np.float64) / 2147483647.0
+    if kind == "one_stranger_per_tile":          # uniform but for ONE key per tile, at varying positions
+        x = np.full(n, 0.5)
+        pos = np.arange(0, n, 8192) + (np.arange(0, (n + 8191) // 8192) * 977) % 8192
+        x[pos[pos < n]] = -3.0
+        return x
+    if kind == "two_values_blocks":              # alternating uniform tiles of two digits, block = one tile
+        return np.where((np.arange(n) // 8192) % 2 == 0, 1.0, 2.0**40)
+    if kind == "mixed_signs_runs":
+        x = rng.standard_normal(n)
+        x[: n // 3] = np.abs(x[: n // 3]); x[n // 3: 2 * n // 3] = -np.abs(x[n // 3: 2 * n // 3])
+        return x
+    raise KeyError(kind)
+
+
+ADVERSARIAL = ["all_equal", "sorted", "reversed", "suite_like", "one_stranger_per_tile", "two_values_blocks", "mixed_signs_runs"]
+
+
+@pytest.mark.parametrize("hist", ["lanes", "shared_bins"])
+@pytest.mark.parametrize("kind", ADVERSARIAL)
+@pytest.mark.parametrize("n", [8192, 8193, 3 * 8192, 1000003])
+def test_sort_keys_adversarial_sets_bit_exact(ctx, n, kind, hist):
+    rng = np.random.default_rng(n + len(kind))
+    x = _adversarial_keys(kind, n, rng)
+    ctx.set_tuning("Algorithm_SORT", unroll=8 if hist == "shared_bins" else 4)
+    try:
+        k = dev(x)
+        ctx.sort_keys(k, _scratch(ctx, n, False))
+        got = k.cpu().numpy()
+    finally:
+        ctx.reset_tuning("Algorithm_SORT")
+    ref = x.copy(); oracle.lib().orc_sort(ref, n)
+    assert np.array_equal(bits(got), bits(ref))
+
+
+@pytest.mark.parametrize("byte", range(8))
+def test_sort_keys_one_byte_varies(ctx, byte):
+    """Keys that differ in ONE byte only: seven passes see nothing but uniform tiles, one pass sees random digits."""
+    n = 5 * 8192 + 17
+    rng = np.random.default_rng(byte)
+    base = np.float64(1.2345678901234567).view(np.uint64)
+    b = rng.integers(0, 128 if byte == 7 else 256, n).astype(np.uint64)          # byte 7: keep the sign bit clear
+    keys = ((base & ~(np.uint64(0xff) << np.uint64(8 * byte))) | (b << np.uint64(8 * byte))).view(np.float64)
+    keys = keys[np.isfinite(keys)] if byte >= 6 else keys
+    keys = keys[~np.isnan(keys)]
+    n = keys.size
+    k = dev(keys)
+    ctx.sort_keys(k, _scratch(ctx, n, False))
+    ref = keys.copy(); oracle.lib().orc_sort(ref, n)
+    assert np.array_equal(bits(k.cpu().numpy()), bits(ref))
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "sorted", "suite_like", "one_stranger_per_tile", "two_values_blocks"])
+@pytest.mark.parametrize("n", [8192, 3 * 8192 + 5, 1000003])
+def test_sort_pairs_adversarial_sets_stable(ctx, n, kind):
+    """The uniform-tile path must keep the order of equal keys (the values are the original positions)."""
+    rng = np.random.default_rng(n)
+    keys = _adversarial_keys(kind, n, rng)
+    vals = np.arange(n, dtype=np.float64)
+    k, v = dev(keys), dev(vals)
+    ctx.sort_pairs(k, v, _scratch(ctx, n, True))
+    order = np.argsort(keys.view(np.int64) ^ ((keys.view(np.int64) >> 63) & 0x7fffffffffffffff), kind="stable")   # IEEE total order
+    assert np.array_equal(bits(k.cpu().numpy()), bits(keys[order]))
+    assert np.array_equal(v.cpu().numpy(), vals[order])
+
+
 @pytest.mark.parametrize("size,reps", [(0, 1), (0, 3), (1, 1), (1000, 2), (123457, 2)])
 def test_sort_suite_checksum_matches_reference_golden(ctx, size, reps):
     """SORT.cpp:56-61: one rand() stream of n*reps keys, rep r sorts segment r in place."""

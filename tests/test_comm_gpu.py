@@ -66,17 +66,41 @@ def test_grid_dims_follow_the_reference_truncation():
         assert cabi.halo_grid_dims(target) == d.tolist()
 
 
-def run_packing_fused(ctx, d, reps):
+FORMS = ["two_launches", "one_launch", "one_launch_x_first", "one_launch_generic"]
+
+
+def run_packing_fused(ctx, d, reps, form="two_launches"):
+    """form: the pack launch + the unpack launch; ONE launch over the merged item list (rpb200_halo_plan_pack_unpack), with
+    the x-face items mixed in or first; the same through the generic work-list API (what the reference-side stub calls)."""
     vars_ = [dev(v) for v in d["vars"]]
     pb = [dev(b) for b in d["pack_bufs"]]
     ub = [dev(b) for b in d["unpack_bufs"]]
     plan = ctx.halo_plan(d["dims"], d["hw"], d["nvars"])
     plan.bind(vars_, pb, ub)
-    for _ in range(reps):
-        plan.pack()
-        plan.unpack()
-    torch.cuda.synchronize()
+    wls = None
+    if form == "one_launch_generic":
+        nv = d["nvars"]
+        mk = lambda bufs, which: ctx.halo_worklist(
+            [(bufs[l].data_ptr() + 8 * v * plan.neighbors[l][which + "_len"], plan.neighbors[l]["d_" + which + "_list"],
+              vars_[v], plan.neighbors[l][which + "_len"], l) for l in range(26) for v in range(nv)])
+        wls = (mk(pb, "pack"), mk(ub, "unpack"))
+    if form == "one_launch_x_first":
+        ctx.set_tuning("Comm_HALO_PACKING_FUSED", unroll=3)
+    try:
+        for _ in range(reps):
+            if form == "two_launches":
+                plan.pack()
+                plan.unpack()
+            elif form == "one_launch_generic":
+                ctx.halo_pack_unpack(*wls)
+            else:
+                plan.pack_unpack()
+        torch.cuda.synchronize()
+    finally:
+        ctx.reset_tuning("Comm_HALO_PACKING_FUSED")
     out = [v.cpu().numpy() for v in vars_], [b.cpu().numpy() for b in pb]
+    if wls:
+        wls[0].close(); wls[1].close()
     plan.close()
     return out
 
@@ -98,20 +122,23 @@ def oracle_packing_fused(d, reps):
     return vars_, pb
 
 
+@pytest.mark.parametrize("form", ["two_launches", "one_launch"])
 @pytest.mark.parametrize("case", GOLD, ids=lambda c: f"s{c['size']}-r{c['reps']}-{'_'.join(c['flags'])}")
-def test_halo_packing_fused_checksum_matches_reference_golden(ctx, case):
+def test_halo_packing_fused_checksum_matches_reference_golden(ctx, case, form):
     f = dict(zip(case["flags"][0::2], case["flags"][1::2]))
     d = sd.halo_packing_fused(case["size"], int(f.get("--halo_width", 1)), int(f.get("--halo_num_vars", 3)))
-    vars_, pb = run_packing_fused(ctx, d, case["reps"])
+    vars_, pb = run_packing_fused(ctx, d, case["reps"], form)
     ck = sum(oracle.checksum(v) for v in vars_) + sum(oracle.checksum(b) for b in pb)
     ref = np.longdouble(case["checksum"])
     assert abs(ck - ref) <= abs(ref) * np.longdouble(4e-19), (ck, ref)
 
 
-@pytest.mark.parametrize("target,hw,nv", [(1, 1, 1), (27, 1, 2), (1000, 3, 1), (50000, 2, 4), (300000, 1, 3)])
-def test_halo_packing_fused_bit_exact_vs_oracle(ctx, target, hw, nv):
+@pytest.mark.parametrize("form", FORMS)
+@pytest.mark.parametrize("target,hw,nv", [(1, 1, 1), (27, 1, 2), (1000, 3, 1), (50000, 2, 4), (300000, 1, 3), (16000000, 1, 3)])
+def test_halo_packing_fused_bit_exact_vs_oracle(ctx, target, hw, nv, form):
+    """(16000000: a 252^3 grid -- the x faces are longer than one chunk, so the X groups of the item list exist)"""
     d = sd.halo_packing_fused(target, hw, nv)
-    vars_, pb = run_packing_fused(ctx, d, 2)
+    vars_, pb = run_packing_fused(ctx, d, 2, form)
     rv, rp = oracle_packing_fused(d, 2)
     for a, b in zip(vars_ + pb, rv + rp):
         assert np.array_equal(a.view(np.int64), b.view(np.int64))
@@ -368,10 +395,19 @@ def test_halo_exchange_fused_suite_checksum_single_rank(ctx, size, reps, hw, nv)
     plan.close()
 
 
-def test_halo_full_size_properties(ctx):
+@pytest.mark.parametrize("unroll", [2, 1], ids=["two_launches", "one_launch"])
+def test_halo_full_size_properties(ctx, unroll):
     """512^3 per GPU (BASELINE config 5): after one exchange every ghost cell equals the periodic
     image of an owned cell; a second exchange is idempotent; owned cells are never modified."""
     n, hw, nv = 512, 1, 3
+    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=unroll)
+    try:
+        _halo_full_size_properties(ctx, n, hw, nv)
+    finally:
+        ctx.reset_tuning("Comm_HALO_EXCHANGE_FUSED")
+
+
+def _halo_full_size_properties(ctx, n, hw, nv):
     plan = ctx.halo_plan((n, n, n), hw, nv)
     e = n + 2 * hw
     vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
@@ -391,4 +427,58 @@ def test_halo_full_size_properties(ctx):
     torch.cuda.synchronize()
     for a, b in zip(vs, before):
         assert torch.equal(a, b)
+    plan.close()
+
+
+@pytest.mark.parametrize("dims,hw,nv", [((6, 6, 6), 1, 3), ((20, 20, 20), 2, 2), ((64, 64, 64), 1, 3), ((252, 252, 252), 1, 3)])
+def test_halo_exchange_one_launch_form_bit_exact(ctx, dims, hw, nv):
+    """Tuning `unroll` 1 of Comm_HALO_EXCHANGE_FUSED: the whole rep is ONE launch over the item list (all pack items, signal,
+    wait + unpack items).  One rank per GPU only (every CTA of a rank must be resident while its peers pack), so on one GPU
+    this is the 1 x 1 x 1 rank grid: 26 self-messages, i.e. the periodic self-exchange of the oracle."""
+    reps = 3
+    plan = ctx.halo_plan(dims, hw, nv)
+    vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
+    plan.window(vs, want_handle=False)
+    plan.connect_ptrs([0])
+    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=1)
+    try:
+        for _ in range(reps):
+            plan.exchange()
+        torch.cuda.synchronize()
+    finally:
+        ctx.reset_tuning("Comm_HALO_EXCHANGE_FUSED")
+    plan.status()
+    ref = simulate_exchange(dims, hw, nv, (1, 1, 1), reps)
+    for v in range(nv):
+        assert np.array_equal(vs[v].cpu().numpy().view(np.int64), ref[0][v].view(np.int64)), v
+    plan.close()
+
+
+def test_halo_packing_fused_full_size_one_launch_equals_two_launches(ctx):
+    """512^3 per GPU, 3 variables (BASELINE config 5): the one-launch form leaves every variable and every pack buffer
+    bit-identical to the pack launch followed by the unpack launch; and the pack buffers hold var[list]."""
+    n, hw, nv = 512, 1, 3
+    plan = ctx.halo_plan((n, n, n), hw, nv)
+    f64 = dict(dtype=torch.float64, device="cuda")
+    results = []
+    for form in ("two", "one"):
+        vs = [torch.arange(plan.var_size, **f64) * 0.5 + v for v in range(nv)]
+        pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        ub = [torch.rand(nv * nb["unpack_len"], generator=gen, **f64) for nb in plan.neighbors]
+        plan.bind(vs, pb, ub)
+        for _ in range(2):
+            if form == "two":
+                plan.pack(); plan.unpack()
+            else:
+                plan.pack_unpack()
+        torch.cuda.synchronize()
+        results.append((vs, pb))
+    for a, b in zip(results[0][0] + results[0][1], results[1][0] + results[1][1]):
+        assert torch.equal(a, b)
+    vs, pb = results[1]
+    l = 1                                                       # the +x face: packed from owned cells i = n
+    lst = torch.from_numpy(dev_list(plan, l, "pack")).cuda().long()
+    for v in range(nv):
+        assert torch.equal(pb[l][v * lst.numel():(v + 1) * lst.numel()], vs[v][lst])
     plan.close()

@@ -1,34 +1,7 @@
-"""Index arithmetic of the two opt-in kernels that were written after round 1's GPU budget was spent (csrc/scan_tma.cu LINE_ST,
-csrc/sort.cu sort_hist_lanes_kernel), restated in numpy: not a test of the CUDA code, a test of the scheme it implements, so
-that the first GPU run (tools/time_quick.py scan_line sort_hist) only has to confirm the transcription."""
+"""Index arithmetic of the lane-private digit histogram (csrc/sort.cu sort_hist_lanes_kernel, the default since round 2)
+restated in numpy: not a test of the CUDA code (tests/test_algorithm_gpu.py runs that, both histogram kernels), a test of the
+counter-packing scheme and of the overflow bound its flush interval rests on."""
 import numpy as np
-
-
-def test_four_lane_piece_transpose_gives_every_lane_one_piece_of_four_rows():
-    """transpose4_pieces: lane 4G+r holds pieces 0..3 of row r; after two butterfly exchanges lane 4G+q holds piece q of
-    rows 0..3, so a warp store instruction j covers the whole 128-byte rows 4G+j."""
-    m = [[(lane, p) for p in range(4)] for lane in range(32)]          # m[lane][slot] = (row, piece)
-
-    def exchange(keep_if_set, keep_if_clear, bit, mask):
-        send = [m[l][keep_if_clear] if l & bit else m[l][keep_if_set] for l in range(32)]
-        for l in range(32):
-            if l & bit:
-                m[l][keep_if_clear] = send[l ^ mask]
-            else:
-                m[l][keep_if_set] = send[l ^ mask]
-
-    exchange(1, 0, 1, 1); exchange(3, 2, 1, 1)        # lane ^ 1 on piece bit 0
-    exchange(2, 0, 2, 2); exchange(3, 1, 2, 2)        # lane ^ 2 on piece bit 1
-    for lane in range(32):
-        for j in range(4):
-            assert m[lane][j] == ((lane & ~3) + j, lane & 3)
-    # the store of instruction j: lane writes 32 bytes at row*128 + piece*32 -> per instruction 8 whole 128-byte lines
-    for j in range(4):
-        lines = {}
-        for lane in range(32):
-            row, piece = m[lane][j]
-            lines.setdefault(row, set()).add(piece)
-        assert len(lines) == 8 and all(v == {0, 1, 2, 3} for v in lines.values())
 
 
 def test_lane_private_packed_counters_reproduce_the_digit_histograms():

@@ -81,39 +81,15 @@ if "ltimes" in which:
     ctx.set_tuning("Apps_LTIMES", -1, 2, 4)
     del phi, psi
 
-if "scan_line" in which:
-    # Algorithm_SCAN, TMA path: row-per-thread stores (default) against line-major stores after a 4-lane transpose (unroll 9;
-    # written after the GPU budget of round 1 was spent -- this section is its first measurement): parity, then A/B/A/B
-    n = 1 << 27
-    x = torch.rand(n, **f64); ya = torch.empty(n, **f64); yb = torch.empty(n, **f64)
-    ctx.set_tuning("Algorithm_SCAN", -1, -1, 4); ctx.scan_exclusive(x, ya)
-    ctx.set_tuning("Algorithm_SCAN", -1, -1, 9); ctx.scan_exclusive(x, yb)
-    ok = bool(torch.equal(ya, yb))
-    print(f"scan line-major stores parity n=2^27: {'OK' if ok else 'FAILED'}", flush=True)
-    res["scan line-major parity 2^27"] = ok
-    for m_ in (n - 12345, 148 * 2 * 8192 + 16 * 7 + 3):          # ragged last tile, tail elements
-        ctx.set_tuning("Algorithm_SCAN", -1, -1, 4); ya.fill_(-1.0); ctx.scan_exclusive(x[:m_], ya[:m_], n=m_)
-        ctx.set_tuning("Algorithm_SCAN", -1, -1, 9); yb.fill_(-1.0); ctx.scan_exclusive(x[:m_], yb[:m_], n=m_)
-        ok = bool(torch.equal(ya, yb))
-        print(f"scan line-major stores parity n={m_}: {'OK' if ok else 'FAILED'}", flush=True)
-        res[f"scan line-major parity {m_}"] = ok
-    for rnd in range(2):
-        for var, label in ((4, "row-per-thread stores (default)"), (9, "line-major stores")):
-            ctx.set_tuning("Algorithm_SCAN", -1, -1, var)
-            ms = time_ms(lambda: ctx.scan_exclusive(x, ya), 20)
-            report(f"scan {label} round {rnd}", 16 * n, ms)
-    ctx.reset_tuning("Algorithm_SCAN")
-    del x, ya, yb
-
 if "sort_hist" in which:
-    # SORT / SORTPAIRS with the lane-private histogram kernel (tuning unroll 9; written after the GPU budget of round 1 was
-    # spent -- this section is its first measurement) against the default histogram: parity of the sorted output, then A/B/A/B
+    # SORT / SORTPAIRS with the lane-private histogram kernel (the default since round 2) against the shared-bin histogram
+    # (tuning unroll 8): parity of the sorted output, then A/B/A/B.  First run: profiles/r02_a_optin.log.
     n = 1 << 27
     x = torch.randint(0, 2**31 - 1, (n,), device="cuda").to(torch.float64).div_(2147483647.0)      # rand()/RAND_MAX
     scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
     for m_ in (n, 1000003, 4097):
         outs = []
-        for var in (4, 9):
+        for var in (8, 4):
             ctx.set_tuning("Algorithm_SORT", -1, -1, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, -1, var)
             k = x[:m_].clone(); ctx.sort_keys(k, scratch, n=m_)
             kb, vb = torch.empty(m_ + 1, **f64), torch.empty(m_ + 1, **f64)
@@ -127,7 +103,7 @@ if "sort_hist" in which:
         del outs
     y = torch.empty_like(x)
     for rnd in range(2):
-        for var, label in ((4, "shared-bin histogram (default)"), (9, "lane-private histogram")):
+        for var, label in ((8, "shared-bin histogram"), (4, "lane-private histogram (default)")):
             ctx.set_tuning("Algorithm_SORT", -1, -1, var)
             ms = time_ms(lambda: ctx.sort_keys(y, scratch), 5, 2, setup=lambda: y.copy_(x))
             report(f"sort keys, {label} round {rnd}", 16 * n, ms, mkeys_per_s=n / ms / 1e3)
