@@ -934,8 +934,23 @@ static int launch_items(const rpb200_ctx* ctx, int kid, const halo_items_args& A
   return 0;
 }
 
-// The one-launch pack + unpack over two work lists; the item list is built on the first call for a (pack, unpack) pair and
-// cached on the pack list.
+// the merged item list of a (pack, unpack) pair, cached on the pack list; rebuilt when the pair or the order tuning changes
+static int ensure_merged(const rpb200_ctx* ctx, worklist_dev& pw, worklist_dev& uw)
+{
+  const int mix = ctx->tune[RPB_K_HALO_PACKING_FUSED].unroll == 3 ? 0 : 1;      // tuning `unroll` 3: X groups first instead of mixed in
+  if (pw.merged_with == (const void*)&uw && pw.merged_mix == mix) return 0;
+  std::vector<halo_item> items;
+  build_items_merged(pw, uw, mix != 0, items);
+  halo_item* d = (halo_item*)pw.d_items;
+  const int rc = upload_items(items, &d);
+  pw.d_items = d;
+  if (rc != 0) { pw.merged_with = nullptr; return rc; }
+  pw.n_items = (int)items.size(); pw.merged_with = &uw; pw.merged_mix = mix;
+  return 0;
+}
+
+// The one-launch pack + unpack over two work lists; the item list is built on the first call for a (pack, unpack) pair
+// (rpb200_halo_plan_bind builds it eagerly).
 static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev& uw, cudaStream_t st)
 {
   const int unroll = ctx->tune[RPB_K_HALO_PACKING_FUSED].unroll;
@@ -944,16 +959,7 @@ static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev&
     const int rc = worklist_launch<true, 0>(ctx, RPB_K_HALO_PACKING_FUSED, pw, exchange_args(), st);
     return rc != 0 ? rc : worklist_launch<false, 0>(ctx, RPB_K_HALO_PACKING_FUSED, uw, exchange_args(), st);
   }
-  const int mix = unroll == 3 ? 0 : 1;             // tuning `unroll` 3: X groups first instead of mixed in
-  if (pw.merged_with != (const void*)&uw || pw.merged_mix != mix) {
-    std::vector<halo_item> items;
-    build_items_merged(pw, uw, mix != 0, items);
-    halo_item* d = (halo_item*)pw.d_items;
-    const int rc = upload_items(items, &d);
-    pw.d_items = d;
-    if (rc != 0) { pw.merged_with = nullptr; return rc; }
-    pw.n_items = (int)items.size(); pw.merged_with = &uw; pw.merged_mix = mix;
-  }
+  { const int rc = ensure_merged(ctx, pw, uw); if (rc != 0) return rc; }
   halo_items_args A;
   memset(&A, 0, sizeof(A));
   A.psegs[0] = A.psegs[1] = pw.d_segs;
@@ -1004,6 +1010,8 @@ extern "C" int rpb200_halo_plan_bind(rpb200_halo_plan* p, double* const* vars, d
   if (rc == 0) rc = worklist_build(p->pack_wl, segs.data(), (int)segs.size());
   if (rc == 0) rc = plan_segments(p, false, vars, unpack_buffers, segs);
   if (rc == 0) rc = worklist_build(p->unpack_wl, segs.data(), (int)segs.size());
+  if (rc == 0 && p->pack_wl.nsegs <= ITEMS_MAX_SEGS && p->unpack_wl.nsegs <= ITEMS_MAX_SEGS)
+    rc = ensure_merged(p->ctx, p->pack_wl, p->unpack_wl);      // eager: rpb200_halo_plan_pack_unpack never allocates
   if (rc != 0) { worklist_free(p->pack_wl); worklist_free(p->unpack_wl); return rc; }
   p->bound = true;
   return 0;

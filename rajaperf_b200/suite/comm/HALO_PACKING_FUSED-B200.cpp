@@ -1,6 +1,6 @@
 // HALO_PACKING_FUSED-B200.cpp -- Base_B200 variant (the analogue of comm/HALO_PACKING_FUSED-Cuda.cpp:95-197):
-// per rep one fused pack launch and one fused unpack launch over device-resident tuples; no
-// cudaStreamSynchronize between or after them (HALO_PACKING_FUSED-Cuda.cpp:149, 187 have one each).
+// per rep ONE launch over device-resident tuples (pack and unpack items interleaved: they touch disjoint memory,
+// HALO_PACKING_FUSED-Seq.cpp:43-97); no cudaStreamSynchronize (HALO_PACKING_FUSED-Cuda.cpp:149, 187 have one each).
 #include "Comm.hpp"
 
 namespace rajaperf {
@@ -8,8 +8,7 @@ namespace comm {
 
 void HALO_PACKING_FUSED::enqueueRep(rpb200_stream_t s)
 {
-  checkAbi(rpb200_halo_plan_pack(m_plan, s), "rpb200_halo_plan_pack");
-  checkAbi(rpb200_halo_plan_unpack(m_plan, s), "rpb200_halo_plan_unpack");
+  checkAbi(rpb200_halo_plan_pack_unpack(m_plan, s), "rpb200_halo_plan_pack_unpack");
 }
 
 void HALO_PACKING_FUSED::runB200Variant(VariantID, size_t) { runRepLoop(); }
@@ -18,10 +17,12 @@ void HALO_PACKING_FUSED::runB200Variant(VariantID, size_t) { runRepLoop(); }
 // constructor but has no entry of its own in the library's tuning table: it keeps the default only.
 void HALO_PACKING_FUSED::setB200TuningDefinitions(VariantID vid)
 {
-  addB200Tuning(vid, getDefaultTuningName());               // contiguous chunk ranges, packs walk the list backwards
+  addB200Tuning(vid, getDefaultTuningName());               // one launch, x-face items mixed in with the streaming items
   if (getKernelID() != rajaperf::Comm_HALO_PACKING_FUSED) return;
-  addB200Tuning(vid, "forward", 256, 4, 1);                 // packs walk forward too
-  addB200Tuning(vid, "round_robin", 128, 4, 1);             // chunks dealt round-robin to the CTAs
+  addB200Tuning(vid, "x_first", 192, 4, 3);                 // one launch, x-face items first
+  addB200Tuning(vid, "two_launches", 192, 4, 2);            // pack launch + unpack launch, contiguous chunk ranges, packs walk backwards
+  addB200Tuning(vid, "two_launches_forward", 256, 4, 2);    // packs walk forward too
+  addB200Tuning(vid, "two_launches_round_robin", 128, 4, 2);   // chunks dealt round-robin to the CTAs
 }
 
 }  // namespace comm

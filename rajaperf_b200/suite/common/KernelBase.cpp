@@ -152,6 +152,7 @@ void KernelBase::runRepLoop()
     (void)ctx();                      // the context (and its scratch) must exist before capture starts
     cudaStream_t cap;
     cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+    checkAbi(rpb200_stream_attach(ctx(), cap), "rpb200_stream_attach");      // its scratch set exists before the capture starts
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
@@ -166,6 +167,7 @@ void KernelBase::runRepLoop()
     stopTimer();
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
+    checkAbi(rpb200_stream_detach(ctx(), cap), "rpb200_stream_detach");
     cudaStreamDestroy(cap);
     return;
   }

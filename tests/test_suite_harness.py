@@ -137,7 +137,7 @@ def test_tunings_are_listed_selected_and_excluded_like_the_reference():
     out = run_exe(["--dryrun", "-k", "Stream", "MASS3DPA", "HALO_PACKING", "HALO_PACKING_FUSED"]).stdout
     names = _variant_lines(out)
     assert names[0] == "Base_B200-default"
-    for t in ("block_256", "persistent_8", "block_512", "elems8_ctas8_ring2", "forward", "round_robin"):
+    for t in ("block_256", "persistent_8", "block_512", "elems8_ctas8_ring2", "x_first", "two_launches", "two_launches_round_robin"):
         assert f"Base_B200-{t}" in names
     assert _variant_lines(run_exe(["--dryrun", "-k", "Stream", "-t", "block_256", "default"]).stdout) == \
         ["Base_B200-default", "Base_B200-block_256"]
@@ -238,7 +238,8 @@ def test_every_tuning_of_every_kernel_reproduces_the_default_checksum(tmp_path):
     assert seen["Stream_TRIAD"] == ["Base_B200-default", "Base_B200-block_256", "Base_B200-persistent_8"]
     assert seen["Stream_DOT"] == ["Base_B200-default", "Base_B200-block_512"]
     assert len(seen["Apps_MASS3DPA"]) == 3 and len(seen["Apps_CONVECTION3DPA"]) == 3 and len(seen["Polybench_GEMM"]) == 3
-    assert seen["Comm_HALO_PACKING_FUSED"] == ["Base_B200-default", "Base_B200-forward", "Base_B200-round_robin"]
+    assert seen["Comm_HALO_PACKING_FUSED"] == ["Base_B200-default", "Base_B200-x_first", "Base_B200-two_launches", "Base_B200-two_launches_forward",
+                                                "Base_B200-two_launches_round_robin"]
     timing = open(os.path.join(tmp_path, "RAJAPerf-timing-Minimum.csv")).read().splitlines()
     cols = [c.strip() for c in timing[1].split(",")]
     assert cols[:2] == ["Kernel", "Base_B200-default"] and {"Base_B200-block_256", "Base_B200-persistent_8", "Base_B200-tile_64"} <= set(cols)
