@@ -22,7 +22,8 @@ The ONE JSON line printed by rank 0 carries:
   kernels    every kernel of the hot path at its BASELINE size: ms, GB/s, fraction of measured peak; at N = 1 each entry
              also carries `cpu_openmp`: the reference binary's fastest Base_OpenMP / RAJA_OpenMP variant of that kernel on
              this box's host threads, on a bounded sample (size, reps and thread count stated)
-  halo_exchange  HALO_EXCHANGE_FUSED time per rep on the N-rank 3-D grid (512^3 cells per GPU)
+  halo_exchange  HALO_EXCHANGE_FUSED time per rep on the N-rank 3-D grid (512^3 cells per GPU; `cells_1024`: 1024^3), with
+             `verified`: after the timed reps every ghost cell equals its periodic image on every rank
 
 --impl reference times the CPU side alone (the reference arm of the comparison).
 There is no CPU fallback on the b200 arm: without librpb200.so or a B200 it raises.
@@ -124,6 +125,17 @@ def init_real_dev(torch, n, factor, device):
     for s in range(0, n, step):
         e = min(n, s + step)
         i = torch.arange(s, e, dtype=torch.float64, device=device)
+        out[s:e] = (factor * (i + 1.1)) / (i + 1.12345)
+    return out
+
+
+def init_real_dev_range(torch, first, n, factor, device):
+    """Elements [first, first + n) of the same sequence (a shard of a larger suite array)."""
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    step = 1 << 24
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        i = torch.arange(first + s, first + e, dtype=torch.float64, device=device)
         out[s:e] = (factor * (i + 1.1)) / (i + 1.12345)
     return out
 
@@ -393,6 +405,11 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     per_kernel_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i in range(5)]
     dot_value = float(dot.item())
+    # what the e2e leg must reproduce: this rank's own DOT (before the all-reduce) and the last kernel's output (TRIAD)
+    dot_local = torch.zeros(1, dtype=torch.float64, device=dev)
+    ctx.stream_dot(x0, x1, dot_local)
+    y_resident = y.clone()
+    torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -410,15 +427,14 @@ def run_b200(args, rank, world, local_rank):
                 "unit": "GB/s", "frac": kernels[names[dom]]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
                 "share_of_step": per_kernel_ms[dom] / sum(per_kernel_ms),
                 "algorithmic_bytes_per_launch": STREAM_BYTES_PER_ELEM[names[dom]] * n}
-    prof = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(names[dom], {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    # traffic: DRAM bytes per launch of the SAME kernel instantiation from an ncu --set full capture (tools/ncu_traffic.py
+    # writes profiles/r02_ncu_traffic.json with the launch shape it was captured with); refused -- left null, with the
+    # reason -- when the capture's size or launch shape is not what this run launched
+    roofline["traffic"], roofline["traffic_source"] = ncu_traffic(ctx, names[dom], n)
 
     # ---- e2e: the same step from pinned host buffers ----------------------------------------------
-    e2e = run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, min(K, 4))
+    e2e = run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, min(K, 4), float(dot_local.item()), y_resident)
+    del y_resident
 
     # ---- every other kernel of the hot path at its BASELINE size -----------------------------------
     halo = None
@@ -459,9 +475,29 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, steps):
+def ncu_traffic(ctx, kernel, n):
+    """(dram bytes per launch, source) of `kernel` from profiles/r02_ncu_traffic.json, or (None, why not)."""
+    prof = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(prof):
+        return None, "no profiles/r02_ncu_traffic.json"
+    try:
+        e = json.load(open(prof)).get(kernel)
+        if not e:
+            return None, f"no ncu capture of {kernel}"
+        if int(e.get("n", -1)) != int(n):
+            return None, f"ncu capture is of n = {e.get('n')}, this run launched n = {n}"
+        if list(e.get("tuning", [])) != list(ctx.get_tuning(kernel)):
+            return None, f"ncu capture is of launch shape {e.get('tuning')}, this run launched {list(ctx.get_tuning(kernel))}"
+        return e["dram_bytes_per_launch"], f"{e.get('kernel_name')} @ {e.get('commit')} ({os.path.basename(prof)})"
+    except Exception as ex:                                   # a malformed file is not a measurement
+        return None, f"unreadable: {ex}"
+
+
+def run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, steps, dot_resident, y_resident):
     """Host-resident inputs -> results back on the host, through the C ABI.  16 chunks round-robin over
-    4 streams so H2D, kernels and D2H of different chunks overlap (PCIe is full duplex)."""
+    4 streams so H2D, kernels and D2H of different chunks overlap (PCIe is full duplex).  The four streams use ONE
+    context concurrently (per-stream scratch: include/rpb200.h); the leg checks its own answer: the DOT it returns must
+    equal the resident step's, and the host copy of the output must equal the last kernel's (TRIAD) resident output."""
     nchunk, nstream = 16, 4
     cs = n // nchunk
     h0 = torch.empty(n, dtype=torch.float64, pin_memory=True)
@@ -507,8 +543,26 @@ def run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, steps):
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    # ---- the leg checks its answer (outside the timed region)
+    e2e_dot = step()
+    # 16 chunk partials summed on the host against one 2^28-element reduction: same products, different association
+    dot_ok = abs(e2e_dot - dot_resident) <= 1e-12 * abs(dot_resident)
+    y_ok = bool(torch.equal(y, y_resident))
+    hy_dev = torch.empty_like(y)
+    hy_dev.copy_(hy)
+    hy_ok = bool(torch.equal(hy_dev, y_resident))
+    del hy_dev
+    verified = bool(dot_ok and y_ok and hy_ok)
+    if world > 1:
+        t = torch.tensor([1.0 if verified else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        verified = bool(t.item() == 1.0)
+    if not verified:
+        raise RuntimeError(f"e2e leg computed a different answer: dot {e2e_dot!r} vs {dot_resident!r} (ok={dot_ok}), "
+                           f"device output equal={y_ok}, host output equal={hy_ok}")
     del h0, h1, hy
-    return {"value": world * STEP_BYTES_PER_ELEM * n * steps / dt / 1e9, "unit": UNIT,
+    return {"value": world * STEP_BYTES_PER_ELEM * n * steps / dt / 1e9, "unit": UNIT, "verified": verified,
+            "dot": e2e_dot, "dot_resident": dot_resident,
             "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 4 * 8 * n + 8 * nchunk, "steps": steps,
             "ms_per_step": dt / steps * 1e3,
             "how": "pinned host -> 16 chunks over 4 streams (H2D x0,x1; COPY,MUL,ADD,TRIAD each followed by D2H "
@@ -590,15 +644,30 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
     del phi, psi
     torch.cuda.empty_cache()
 
-    # ---- Comm: 512^3 cells per GPU, halo 1, 3 variables ----------------------------------------------
-    g, hw, nv = 512, 1, 3
-    plan = ctx.halo_plan((g, g, g), hw, nv, rank, rank_grid(world))
-    vars_ = [torch.arange(plan.var_size, **f64) + v for v in range(nv)]
-    halo_elems = sum(nb["pack_len"] for nb in plan.neighbors) * nv
-    pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
-    ub = [torch.zeros(nv * nb["unpack_len"], **f64) for nb in plan.neighbors]
-    plan.bind(vars_, pb, ub)
+    # ---- DOT / REDUCE_SUM as ONE global reduction over N shards: rank r owns elements [r n, (r+1) n) of an
+    # N n-element array, reduces its shard, and one all-reduce of one double combines them (rank order is NCCL's) --------------
+    n = ALGO_N
+    xs = init_real_dev_range(torch, rank * n, n, 0.2, dev)
+    part = torch.zeros(1, **f64)
 
+    def sharded_reduce():
+        ctx.reduce_sum(xs, part)
+        if world > 1:
+            dist.all_reduce(part)
+    ms = time_events(torch, sharded_reduce, 20, 3)
+    got = float(part.item())
+    want = torch.zeros(1, **f64)
+    want += xs.sum()                                           # torch's own pairwise sum of the same shard, then the same all-reduce
+    if world > 1:
+        dist.all_reduce(want)
+        t = torch.tensor([ms], **f64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ok = abs(got - float(want.item())) <= 1e-11 * abs(float(want.item()))
+    rec("Algorithm_REDUCE_SUM_sharded", world * n, 8 * n * world, ms, n_gpus=world, value=got, verified=bool(ok),
+        note="N shards of 2^27 doubles, local reduction + one all-reduce of one double; time = max over ranks, bytes = all shards")
+    del xs
+    torch.cuda.empty_cache()
+
+    # ---- Comm: 512^3 and 1024^3 cells per GPU, halo 1, 3 variables ------------------------------------
     def graph_ms(body, reps):
         """reps x body() captured into ONE CUDA graph (the rep loop of the suite's runKernel), replayed and
         timed with CUDA events: removes the ~10 us/launch cost of calling the C ABI from Python."""
@@ -615,33 +684,67 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def packing():
-        plan.pack(); plan.unpack()
-    rec("Comm_HALO_PACKING_FUSED", halo_elems, 40 * halo_elems, graph_ms(packing, 100),
-        grid=[g, g, g], launches_per_rep=2, timed="100 reps in one CUDA graph")
+    def ghosts_are_periodic_images(vars_, g, hw):
+        """Every rank holds var[i] = i + v, so after an exchange on ANY rank grid each ghost cell must hold the value of
+        its periodic image inside the owned box, and owned cells must be untouched (tests/test_comm_gpu.py: the full-size
+        property test).  Checked on the device, all variables."""
+        e = g + 2 * hw
+        idx = torch.arange(e, device=dev)
+        src = ((idx - hw) % g) + hw
+        want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64)
+        ok = all(bool(torch.equal(vars_[v].view(e, e, e), want + v)) for v in range(len(vars_)))
+        del want
+        return ok
 
-    _, _, handle = plan.window(vars_)
-    if world > 1:
-        handles = [None] * world
-        dist.all_gather_object(handles, handle)
-        plan.connect(handles)
-        dist.barrier()
-    else:
-        plan.connect_ptrs([0])
-    ms = graph_ms(plan.exchange, 100)
-    plan.status()
-    if world > 1:
-        t = torch.tensor([ms], **f64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        dist.barrier()
-    rec("Comm_HALO_EXCHANGE_FUSED", halo_elems, 56 * halo_elems, ms, grid=[g, g, g], launches_per_rep=2,
-        timed="100 reps in one CUDA graph, max over ranks")
-    halo = {"ms_per_rep": ms, "n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": [g, g, g],
-            "halo_width": hw, "num_vars": nv, "bytes_sent_per_gpu_per_rep": 8 * halo_elems,
-            "transport": "pack kernel stores into the peer's receive window over NVLink (CUDA IPC), "
-                         "per-message release/acquire flags; no host sync, no MPI"}
-    plan.close()
+    halo = None
+    for g in (512, 1024):
+        hw, nv, reps = 1, 3, (100 if g == 512 else 40)
+        suffix = "" if g == 512 else f"_{g}"
+        plan = ctx.halo_plan((g, g, g), hw, nv, rank, rank_grid(world))
+        vars_ = [torch.arange(plan.var_size, **f64) + v for v in range(nv)]
+        halo_elems = sum(nb["pack_len"] for nb in plan.neighbors) * nv
+        pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
+        ub = [torch.zeros(nv * nb["unpack_len"], **f64) for nb in plan.neighbors]
+        plan.bind(vars_, pb, ub)
+        rec("Comm_HALO_PACKING_FUSED" + suffix, halo_elems, 40 * halo_elems, graph_ms(plan.pack_unpack, reps),
+            grid=[g, g, g], launches_per_rep=1, timed=f"{reps} reps in one CUDA graph")
+        del pb, ub
+        for v in range(nv):                                    # the packing test filled the ghost cells with zeros
+            vars_[v].copy_(torch.arange(plan.var_size, **f64) + v)
+        _, _, handle = plan.window(vars_)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, handle)
+            plan.connect(handles)
+            dist.barrier()
+        else:
+            plan.connect_ptrs([0])
+        ms = graph_ms(plan.exchange, reps)
+        plan.status()                                          # raises if any rank's unpack timed out on a message
+        verified = ghosts_are_periodic_images(vars_, g, hw)
+        if world > 1:
+            t = torch.tensor([ms, 0.0 if verified else 1.0], **f64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, verified = float(t[0].item()), bool(t[1].item() == 0.0)
+            dist.barrier()
+        launches = 1 if ctx.get_tuning("Comm_HALO_EXCHANGE_FUSED")[2] == 1 else 2
+        rec("Comm_HALO_EXCHANGE_FUSED" + suffix, halo_elems, 56 * halo_elems, ms, grid=[g, g, g], launches_per_rep=launches,
+            verified=verified, timed=f"{reps} reps in one CUDA graph, max over ranks")
+        h = {"ms_per_rep": ms, "n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": [g, g, g],
+             "halo_width": hw, "num_vars": nv, "bytes_sent_per_gpu_per_rep": 8 * halo_elems, "verified": verified,
+             "verified_how": "after the timed reps every ghost cell of every variable equals its periodic image and every owned "
+                             "cell is untouched (device-side comparison on every rank, AND-reduced)",
+             "transport": "pack kernel stores into the peer's receive window over NVLink (CUDA IPC), "
+                          "per-message release/acquire flags; no host sync, no MPI"}
+        if g == 512:
+            halo = h
+        else:
+            halo["cells_1024"] = h
+        plan.close()
+        del vars_
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
     return out, halo
 
 

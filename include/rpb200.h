@@ -15,7 +15,7 @@
  *     besides the caller's arrays (reduction partials and tickets, scan / index-list look-back
  *     descriptors, tickets and epochs, PA basis tables) exists once per (context, stream) -- the
  *     reference likewise gives every reducer its own scratch, GPUUtils.hpp:250-330 -- and is
- *     attached to a stream at its first call (no allocation for the first 4 streams; see
+ *     attached to a stream at its first call (no allocation for the first 8 streams; see
  *     rpb200_stream_attach).  The three Apps_*3DPA kernels keep their basis tables in
  *     __constant__ memory, one set per DEVICE: calls on different streams are safe but
  *     serialise (an event orders each call behind the device's previous PA call).
@@ -56,9 +56,9 @@ void        rpb200_destroy(rpb200_ctx* ctx);
 const char* rpb200_error_string(int err);
 int         rpb200_sm_count(const rpb200_ctx* ctx);
 const char* rpb200_version(void);
-/* Optional.  attach: give `stream` its scratch set NOW (allocating one if the 4 pre-allocated sets are taken, and sizing
+/* Optional.  attach: give `stream` its scratch set NOW (allocating one if the 8 pre-allocated sets are taken, and sizing
  * its look-back state to the largest rpb200_scan_reserve / rpb200_indexlist_reserve so far; synchronises) -- required only
- * before CAPTURING calls on a stream that is the 5th or later stream of the context, since a capture may not allocate.
+ * before CAPTURING calls on a stream that is the 9th or later stream of the context, since a capture may not allocate.
  * detach: the stream is about to be destroyed; its set is kept for the next stream that attaches (at most 64 attached
  * streams per context: RPB200_ENOSLOT).                                                                               */
 int rpb200_stream_attach(rpb200_ctx* ctx, rpb200_stream_t stream);
@@ -81,6 +81,8 @@ int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
  * Every setting computes the same result; the defaults are the measured best (profiles/).            */
 int rpb200_set_tuning(rpb200_ctx* ctx, const char* kernel, int block_size,
                       int ctas_per_sm, int unroll);
+/* The current launch shape of `kernel` (what an ncu capture must record to be comparable with a later run).            */
+int rpb200_get_tuning(const rpb200_ctx* ctx, const char* kernel, int* block_size, int* ctas_per_sm, int* unroll);
 /* Back to the built-in (measured best) launch shape of `kernel`; NULL = of every kernel.  The suite harness brackets
  * each non-default tuning of a kernel with set / reset (KernelBase::execute).                                          */
 int rpb200_reset_tuning(rpb200_ctx* ctx, const char* kernel);
@@ -218,10 +220,11 @@ int  rpb200_halo_plan_pack(rpb200_halo_plan*, rpb200_stream_t);
 int  rpb200_halo_plan_unpack(rpb200_halo_plan*, rpb200_stream_t);
 /* One rep of HALO_PACKING_FUSED in ONE launch.  The pack (HALO_PACKING_FUSED-Seq.cpp:43-61: owned cells -> pack buffers) and
  * the unpack (:71-97: unpack buffers -> ghost cells) touch disjoint cells and disjoint buffers, so the result does not
- * depend on how their work interleaves; the launch walks an item list that keeps chunk c of pack(-x), pack(+x), unpack(-x),
- * unpack(+x) of a variable adjacent -- those four touch the same one or two 32-byte sectors per grid row, so the strided
- * faces cost one DRAM burst per row instead of four (csrc/halo.cu: halo_items_kernel).  Same result as pack then unpack.
- * Tuning Comm_HALO_PACKING_FUSED `unroll` 2 = run the two launches instead; 3 = x-face items first instead of mixed in.  */
+ * depend on how their work interleaves; the launch walks a list of UNITS dealt round-robin to the CTAs, where chunk c of
+ * pack(-x), pack(+x), unpack(-x), unpack(+x) of a variable is ONE unit (one CTA, back to back) -- those four touch the same
+ * one or two 32-byte sectors per grid row (csrc/halo.cu: halo_items_kernel).  Same result as pack then unpack.
+ * Tuning Comm_HALO_PACKING_FUSED `unroll`: 2 = run the two launches instead; 3 = x-face units first instead of mixed in;
+ * 5 = two phases in the one launch (every pack unit, then every unpack unit, x faces last / first).                      */
 int  rpb200_halo_plan_pack_unpack(rpb200_halo_plan*, rpb200_stream_t);
 
 /* (3) HALO_EXCHANGE_FUSED over NVLink peer memory (replaces MPI_Irecv / MPI_Isend /

@@ -40,6 +40,7 @@ SIGNATURES = {
     "rpb200_stream_detach": (c_int, [_P, _P]),
     "rpb200_set_tuning": (c_int, [_P, c_char_p, c_int, c_int, c_int]),
     "rpb200_reset_tuning": (c_int, [_P, c_char_p]),
+    "rpb200_get_tuning": (c_int, [_P, c_char_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "rpb200_stream_copy": (c_int, [_P, _P, _P, c_int64, _P]),
     "rpb200_stream_mul": (c_int, [_P, _P, _P, c_double, c_int64, _P]),
     "rpb200_stream_add": (c_int, [_P, _P, _P, _P, c_int64, _P]),
@@ -180,6 +181,13 @@ class Context:
     def set_tuning(self, kernel: str, block_size: int = -1, ctas_per_sm: int = -1, unroll: int = -1):
         check(self.lib.rpb200_set_tuning(self.h, kernel.encode(), block_size, ctas_per_sm, unroll),
               f"set_tuning({kernel})")
+
+    def get_tuning(self, kernel: str):
+        """(block_size, ctas_per_sm, unroll) currently in force for `kernel`."""
+        b, c, u = c_int(), c_int(), c_int()
+        check(self.lib.rpb200_get_tuning(self.h, kernel.encode(), ctypes.byref(b), ctypes.byref(c), ctypes.byref(u)),
+              f"get_tuning({kernel})")
+        return b.value, c.value, u.value
 
     def reset_tuning(self, kernel: str | None = None):
         """Built-in launch shape of `kernel` (None: of every kernel) again."""

@@ -37,7 +37,7 @@ enum rpb_kernel_id {
 
 #define RPB_MAX_PARTIALS 8192
 #define RPB_MAX_STREAMS 64        // distinct streams one context can serve at the same time
-#define RPB_PREALLOC_STREAMS 4    // scratch sets allocated by rpb200_create (no allocation on the first call of a stream)
+#define RPB_PREALLOC_STREAMS 8    // scratch sets allocated by rpb200_create (no allocation on the first call of a stream)
 
 // Everything a kernel writes besides the caller's arrays, ONE SET PER (context, stream): calls on different streams of one
 // context never share a ticket, a partial, a look-back descriptor or an epoch (the reference gives every reducer its own

@@ -222,6 +222,19 @@ extern "C" int rpb200_set_tuning(rpb200_ctx* c, const char* kernel, int block_si
   return RPB200_EINVAL;
 }
 
+extern "C" int rpb200_get_tuning(const rpb200_ctx* c, const char* kernel, int* block_size, int* ctas_per_sm, int* unroll)
+{
+  if (!c || !kernel) return RPB200_EINVAL;
+  for (int k = 0; k < RPB_K_COUNT; ++k)
+    if (strcmp(kernel, k_kernel_names[k]) == 0) {
+      if (block_size) *block_size = c->tune[k].block_size;
+      if (ctas_per_sm) *ctas_per_sm = c->tune[k].ctas_per_sm;
+      if (unroll) *unroll = c->tune[k].unroll;
+      return 0;
+    }
+  return RPB200_EINVAL;
+}
+
 extern "C" int rpb200_reset_tuning(rpb200_ctx* c, const char* kernel)
 {
   if (!c) return RPB200_EINVAL;

@@ -259,16 +259,17 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
 //      (nx, j, k)  (nx+1, j, k)  (0, j+1, k)  (1, j+1, k)      =  +x owned, +x ghost, -x ghost, -x owned
 // are CONSECUTIVE (the end of row j and the start of row j + 1): 32 bytes, one sector when j is even, two adjacent sectors
 // when j is odd.  So element n of the four tuples  pack(-x), pack(+x), unpack(-x), unpack(+x)  of one variable touch the same
-// one or two sectors.  An item list that puts chunk c of those four tuples NEXT TO EACH OTHER, dealt round-robin to
-// neighbouring CTAs, turns four DRAM bursts (one of them a read-modify-write) into one burst read + one write-back: the other
-// three accesses hit the line in L2 while it is still there.  The same adjacency serves the index lists: the items of the
-// three variables of one (neighbour, chunk) sit together, so a list chunk is fetched from DRAM once and hit twice.
+// one or two sectors.  The item list therefore groups chunk c of those four tuples into one UNIT, and a unit is the grain of
+// dealing: ONE CTA moves its four chunks back to back, so thread t touches (1, j_t, k), (nx, j_t, k), (0, j_t, k),
+// (nx+1, j_t, k) within a microsecond -- the second to fourth access find the sector in this SM's L1 or in L2, and the
+// strided faces cost one DRAM burst read + one write-back per row instead of four bursts (one a read-modify-write).
+// (Round 2, call b measured the same four chunks dealt to four DIFFERENT CTAs: 108 us against 96 us for two launches at 512^3
+// -- adjacency in the list is not locality on the chip; profiles/r02_b/.)  Every other chunk is a unit of its own.
 // Pack and unpack of HALO_PACKING_FUSED touch disjoint cells (owned / ghost) and disjoint buffers
 // (HALO_PACKING_FUSED-Seq.cpp:43-97), so any interleaving computes the reference's result.
 //
-// Dealing is round-robin (item i -> CTA i mod grid), which spreads the slow strided items and the streaming items evenly
-// over every CTA; the list order mixes the two kinds so that the burst-bound x-face work overlaps the bandwidth-bound rest.
-// A thread keeps the index loads of its NEXT item in flight while it gathers / scatters the current one.
+// Dealing is round-robin over units (unit u -> CTA u mod grid), which spreads the slow strided units and the streaming ones
+// evenly over every CTA.  A thread keeps the index loads of its NEXT item in flight while it gathers / scatters the current one.
 struct halo_item { int seg; int chunk; };            // seg: tuple index, bit 30 set = unpack side
 constexpr int ITEM_UNPACK = 1 << 30;
 constexpr int ITEMS_MAX_SEGS = 128;                  // tuples per side kept in shared memory (26 neighbours x <= 4 variables)
@@ -277,7 +278,8 @@ struct halo_items_args {
   const rpb200_halo_seg* psegs[2];                   // pack tuples, generation 0 / 1 (the same array for HALO_PACKING_FUSED)
   const rpb200_halo_seg* usegs[2];
   const halo_item* items;
-  int n_items, n_pack_items, npsegs, nusegs;         // XCHG: items [0, n_pack_items) are the pack phase
+  const int* unit_first;                             // unit u = items [unit_first[u], unit_first[u + 1])
+  int n_units, n_pack_units, npsegs, nusegs;         // XCHG: units [0, n_pack_units) are the pack phase
   const halo_msg* pmsgs; const halo_msg* umsgs;
   unsigned int* msg_done; unsigned long long* d_epoch; unsigned int* unpack_done; int* error;
   unsigned long long timeout_ns;
@@ -340,18 +342,36 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
     }
   };
 
-  // ---- phase 1: every item (HALO_PACKING_FUSED) / the pack items (exchange)
-  const int end1 = XCHG ? A.n_pack_items : A.n_items;
+  // this CTA's items in order: the items of unit u, then of unit u + G, ...
+  struct cursor { int u, it, end_it; };
+  auto cursor_begin = [&](int u0, int u_end) {
+    cursor c{u0, 0, 0};
+    if (u0 < u_end) { c.it = __ldg(A.unit_first + u0); c.end_it = __ldg(A.unit_first + u0 + 1); }
+    return c;
+  };
+  auto cursor_next = [&](cursor c, int u_end) {
+    if (++c.it == c.end_it) {
+      c.u += G;
+      if (c.u < u_end) { c.it = __ldg(A.unit_first + c.u); c.end_it = __ldg(A.unit_first + c.u + 1); }
+    }
+    return c;
+  };
+
+  // ---- phase 1: every unit (HALO_PACKING_FUSED) / the pack units (exchange)
+  const int end1 = XCHG ? A.n_pack_units : A.n_units;
   {
     halo_item h, nh;
-    fetch((int)blockIdx.x, end1, idx, h);
-    for (int it = blockIdx.x; it < end1; it += G) {
-      fetch(it + G, end1, nidx, nh);
+    cursor c = cursor_begin((int)blockIdx.x, end1);
+    fetch(c.u < end1 ? c.it : 1, c.u < end1 ? c.it + 1 : 0, idx, h);
+    while (c.u < end1) {
+      const cursor n = cursor_next(c, end1);
+      fetch(n.u < end1 ? n.it : 1, n.u < end1 ? n.it + 1 : 0, nidx, nh);
       move(h, idx);
       if (XCHG && threadIdx.x == 0) s_credit[s_seg[0][h.seg].msg] += 1u;     // only thread 0 touches s_credit between barriers
 #pragma unroll
       for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
       h = nh;
+      c = n;
     }
   }
   if (!XCHG) return;
@@ -378,10 +398,11 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
   bool failed = false;
   {
     halo_item h, nh;
-    const int first = A.n_pack_items + (int)blockIdx.x;
-    fetch(first, A.n_items, idx, h);
-    for (int it = first; it < A.n_items; it += G) {
-      fetch(it + G, A.n_items, nidx, nh);
+    cursor c = cursor_begin(A.n_pack_units + (int)blockIdx.x, A.n_units);
+    fetch(c.u < A.n_units ? c.it : 1, c.u < A.n_units ? c.it + 1 : 0, idx, h);
+    while (c.u < A.n_units) {
+      const cursor n = cursor_next(c, A.n_units);
+      fetch(n.u < A.n_units ? n.it : 1, n.u < A.n_units ? n.it + 1 : 0, nidx, nh);
       const int m = s_seg[1][h.seg & (ITEM_UNPACK - 1)].msg;
       if (m != waited_msg) {
         if (threadIdx.x == 0) {
@@ -405,6 +426,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
 #pragma unroll
       for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
       h = nh;
+      c = n;
     }
   }
   __syncthreads();
@@ -455,7 +477,8 @@ struct worklist_dev {
   std::vector<long long> first;     // host copy: first chunk of every tuple
   std::vector<rpb200_halo_seg> h_segs;   // host copy of the tuples as built (geometry: len, msg, flags, var)
   // item list of the one-launch pack+unpack kernel, cached on the PACK list for the unpack list it was merged with
-  void* d_items = nullptr; int n_items = 0; const void* merged_with = nullptr; int merged_mix = -1;
+  void* d_items = nullptr; const halo_item* d_item_list = nullptr; const int* d_unit_first = nullptr; int n_units = 0;
+  const void* merged_with = nullptr; int merged_order = -1;
 };
 
 int worklist_free(worklist_dev& w)
@@ -639,7 +662,8 @@ struct rpb200_halo_plan {
   unsigned int* d_unpack_done = nullptr;
   bool connected = false;
   // item lists of the one-launch kernels (halo_items_kernel): HALO_PACKING_FUSED merged, exchange pack-then-unpack
-  halo_item* d_items_xchg = nullptr;   int n_items_xchg = 0, n_pack_items_xchg = 0;
+  void* d_xchg_block = nullptr; const halo_item* d_items_xchg = nullptr; const int* d_unit_first_xchg = nullptr;
+  int n_units_xchg = 0, n_pack_units_xchg = 0;
 };
 
 extern "C" int rpb200_halo_chunk(void) { return HALO_CHUNK; }
@@ -710,7 +734,7 @@ extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
   cudaFree(p->d_window);
   cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_send_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
   cudaFree(p->d_epoch); cudaFree(p->d_unpack_done);
-  cudaFree(p->d_items_xchg);
+  cudaFree(p->d_xchg_block);
   delete p;
 }
 
@@ -830,23 +854,15 @@ static std::vector<x_ref> x_tuples(const worklist_dev& pw, const worklist_dev& u
   return x;
 }
 
-// mix: spread the X groups evenly among the streaming groups (Bresenham), so that the burst-bound and the bandwidth-bound
-// traffic are in flight together; otherwise X groups first.
-static void merge_groups(const std::vector<std::vector<halo_item>>& xg, const std::vector<std::vector<halo_item>>& sg, bool mix,
-                         std::vector<halo_item>& out)
-{
-  size_t ix = 0, is = 0;
-  const size_t nx = xg.size(), ns = sg.size();
-  while (ix < nx || is < ns) {
-    bool take_x;
-    if (!mix) take_x = ix < nx;
-    else if (ix >= nx) take_x = false;
-    else if (is >= ns) take_x = true;
-    else take_x = (ix + 1) * ns <= (is + 1) * nx;      // keep ix / nx and is / ns level
-    const std::vector<halo_item>& g = take_x ? xg[ix++] : sg[is++];
-    out.insert(out.end(), g.begin(), g.end());
-  }
-}
+// A unit list under construction: items + the first item of every unit
+struct unit_list {
+  std::vector<halo_item> items;
+  std::vector<int> first;                              // first[u]; the end sentinel is appended by finish()
+  void add_unit(const std::vector<halo_item>& g) { if (g.empty()) return; first.push_back((int)items.size()); items.insert(items.end(), g.begin(), g.end()); }
+  void add_singles(const std::vector<halo_item>& g) { for (const halo_item& h : g) { first.push_back((int)items.size()); items.push_back(h); } }
+  int units() const { return (int)first.size(); }
+  void finish() { first.push_back((int)items.size()); }
+};
 
 // streaming groups of one list: for every message (run of consecutive tuples with the same msg), chunk-major
 static void stream_groups(const worklist_dev& w, int64_t xlen, int bit, std::vector<std::vector<halo_item>>& sg)
@@ -866,67 +882,108 @@ static void stream_groups(const worklist_dev& w, int64_t xlen, int bit, std::vec
   }
 }
 
-// HALO_PACKING_FUSED: pack and unpack items interleaved
-static void build_items_merged(const worklist_dev& pw, const worklist_dev& uw, bool mix, std::vector<halo_item>& items)
+// the X tuples of one variable: consecutive entries of x_tuples() with the same var
+static std::vector<std::vector<x_ref>> by_variable(const std::vector<x_ref>& x)
 {
-  const int64_t xlen = x_tuple_len(pw, uw);
-  std::vector<std::vector<halo_item>> xg, sg, sp, su;
-  const std::vector<x_ref> x = x_tuples(pw, uw, xlen, true, true);
-  for (int64_t c = 0; c < plan_chunks(xlen) && !x.empty(); ++c) {
-    std::vector<halo_item> g;
-    for (const x_ref& r : x) g.push_back(halo_item{r.seg, (int)c});
-    xg.push_back(g);
+  std::vector<std::vector<x_ref>> out;
+  for (const x_ref& r : x) {
+    if (out.empty() || out.back().front().var != r.var) out.emplace_back();
+    out.back().push_back(r);
   }
-  stream_groups(pw, xlen, 0, sp);
-  stream_groups(uw, xlen, ITEM_UNPACK, su);
-  for (size_t k = 0; k < sp.size() || k < su.size(); ++k) {        // pack group, unpack group, pack group, ...
-    if (k < sp.size()) sg.push_back(sp[k]);
-    if (k < su.size()) sg.push_back(su[k]);
-  }
-  items.clear();
-  merge_groups(xg, sg, mix, items);
+  return out;
 }
 
-// HALO_EXCHANGE_FUSED: all pack items, then all unpack items.  The X tuples are packed LAST (ascending chunks) and unpacked
-// FIRST (descending chunks): the ghost cells share their L2 lines with the owned cells read a moment earlier (LIFO reuse
-// across the signal), and the -x / +x chunks of one variable stay adjacent so that they share their DRAM bursts.
-static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, std::vector<halo_item>& items, int* n_pack)
+// HALO_PACKING_FUSED in one launch.  order 1: X units {pack(-x), pack(+x), unpack(-x), unpack(+x)} of (chunk, variable) spread
+// evenly among the streaming units (Bresenham: burst-bound and bandwidth-bound traffic in flight together); 3: X units first;
+// 5: two phases in one launch -- every pack unit (X pairs last), then every unpack unit (X pairs first, descending): the
+// order of the exchange, where the phases cannot interleave.
+static void build_items_merged(const worklist_dev& pw, const worklist_dev& uw, int order, unit_list& L)
 {
   const int64_t xlen = x_tuple_len(pw, uw);
   std::vector<std::vector<halo_item>> sp, su;
   stream_groups(pw, xlen, 0, sp);
   stream_groups(uw, xlen, ITEM_UNPACK, su);
-  const std::vector<x_ref> xp = x_tuples(pw, uw, xlen, true, false), xu = x_tuples(pw, uw, xlen, false, true);
-  items.clear();
-  for (const auto& g : sp) items.insert(items.end(), g.begin(), g.end());
-  for (int64_t c = 0; c < plan_chunks(xlen) && !xp.empty(); ++c)
-    for (const x_ref& r : xp) items.push_back(halo_item{r.seg, (int)c});
-  *n_pack = (int)items.size();
-  for (int64_t c = plan_chunks(xlen) - 1; c >= 0 && !xu.empty(); --c)
-    for (size_t k = xu.size(); k-- > 0;) items.push_back(halo_item{xu[k].seg, (int)c});
-  for (const auto& g : su) items.insert(items.end(), g.begin(), g.end());
+  if (order == 5) {
+    const auto xp = by_variable(x_tuples(pw, uw, xlen, true, false)), xu = by_variable(x_tuples(pw, uw, xlen, false, true));
+    for (const auto& g : sp) L.add_singles(g);
+    for (int64_t c = 0; c < plan_chunks(xlen); ++c)
+      for (const auto& var : xp) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+    for (int64_t c = plan_chunks(xlen) - 1; c >= 0; --c)
+      for (size_t k = xu.size(); k-- > 0;) { std::vector<halo_item> g; for (const x_ref& r : xu[k]) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+    for (const auto& g : su) L.add_singles(g);
+    L.finish();
+    return;
+  }
+  const auto xv = by_variable(x_tuples(pw, uw, xlen, true, true));
+  // streaming groups alternate pack / unpack
+  std::vector<std::vector<halo_item>> sg;
+  for (size_t k = 0; k < sp.size() || k < su.size(); ++k) {
+    if (k < sp.size()) sg.push_back(sp[k]);
+    if (k < su.size()) sg.push_back(su[k]);
+  }
+  const size_t nx = xv.empty() ? 0 : (size_t)plan_chunks(xlen), ns = sg.size();
+  size_t ix = 0, is = 0;
+  while (ix < nx || is < ns) {
+    bool take_x;
+    if (order == 3) take_x = ix < nx;
+    else if (ix >= nx) take_x = false;
+    else if (is >= ns) take_x = true;
+    else take_x = (ix + 1) * ns <= (is + 1) * nx;      // keep ix / nx and is / ns level
+    if (take_x) {
+      for (const auto& var : xv) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)ix}); L.add_unit(g); }
+      ++ix;
+    } else {
+      L.add_singles(sg[is++]);
+    }
+  }
+  L.finish();
 }
 
-static int upload_items(const std::vector<halo_item>& items, halo_item** d_items)
+// HALO_EXCHANGE_FUSED: all pack units, then all unpack units.  The X tuples are packed LAST (ascending chunks) and unpacked
+// FIRST (descending chunks): the ghost cells share their L2 lines with the owned cells read a moment earlier (LIFO reuse
+// across the signal); the -x / +x chunks of one variable form one unit (one CTA: shared sectors, shared DRAM bursts).
+static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, unit_list& L, int* n_pack_units)
 {
-  cudaFree(*d_items); *d_items = nullptr;
-  if (items.empty()) return 0;
-  RPB_CHECK(cudaMalloc(d_items, sizeof(halo_item) * items.size()));
-  RPB_CHECK(cudaMemcpy(*d_items, items.data(), sizeof(halo_item) * items.size(), cudaMemcpyHostToDevice));
+  const int64_t xlen = x_tuple_len(pw, uw);
+  std::vector<std::vector<halo_item>> sp, su;
+  stream_groups(pw, xlen, 0, sp);
+  stream_groups(uw, xlen, ITEM_UNPACK, su);
+  const auto xp = by_variable(x_tuples(pw, uw, xlen, true, false)), xu = by_variable(x_tuples(pw, uw, xlen, false, true));
+  for (const auto& g : sp) L.add_singles(g);
+  for (int64_t c = 0; c < plan_chunks(xlen); ++c)
+    for (const auto& var : xp) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+  *n_pack_units = L.units();
+  for (int64_t c = plan_chunks(xlen) - 1; c >= 0; --c)
+    for (size_t k = xu.size(); k-- > 0;) { std::vector<halo_item> g; for (const x_ref& r : xu[k]) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+  for (const auto& g : su) L.add_singles(g);
+  L.finish();
+}
+
+// items and unit_first in ONE device allocation: [items | unit_first]
+static int upload_units(const unit_list& L, void** d_block, const halo_item** d_items, const int** d_unit_first)
+{
+  cudaFree(*d_block); *d_block = nullptr; *d_items = nullptr; *d_unit_first = nullptr;
+  if (L.items.empty()) return 0;
+  const size_t ib = sizeof(halo_item) * L.items.size(), ub = sizeof(int) * L.first.size();
+  RPB_CHECK(cudaMalloc(d_block, ib + ub));
+  RPB_CHECK(cudaMemcpy(*d_block, L.items.data(), ib, cudaMemcpyHostToDevice));
+  RPB_CHECK(cudaMemcpy((char*)*d_block + ib, L.first.data(), ub, cudaMemcpyHostToDevice));
+  *d_items = (const halo_item*)*d_block;
+  *d_unit_first = (const int*)((char*)*d_block + ib);
   return 0;
 }
 
 template <bool XCHG>
 static int launch_items(const rpb200_ctx* ctx, int kid, const halo_items_args& A, cudaStream_t st)
 {
-  if (A.n_items == 0) return 0;
+  if (A.n_units == 0) return 0;
   int resident = 0;             // XCHG: the grid must be fully co-resident (phase 2 spins on flags other ranks' phase 1 releases)
   RPB_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, halo_items_kernel<XCHG>, HALO_BLOCK, 0));
   if (resident < 1) return (int)cudaErrorLaunchOutOfResources;
   int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
   if (cps > resident) cps = resident;
   int64_t grid = (int64_t)ctx->sm_count * cps;
-  const int64_t most = XCHG ? (A.n_pack_items > A.n_items - A.n_pack_items ? A.n_pack_items : A.n_items - A.n_pack_items) : A.n_items;
+  const int64_t most = XCHG ? (A.n_pack_units > A.n_units - A.n_pack_units ? A.n_pack_units : A.n_units - A.n_pack_units) : A.n_units;
   if (grid > most) grid = most;
   if (grid < 1) grid = 1;
   halo_items_kernel<XCHG><<<(int)grid, HALO_BLOCK, 0, st>>>(A);
@@ -935,17 +992,20 @@ static int launch_items(const rpb200_ctx* ctx, int kid, const halo_items_args& A
 }
 
 // the merged item list of a (pack, unpack) pair, cached on the pack list; rebuilt when the pair or the order tuning changes
+static int merged_order_of(const rpb200_ctx* ctx)
+{
+  const int u = ctx->tune[RPB_K_HALO_PACKING_FUSED].unroll;       // tuning `unroll`: 3 = X units first, 5 = two phases, else X units mixed in
+  return (u == 3 || u == 5) ? u : 1;
+}
 static int ensure_merged(const rpb200_ctx* ctx, worklist_dev& pw, worklist_dev& uw)
 {
-  const int mix = ctx->tune[RPB_K_HALO_PACKING_FUSED].unroll == 3 ? 0 : 1;      // tuning `unroll` 3: X groups first instead of mixed in
-  if (pw.merged_with == (const void*)&uw && pw.merged_mix == mix) return 0;
-  std::vector<halo_item> items;
-  build_items_merged(pw, uw, mix != 0, items);
-  halo_item* d = (halo_item*)pw.d_items;
-  const int rc = upload_items(items, &d);
-  pw.d_items = d;
+  const int order = merged_order_of(ctx);
+  if (pw.merged_with == (const void*)&uw && pw.merged_order == order) return 0;
+  unit_list L;
+  build_items_merged(pw, uw, order, L);
+  const int rc = upload_units(L, &pw.d_items, &pw.d_item_list, &pw.d_unit_first);
   if (rc != 0) { pw.merged_with = nullptr; return rc; }
-  pw.n_items = (int)items.size(); pw.merged_with = &uw; pw.merged_mix = mix;
+  pw.n_units = L.units(); pw.merged_with = &uw; pw.merged_order = order;
   return 0;
 }
 
@@ -964,7 +1024,7 @@ static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev&
   memset(&A, 0, sizeof(A));
   A.psegs[0] = A.psegs[1] = pw.d_segs;
   A.usegs[0] = A.usegs[1] = uw.d_segs;
-  A.items = (const halo_item*)pw.d_items; A.n_items = pw.n_items; A.n_pack_items = 0;
+  A.items = pw.d_item_list; A.unit_first = pw.d_unit_first; A.n_units = pw.n_units; A.n_pack_units = 0;
   A.npsegs = pw.nsegs; A.nusegs = uw.nsegs;
   return launch_items<false>(ctx, RPB_K_HALO_PACKING_FUSED, A, st);
 }
@@ -1112,14 +1172,14 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
   }
   RPB_CHECK(cudaMemcpy(p->d_pack_msgs, pm.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
   RPB_CHECK(cudaMemcpy(p->d_unpack_msgs, um.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
-  cudaFree(p->d_items_xchg); p->d_items_xchg = nullptr; p->n_items_xchg = 0;
+  p->n_units_xchg = 0;
   if (!p->vars.empty() && NNB * p->nvars <= ITEMS_MAX_SEGS) {
-    std::vector<halo_item> items;
+    unit_list L;
     int n_pack = 0;
-    build_items_xchg(p->xpack_wl[0], p->xunpack_wl[0], items, &n_pack);
-    const int rc = upload_items(items, &p->d_items_xchg);
+    build_items_xchg(p->xpack_wl[0], p->xunpack_wl[0], L, &n_pack);
+    const int rc = upload_units(L, &p->d_xchg_block, &p->d_items_xchg, &p->d_unit_first_xchg);
     if (rc != 0) return rc;
-    p->n_items_xchg = (int)items.size(); p->n_pack_items_xchg = n_pack;
+    p->n_units_xchg = L.units(); p->n_pack_units_xchg = n_pack;
   }
   p->connected = true;
   return 0;
@@ -1205,7 +1265,7 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
     const int rc = rpb200_halo_exchange_pack(p, s);
     return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
   }
-  if (!p->d_items_xchg) {       // more tuples than the item kernel keeps in shared memory: two launches
+  if (!p->d_items_xchg || p->n_units_xchg == 0) {       // more tuples than the item kernel keeps in shared memory: two launches
     const int rc = rpb200_halo_exchange_pack(p, s);
     return rc != 0 ? rc : rpb200_halo_exchange_unpack(p, s);
   }
@@ -1213,7 +1273,7 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
   memset(&A, 0, sizeof(A));
   A.psegs[0] = p->xpack_wl[0].d_segs; A.psegs[1] = p->xpack_wl[1].d_segs;
   A.usegs[0] = p->xunpack_wl[0].d_segs; A.usegs[1] = p->xunpack_wl[1].d_segs;
-  A.items = p->d_items_xchg; A.n_items = p->n_items_xchg; A.n_pack_items = p->n_pack_items_xchg;
+  A.items = p->d_items_xchg; A.unit_first = p->d_unit_first_xchg; A.n_units = p->n_units_xchg; A.n_pack_units = p->n_pack_units_xchg;
   A.npsegs = p->xpack_wl[0].nsegs; A.nusegs = p->xunpack_wl[0].nsegs;
   A.pmsgs = p->d_pack_msgs; A.umsgs = p->d_unpack_msgs; A.msg_done = p->d_msg_done; A.d_epoch = p->d_epoch;
   A.unpack_done = p->d_unpack_done; A.error = p->d_error; A.timeout_ns = halo_timeout_ns();

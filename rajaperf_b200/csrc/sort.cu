@@ -246,13 +246,15 @@ sort_hist_lanes_kernel(const unsigned long long* __restrict__ keys, int64_t n, u
   }
 }
 
-// exclusive scan of each digit histogram in place: g_hist[p][b] = #keys with digit_p < b
+// exclusive scan of each digit histogram in place: g_hist[p][b] = #keys with digit_p < b; skewed[p] = 1 if one digit of pass p
+// holds at least a quarter of the keys (then uniform tiles are likely and the pass tests for them)
 __global__ void __launch_bounds__(RADIX)
-sort_hist_scan_kernel(unsigned long long* __restrict__ g_hist)
+sort_hist_scan_kernel(unsigned long long* __restrict__ g_hist, unsigned int* __restrict__ skewed, unsigned long long n)
 {
   __shared__ unsigned long long s[RADIX];
   const int p = blockIdx.x, b = threadIdx.x;
   const unsigned long long c = g_hist[p * RADIX + b];
+  if (4ull * c >= n) skewed[p] = 1u;                 // cleared per call with the histograms
   s[b] = c;
   __syncthreads();
   for (int o = 1; o < RADIX; o <<= 1) {
@@ -293,7 +295,7 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
                      const unsigned long long* __restrict__ vals_in, unsigned long long* __restrict__ vals_out,
                      int64_t n, int shift, const unsigned long long* __restrict__ g_base /*[RADIX]*/,
                      unsigned long long* __restrict__ desc, unsigned int* __restrict__ ticket,
-                     unsigned int num_tiles, unsigned int parity)
+                     unsigned int num_tiles, unsigned int parity, const unsigned int* __restrict__ skewed)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_keys = reinterpret_cast<unsigned long long*>(smem_raw);            // [TILE]
@@ -337,24 +339,36 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
   }
 
   // ---- uniform tile?  every key of the tile has the digit of the tile's first key (full tiles only: the padding of the
-  // last tile carries digit 0xff).  One vote per warp, one word per warp in shared memory, one barrier.
+  // last tile carries digit 0xff).  Tested only in passes whose histogram is skewed enough for such tiles to be likely
+  // (`skewed`: some digit holds at least a quarter of the keys, sort_hist_scan_kernel), and cheaply: OR the XOR of every key
+  // with the thread's first key (one LOP3 per key on the 32-bit half that holds the digit), look at the digit's bits once,
+  // one vote per warp, one word per warp in shared memory, one barrier.
   __shared__ unsigned int s_wdigit[SORT_WARPS];
-  {
+  bool uniform = false;                                    // CTA-uniform
+  if (skewed[0] != 0u) {
     const unsigned int d0 = __shfl_sync(0xffffffffu, key_digit(key[0], shift), 0);
-    bool same = full;
+    const bool hi = (shift & 32) != 0;
+    const unsigned int w0 = hi ? (unsigned int)(key[0] >> 32) : (unsigned int)key[0];
+    unsigned int diff = 0;
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) same = same && (key_digit(key[r], shift) == d0);
+    for (int r = 1; r < SORT_IPT; ++r) diff |= (hi ? (unsigned int)(key[r] >> 32) : (unsigned int)key[r]) ^ w0;
+    bool same = full && ((diff >> (shift & 31)) & (RADIX - 1)) == 0u && key_digit(key[0], shift) == d0;
     same = __all_sync(0xffffffffu, same);
     if (lane == 0) s_wdigit[warp] = same ? d0 : 0xffffffffu;
-  }
-  __syncthreads();
-  unsigned int udigit = s_wdigit[0];
+    __syncthreads();
+    unsigned int udig = s_wdigit[0];
 #pragma unroll
-  for (int w = 1; w < SORT_WARPS; ++w) udigit = (s_wdigit[w] == udigit) ? udigit : 0xffffffffu;
-  const bool uniform = udigit != 0xffffffffu;             // CTA-uniform
+    for (int w = 1; w < SORT_WARPS; ++w) udig = (s_wdigit[w] == udig) ? udig : 0xffffffffu;
+    uniform = udig != 0xffffffffu;
+  }
+  const unsigned int udigit = uniform ? s_wdigit[0] : 0u;
 
-  // ---- rank inside the warp chunk (stable): match-any on the digit.  Two 16-bit ranks per register.
-  unsigned int rank2[SORT_IPT / 2];
+  // ---- rank inside the warp chunk (stable): match-any on the digit.  The pairs kernel keeps two 16-bit ranks (and, below,
+  // positions) per register: its value loads need the registers (no spills: 80-88 bytes before); the keys kernel is bound
+  // by instruction issue and keeps one per register (the packing costs ~4 instructions per key: 3 % of a pass, measured).
+  constexpr int RK = PAIRS ? SORT_IPT / 2 : SORT_IPT;
+  unsigned int rank2[RK];
+  auto rank_get = [&](int r) { return PAIRS ? ((rank2[r >> 1] >> ((r & 1) * 16)) & 0xffffu) : rank2[r]; };
   unsigned int* my_cnt = s_cnt + warp * RADIX;
   if (!uniform) {
 #pragma unroll
@@ -366,7 +380,8 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
       if (lane == leader) { before = my_cnt[d]; my_cnt[d] = before + __popc(peers); }
       before = __shfl_sync(0xffffffffu, before, leader);
       const unsigned int rk = before + __popc(peers & lt_mask);
-      rank2[r >> 1] = (r & 1) ? (rank2[r >> 1] | (rk << 16)) : rk;
+      if (PAIRS) rank2[r >> 1] = (r & 1) ? (rank2[r >> 1] | (rk << 16)) : rk;
+      else rank2[r] = rk;
       __syncwarp();
     }
     __syncthreads();
@@ -443,13 +458,13 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
     return;
   }
 
-  // ---- reorder by digit in shared memory (positions: two 16-bit values per register)
-  unsigned int pos2[SORT_IPT / 2];
+  // ---- reorder by digit in shared memory (pairs: the positions are kept, two 16-bit values per register)
+  unsigned int pos2[PAIRS ? SORT_IPT / 2 : 1];
 #pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
     const unsigned int d = key_digit(key[r], shift);
-    const unsigned int ps = s_bin_start[d] + my_cnt[d] + ((rank2[r >> 1] >> ((r & 1) * 16)) & 0xffffu);
-    pos2[r >> 1] = (r & 1) ? (pos2[r >> 1] | (ps << 16)) : ps;
+    const unsigned int ps = s_bin_start[d] + my_cnt[d] + rank_get(r);
+    if (PAIRS) pos2[r >> 1] = (r & 1) ? (pos2[r >> 1] | (ps << 16)) : ps;
     s_keys[ps] = key[r];
     if (PAIRS) s_digit[ps] = (unsigned char)d;
   }
@@ -530,7 +545,7 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
       sort_hist_kernel<<<grid, 512, 0, st>>>((const unsigned long long*)keys, n, hist, rpb_aligned(keys, 32) ? 1 : 0);
     }
     RPB_LAUNCH_CHECK();
-    sort_hist_scan_kernel<<<NUM_PASSES, RADIX, 0, st>>>(hist);
+    sort_hist_scan_kernel<<<NUM_PASSES, RADIX, 0, st>>>(hist, ctrs + 2 * NUM_PASSES, (unsigned long long)n);
     RPB_LAUNCH_CHECK();
   }
 
@@ -547,11 +562,11 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
     const unsigned int parity = (unsigned int)(p & 1);
     const int shift = p * RADIX_BITS;
     if (p == 0)
-      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
     else if (p == NUM_PASSES - 1)
-      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
     else
-      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity);
+      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
     RPB_LAUNCH_CHECK();
     unsigned long long* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Multi-GPU parity check, launched by torchrun (one rank per GPU):
-  * HALO_EXCHANGE_FUSED on the default rank grid vs the CPU simulation of the same grid (bit-exact)
-  * global DOT / REDUCE_SUM: shards + one all-reduced scalar vs the oracle on the whole array."""
+  * HALO_EXCHANGE_FUSED on the default rank grid vs the CPU simulation of the same grid (bit-exact), in both launch forms
+    (pack launch + unpack launch; ONE launch over the item list)
+  * global DOT / REDUCE_SUM: shards + one all-reduced scalar vs the oracle on the whole array.
+Rank 0 prints `MGPU_CHECK PASS|FAIL ...` and one JSON line with what was compared (tools/gpu_r02_mgpu.sh keeps both)."""
+import json
 import os
 import sys
 
@@ -23,7 +26,10 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = Context(local)
 pd = rdist.rank_grid(world)
 ok = True
-for dims, hw, nv, reps in (((6, 6, 6), 1, 3, 3), ((40, 40, 40), 2, 2, 4), ((128, 128, 128), 1, 3, 5)):
+cases = []
+for unroll, dims, hw, nv, reps in [(u,) + c for u in (2, 1) for c in (((6, 6, 6), 1, 3, 3), ((40, 40, 40), 2, 2, 4), ((128, 128, 128), 1, 3, 5),
+                                                                        ((252, 252, 252), 1, 3, 2))]:
+    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=unroll)
     plan = ctx.halo_plan(dims, hw, nv, rank, pd)
     vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
     rdist.connect_halo_plan(plan, vs)
@@ -40,6 +46,8 @@ for dims, hw, nv, reps in (((6, 6, 6), 1, 3, 3), ((40, 40, 40), 2, 2, 4), ((128,
             print(f"rank {rank}: halo mismatch dims={dims} var={v}", flush=True)
     dist.barrier()
     plan.close()
+    cases.append({"launches_per_rep": 1 if unroll == 1 else 2, "cells": list(dims), "halo_width": hw, "vars": nv, "reps": reps})
+ctx.reset_tuning("Comm_HALO_EXCHANGE_FUSED")
 
 n = 3000001
 d = sd.stream_dot(n)
@@ -62,5 +70,8 @@ flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("MGPU_CHECK", "PASS" if flag.item() == 1 else "FAIL", f"world={world} grid={pd}", flush=True)
+    print(json.dumps({"mgpu_check": "PASS" if flag.item() == 1 else "FAIL", "world": world, "rank_grid": pd,
+                      "halo_exchange_cases_bit_exact_vs_cpu_simulation": cases,
+                      "sharded_dot_and_reduce_sum_vs_oracle": {"n": n, "tolerance_abs": 1e-7}}), flush=True)
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)

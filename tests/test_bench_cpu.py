@@ -75,3 +75,26 @@ def test_measured_peak_falls_back_to_the_profiling_guide_number(bench, monkeypat
     (tmp_path / "MEASURED_PEAKS.json").write_text(json.dumps({"hbm_gbs": 6554.9}))
     peak, src = bench.measured_peak()
     assert peak == 6554.9 and "measured" in src
+
+
+def test_ncu_traffic_is_refused_unless_it_is_of_the_launch_this_run_makes(bench, monkeypatch, tmp_path):
+    """roofline.traffic comes from an ncu capture of the same kernel at the same size and launch shape, or it is null."""
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    (prof / "r02_ncu_traffic.json").write_text(json.dumps({
+        "Stream_TRIAD": {"kernel_name": "stream_ew_kernel<3, 2>", "n": 1 << 28, "tuning": [512, 0, 2],
+                         "dram_bytes_per_launch": 6.4e9, "commit": "abc1234"}}))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+
+    class Ctx:
+        def __init__(self, t): self.t = t
+        def get_tuning(self, kernel): return self.t
+
+    got, src = bench.ncu_traffic(Ctx((512, 0, 2)), "Stream_TRIAD", 1 << 28)
+    assert got == 6.4e9 and "stream_ew_kernel<3, 2>" in src and "abc1234" in src
+    got, why = bench.ncu_traffic(Ctx((256, 8, 4)), "Stream_TRIAD", 1 << 28)
+    assert got is None and "launch shape" in why
+    got, why = bench.ncu_traffic(Ctx((512, 0, 2)), "Stream_TRIAD", 1 << 20)
+    assert got is None and "n =" in why
+    got, why = bench.ncu_traffic(Ctx((512, 0, 2)), "Stream_COPY", 1 << 28)
+    assert got is None and "no ncu capture" in why

@@ -66,7 +66,7 @@ def test_grid_dims_follow_the_reference_truncation():
         assert cabi.halo_grid_dims(target) == d.tolist()
 
 
-FORMS = ["two_launches", "one_launch", "one_launch_x_first", "one_launch_generic"]
+FORMS = ["two_launches", "one_launch", "one_launch_x_first", "one_launch_two_phases", "one_launch_generic"]
 
 
 def run_packing_fused(ctx, d, reps, form="two_launches"):
@@ -84,8 +84,8 @@ def run_packing_fused(ctx, d, reps, form="two_launches"):
             [(bufs[l].data_ptr() + 8 * v * plan.neighbors[l][which + "_len"], plan.neighbors[l]["d_" + which + "_list"],
               vars_[v], plan.neighbors[l][which + "_len"], l) for l in range(26) for v in range(nv)])
         wls = (mk(pb, "pack"), mk(ub, "unpack"))
-    if form == "one_launch_x_first":
-        ctx.set_tuning("Comm_HALO_PACKING_FUSED", unroll=3)
+    if form in ("one_launch_x_first", "one_launch_two_phases"):
+        ctx.set_tuning("Comm_HALO_PACKING_FUSED", unroll=3 if form == "one_launch_x_first" else 5)
     try:
         for _ in range(reps):
             if form == "two_launches":

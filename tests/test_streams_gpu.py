@@ -70,6 +70,8 @@ def test_four_streams_reductions_scans_indexlists_concurrently(ctx):
         want = np.full(n, -1, dtype=np.int32)
         k = L.orc_indexlist(a, want, n)
         assert ln[i].item() == k and np.array_equal(lst[i].cpu().numpy(), want), i
+    for st in streams:
+        ctx.stream_detach(st.cuda_stream)
 
 
 @pytest.mark.parametrize("n", [200003, (1 << 23) + 48])     # register-staged kernels; TMA-staged kernels (n >= 2 * 8192 * SMs)
@@ -82,9 +84,13 @@ def test_one_scan_graph_replayed_with_new_inputs(ctx, n):
     ln = torch.zeros(1, dtype=torch.int64, device="cuda")
     ctx.scan_reserve(n)                              # a capture may not allocate (rpb200.h)
     ctx.indexlist_reserve(n)
+    # the capture stream gets its scratch set BEFORE the capture starts: this session's context has served more streams than
+    # it pre-allocates sets for, and a capture may not allocate (rpb200.h, rpb200_stream_attach)
+    cap = torch.cuda.Stream()
+    ctx.stream_attach(cap.cuda_stream)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=cap):
         ctx.scan_exclusive(x, y)                     # ONE scan and ONE index list in the graph
         ctx.indexlist(x, lst, ln)
     for rep in range(4):
@@ -102,6 +108,8 @@ def test_one_scan_graph_replayed_with_new_inputs(ctx, n):
     ctx.scan_exclusive(x, y)
     torch.cuda.synchronize()
     assert np.array_equal(bits(y.cpu().numpy()), bits(ref))
+    del g
+    ctx.stream_detach(cap.cuda_stream)
 
 
 def test_reduction_graph_replayed_with_new_inputs(ctx):
@@ -110,8 +118,11 @@ def test_reduction_graph_replayed_with_new_inputs(ctx):
     rng = np.random.default_rng(5)
     a = torch.zeros(n, dtype=torch.float64, device="cuda"); b = torch.zeros_like(a)
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    cap = torch.cuda.Stream()
+    ctx.stream_attach(cap.cuda_stream)
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=cap):
         for _ in range(3):
             ctx.stream_dot(a, b, out, accumulate=True)     # DOT-Seq.cpp:45: m_dot += dot, three reps in one graph
     for rep in range(3):
@@ -120,6 +131,8 @@ def test_reduction_graph_replayed_with_new_inputs(ctx):
         g.replay()
         torch.cuda.synchronize()
         assert out.item() == 3.0 * L.orc_stream_dot(ha, hb, n, 0.0)
+    del g
+    ctx.stream_detach(cap.cuda_stream)
 
 
 def test_pa_kernels_on_two_streams_with_different_bases(ctx):
@@ -148,6 +161,8 @@ def test_pa_kernels_on_two_streams_with_different_bases(ctx):
         for _ in range(5):
             L.orc_mass3dpa(B, Bt, D, X, ref, NE)
         assert np.array_equal(bits(dY.cpu().numpy()), bits(ref)), i
+    for st in streams:
+        ctx.stream_detach(st.cuda_stream)
 
 
 def test_more_streams_than_preallocated_sets_and_detach(ctx):
@@ -156,7 +171,7 @@ def test_more_streams_than_preallocated_sets_and_detach(ctx):
     a = np.random.default_rng(9).integers(-5, 5, n).astype(np.float64)
     d_a = dev(a)
     want = L.orc_reduce_sum(a, n, 0.0)
-    streams = [torch.cuda.Stream() for _ in range(7)]
+    streams = [torch.cuda.Stream() for _ in range(11)]          # more than the 8 pre-allocated scratch sets
     outs = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in streams]
     torch.cuda.synchronize()
     for st, o in zip(streams, outs):

@@ -238,7 +238,7 @@ def test_every_tuning_of_every_kernel_reproduces_the_default_checksum(tmp_path):
     assert seen["Stream_TRIAD"] == ["Base_B200-default", "Base_B200-block_256", "Base_B200-persistent_8"]
     assert seen["Stream_DOT"] == ["Base_B200-default", "Base_B200-block_512"]
     assert len(seen["Apps_MASS3DPA"]) == 3 and len(seen["Apps_CONVECTION3DPA"]) == 3 and len(seen["Polybench_GEMM"]) == 3
-    assert seen["Comm_HALO_PACKING_FUSED"] == ["Base_B200-default", "Base_B200-x_first", "Base_B200-two_launches", "Base_B200-two_launches_forward",
+    assert seen["Comm_HALO_PACKING_FUSED"] == ["Base_B200-default", "Base_B200-x_first", "Base_B200-two_phases", "Base_B200-two_launches", "Base_B200-two_launches_forward",
                                                 "Base_B200-two_launches_round_robin"]
     timing = open(os.path.join(tmp_path, "RAJAPerf-timing-Minimum.csv")).read().splitlines()
     cols = [c.strip() for c in timing[1].split(",")]

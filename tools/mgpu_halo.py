@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """HALO_EXCHANGE_FUSED time per rep on the N-rank grid for several launch tunings (torchrun, one rank per GPU):
-block_size 256/128 = contiguous / round-robin chunks, unroll 1 = one fused launch, 2 = pack launch + unpack launch."""
+unroll 1 = ONE launch over the item list (pack items, signal, wait + unpack items), 2 = pack launch + unpack launch
+(block_size 192: packs walk backwards); G=512 (default) or G=1024 cells per GPU and dimension.  After every timed form the
+ghost cells of every variable are compared with their periodic images on every rank (`verified`)."""
 import json, os, sys
 import torch
 import torch.distributed as dist
@@ -44,13 +46,32 @@ def graph_ms(body, reps=100):
         best = min(best, ms)
     return best
 
-res = {}
-for blk, cps, xu in ((256, 4, 2), (192, 4, 2), (192, 8, 2)):
-    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
-    ms = graph_ms(plan.exchange)
-    plan.status()
-    res[f"{'rr' if blk == 128 else ('rv' if blk == 192 else 'ct')}{cps}/{'1L' if xu == 1 else '2L'}"] = round(ms * 1e3, 1)
+def verified():
+    e = g + 2
+    idx = torch.arange(e, device=dev)
+    src = ((idx - 1) % g) + 1
+    want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64)
+    ok = all(bool(torch.equal(vars_[v].view(e, e, e), want + v)) for v in range(nv))
+    if world > 1:
+        t = torch.tensor([0.0 if ok else 1.0], **f64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ok = t.item() == 0.0
+    return bool(ok)
+
+res, ver = {}, {}
+reps = 100 if g <= 512 else 40
+for rnd in range(2):
+    for blk, cps, xu in ((192, 4, 2), (192, 4, 1), (192, 3, 1)):
+        ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
+        for v in range(nv):                                     # fresh ghost cells: the check must see THIS form's work
+            vars_[v].copy_(torch.arange(plan.var_size, **f64) + v)
+            e = g + 2
+            a = vars_[v].view(e, e, e)
+            a[0].fill_(-1.0); a[-1].fill_(-1.0); a[:, 0].fill_(-1.0); a[:, -1].fill_(-1.0); a[:, :, 0].fill_(-1.0); a[:, :, -1].fill_(-1.0)
+        ms = graph_ms(plan.exchange, reps)
+        plan.status()
+        key = f"{'1 launch' if xu == 1 else '2 launches'}, {cps} CTAs/SM"
+        res[key] = min(res.get(key, 1e9), round(ms * 1e3, 1))
+        ver[key] = ver.get(key, True) and verified()
 if rank == 0:
-    print(json.dumps({"n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": g, "us_per_rep": res}), flush=True)
+    print(json.dumps({"n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": g, "us_per_rep": res, "verified": ver}), flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

@@ -49,10 +49,14 @@ KERNELS = {
     "Apps_MASS3DPA": (500000000, 20, "Base_CUDA", "block_25"),
     "Apps_DIFFUSION3DPA": (256000000, 20, "Base_CUDA", "block_64"),
     "Apps_CONVECTION3DPA": (256000000, 20, "Base_CUDA", "block_64"),
-    "Apps_LTIMES": (1024000000, 10, "Base_CUDA", "block_256"),
+    "Apps_LTIMES": (1024000000, 20, "Base_CUDA", "block_256"),
     "Comm_HALO_PACKING_FUSED": (1 << 27, 200, "Base_CUDA", "direct_1024"),
 }
 CHECK_REPS = {"Algorithm_SORT": 2, "Algorithm_SORTPAIRS": 2, "Apps_LTIMES": 1}   # Base_Seq at these sizes: 12-25 s per rep
+# The reference's own LTIMES GPU variants launch a 3-D grid with gridDim.z = num_z (LTIMES-Cuda.cpp:44-102): beyond
+# num_z = 65535 the launch fails ("invalid configuration argument", r02_a / r02_b logs), so the incumbent cannot run the
+# BASELINE size (num_z = 500000).  Its timing phase uses the largest size the reference can launch: num_z = 65535.
+TIMING_SIZE = {"Apps_LTIMES": 65535 * 2048}
 
 
 def run(cmd, log, timeout):
@@ -145,11 +149,9 @@ def main():
         for k in names:
             _, reps, var, tune = KERNELS[k]
             odir = os.path.join(a.out, "timing_" + k)
-            # LTIMES: the reference's own warm-up kernel (Basic_DAXPY, Base_CUDA) aborts with "invalid configuration argument"
-            # at --size 1024000000 (r02_a), so this one kernel is timed without the warm-up phase
-            extra = ["--disable-warmup"] if k == "Apps_LTIMES" else []
-            rc, sec = run([EXE, "-k", k, "-v", var, "Base_B200", "-t", tune, "default", "--size", str(size(k)), "--checkrun",
-                           str(reps), "--outdir", odir] + extra, odir + ".log", a.timeout)
+            tsize = TIMING_SIZE.get(k, KERNELS[k][0]) // (64 if a.quick else 1)
+            rc, sec = run([EXE, "-k", k, "-v", var, "Base_B200", "-t", tune, "default", "--size", str(tsize), "--checkrun",
+                           str(reps), "--outdir", odir], odir + ".log", a.timeout)
             row = collect(odir, [k])[k]
             row.update(rc=rc, wall_s=sec, incumbent=f"{var}-{tune}")
             ms = row.get("ms_per_rep", {})

@@ -96,16 +96,10 @@ def halo(g):
     for rnd in range(2):
         ctx.set_tuning(K, 192, 4, 2)
         report(f"halo{g} pack+unpack TWO launches (r01 default) round {rnd}", 40 * ne, graph_ms(lambda: (plan.pack(), plan.unpack())))
-        for cps in (4, 3, 2):
-            for order, label in ((1, "mixed"), (3, "x first")):
+        for cps in (4, 3):
+            for order, label in ((1, "x units mixed in"), (3, "x units first"), (5, "two phases")):
                 ctx.set_tuning(K, 192, cps, order)
                 report(f"halo{g} pack+unpack ONE launch, {label}, {cps} CTAs/SM round {rnd}", 40 * ne, graph_ms(plan.pack_unpack))
-    for gran in (32, 128, 64):
-        rc, got = set_l2_fetch(gran)
-        ctx.set_tuning(K, 192, 4, 1)
-        report(f"halo{g} pack+unpack ONE launch, mixed, 4 CTAs/SM, L2 fetch granularity {got} (rc {rc})", 40 * ne, graph_ms(plan.pack_unpack))
-        ctx.set_tuning(K, 192, 4, 2)
-        report(f"halo{g} pack+unpack TWO launches, L2 fetch granularity {got}", 40 * ne, graph_ms(lambda: (plan.pack(), plan.unpack())))
     ctx.reset_tuning(K)
     X = "Comm_HALO_EXCHANGE_FUSED"
     for rnd in range(2):
