@@ -74,7 +74,7 @@ int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
  *       eviction-priority hints on.  One-launch forms (rpb200_halo_plan_pack_unpack, rpb200_halo_exchange): ctas_per_sm;
  *       exchange unroll 1 = ONE launch per rep over the item list, 2 / 4 = pack launch + unpack launch;
  *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 8 = digit histograms in shared bins instead of the lane-private 16-bit
- *       counters (default since round 2: profiles/r02_a_optin.log);
+ *       counters (default since round 2: profiles/r02_a_optin.log); 7 = no pass tests its tiles for uniformity;
  *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
  *   Apps_LTIMES: ctas_per_sm; unroll 5..8 = psi staged through a bulk-async ring, 10 = row-chunk A fragments, else line-major (default);
  *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.
@@ -195,6 +195,14 @@ int rpb200_halo_unpack(rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t
  * builds and uploads the merged item list (synchronises: make it before capturing into a graph); see
  * rpb200_halo_plan_pack_unpack below for what the item order buys.                                                      */
 int rpb200_halo_pack_unpack(rpb200_ctx*, rpb200_halo_worklist* pack, rpb200_halo_worklist* unpack, rpb200_stream_t);
+/* Test hook, host-only (no device is touched): the unit list the one-launch kernels walk for tuples of the given geometry
+ * (lengths, strided flags, message ordinals, variable ids).  order 1 / 3 / 5 = the HALO_PACKING_FUSED orders (x units mixed
+ * in / first / two phases), 0 = the exchange order.  items_out: (tuple index | 1 << 30 for the unpack side, chunk) pairs;
+ * unit_first_out: n_units + 1 entries.  Lets the CPU test-suite check that every (tuple, chunk) is moved exactly once.   */
+int rpb200_debug_halo_units(const int64_t* pack_len, const int* pack_strided, const int* pack_msg, const int* pack_var, int npack,
+                            const int64_t* unpack_len, const int* unpack_strided, const int* unpack_msg, const int* unpack_var,
+                            int nunpack, int order, int* items_out, int max_items, int* unit_first_out, int max_units,
+                            int* n_items, int* n_units, int* n_pack_units);
 
 /* (2) HALO_base: the 26-neighbour periodic decomposition and its index lists
  *     (comm/HALO_base.cpp:31-35 grid dims, :82-116 offsets, :118-166 extents, :169-291

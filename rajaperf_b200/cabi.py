@@ -67,6 +67,9 @@ SIGNATURES = {
     "rpb200_halo_pack": (c_int, [_P, _P, _P]),
     "rpb200_halo_unpack": (c_int, [_P, _P, _P]),
     "rpb200_halo_pack_unpack": (c_int, [_P, _P, _P, _P]),
+    "rpb200_debug_halo_units": (c_int, [POINTER(c_int64), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int,
+                                        POINTER(c_int64), POINTER(c_int), POINTER(c_int), POINTER(c_int), c_int, c_int,
+                                        POINTER(c_int), c_int, POINTER(c_int), c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "rpb200_halo_grid_dims": (None, [c_int64, POINTER(c_int64)]),
     "rpb200_halo_plan_create": (c_int, [_P, POINTER(c_int64), c_int64, c_int, c_int, POINTER(c_int), POINTER(_P)]),
     "rpb200_halo_plan_destroy": (None, [_P]),

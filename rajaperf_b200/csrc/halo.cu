@@ -394,7 +394,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
 
   // ---- phase 2: wait + unpack.  The grid is fully co-resident and phase 1 never waits, so every rank's flags are
   // eventually released.  A message that does not arrive within the time-out is NOT unpacked and the epoch is NOT committed.
-  int waited_msg = -1;
+  unsigned int acquired = 0u;            // bit m: this CTA has already seen message m's flag (thread-uniform)
   bool failed = false;
   {
     halo_item h, nh;
@@ -404,7 +404,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
       const cursor n = cursor_next(c, A.n_units);
       fetch(n.u < A.n_units ? n.it : 1, n.u < A.n_units ? n.it + 1 : 0, nidx, nh);
       const int m = s_seg[1][h.seg & (ITEM_UNPACK - 1)].msg;
-      if (m != waited_msg) {
+      if (!((acquired >> m) & 1u)) {       // first item of message m in this CTA: acquire its flag (units alternate between messages)
         if (threadIdx.x == 0) {
           const unsigned long long* f = A.umsgs[m].my_flag;
           unsigned long long t0 = 0, t1 = 0;
@@ -420,7 +420,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
         __syncthreads();
         failed = failed || (s_ok == 0);
         __syncthreads();
-        waited_msg = m;
+        acquired |= 1u << m;
       }
       if (!failed) move(h, idx);
 #pragma unroll
@@ -860,8 +860,9 @@ struct unit_list {
   std::vector<int> first;                              // first[u]; the end sentinel is appended by finish()
   void add_unit(const std::vector<halo_item>& g) { if (g.empty()) return; first.push_back((int)items.size()); items.insert(items.end(), g.begin(), g.end()); }
   void add_singles(const std::vector<halo_item>& g) { for (const halo_item& h : g) { first.push_back((int)items.size()); items.push_back(h); } }
-  int units() const { return (int)first.size(); }
-  void finish() { first.push_back((int)items.size()); }
+  bool finished = false;
+  int units() const { return (int)first.size() - (finished ? 1 : 0); }
+  void finish() { first.push_back((int)items.size()); finished = true; }
 };
 
 // streaming groups of one list: for every message (run of consecutive tuples with the same msg), chunk-major
@@ -1027,6 +1028,40 @@ static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev&
   A.items = pw.d_item_list; A.unit_first = pw.d_unit_first; A.n_units = pw.n_units; A.n_pack_units = 0;
   A.npsegs = pw.nsegs; A.nusegs = uw.nsegs;
   return launch_items<false>(ctx, RPB_K_HALO_PACKING_FUSED, A, st);
+}
+
+// Host-only: the unit list the one-launch kernels would walk for tuples of the given geometry (no device memory is touched, so
+// the CPU test-suite checks the builders: every (tuple, chunk) exactly once, units well-formed, pack units before unpack units
+// for the exchange).  order: 1 / 3 / 5 = the HALO_PACKING_FUSED orders, 0 = the exchange order.
+extern "C" int rpb200_debug_halo_units(const int64_t* pack_len, const int* pack_strided, const int* pack_msg, const int* pack_var, int npack,
+                                       const int64_t* unpack_len, const int* unpack_strided, const int* unpack_msg, const int* unpack_var,
+                                       int nunpack, int order, int* items_out, int max_items, int* unit_first_out, int max_units,
+                                       int* n_items, int* n_units, int* n_pack_units)
+{
+  if (npack < 0 || nunpack < 0 || !n_items || !n_units) return RPB200_EINVAL;
+  worklist_dev pw, uw;
+  auto fill = [](worklist_dev& w, const int64_t* len, const int* strided, const int* msg, const int* var, int n) {
+    w.nsegs = n;
+    for (int i = 0; i < n; ++i) {
+      rpb200_halo_seg s;
+      memset(&s, 0, sizeof(s));
+      s.len = len[i]; s.msg = msg[i]; s.flags = strided[i] ? SEG_STRIDED : 0;
+      s.var = reinterpret_cast<double*>((uintptr_t)(var[i] + 1) * 4096);      // identity of the variable only
+      w.h_segs.push_back(s);
+    }
+  };
+  fill(pw, pack_len, pack_strided, pack_msg, pack_var, npack);
+  fill(uw, unpack_len, unpack_strided, unpack_msg, unpack_var, nunpack);
+  unit_list L;
+  int npu = 0;
+  if (order == 0) build_items_xchg(pw, uw, L, &npu);
+  else build_items_merged(pw, uw, order, L);
+  *n_items = (int)L.items.size(); *n_units = L.units();
+  if (n_pack_units) *n_pack_units = npu;
+  if ((int)L.items.size() > max_items || (int)L.first.size() > max_units + 1) return RPB200_EINVAL;
+  for (size_t i = 0; i < L.items.size(); ++i) { items_out[2 * i] = L.items[i].seg; items_out[2 * i + 1] = L.items[i].chunk; }
+  for (size_t i = 0; i < L.first.size(); ++i) unit_first_out[i] = L.first[i];
+  return 0;
 }
 
 extern "C" int rpb200_halo_pack_unpack(rpb200_ctx* ctx, rpb200_halo_worklist* pack, rpb200_halo_worklist* unpack, rpb200_stream_t s)

@@ -556,17 +556,20 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
   RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+  // skew[p] != 0: pass p tests its tiles for uniformity; skew[NUM_PASSES] is never set (tuning `unroll` 7: no pass tests)
+  const unsigned int* skew = ctrs + 2 * NUM_PASSES;
+  const bool no_uniform = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll == 7;
   unsigned long long* kin = (unsigned long long*)keys; unsigned long long* kout = alt_keys;
   unsigned long long* vin = (unsigned long long*)vals; unsigned long long* vout = alt_vals;
   for (int p = 0; p < NUM_PASSES; ++p) {
     const unsigned int parity = (unsigned int)(p & 1);
     const int shift = p * RADIX_BITS;
     if (p == 0)
-      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
+      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
     else if (p == NUM_PASSES - 1)
-      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
+      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
     else
-      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, ctrs + 2 * NUM_PASSES + p);
+      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
     RPB_LAUNCH_CHECK();
     unsigned long long* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;

@@ -1,0 +1,119 @@
+"""CPU: the unit lists the one-launch halo kernels walk (csrc/halo.cu: build_items_merged / build_items_xchg), through the
+host-only hook rpb200_debug_halo_units -- no GPU is touched.
+
+Checked for HALO_base geometries (the tuples of rpb200_halo_plan_bind: neighbour-major, variable-minor) and for ragged generic
+tuples: every (tuple, chunk) of both lists appears EXACTLY once; units are well-formed; the four x-face chunks of a variable
+form one unit; the exchange order keeps every pack unit before every unpack unit; and a Python model of the kernel's cursor
+(CTA b walks units b, b + G, ...) visits every item exactly once for several grid sizes."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import suite_data as sd
+
+CHUNK = 2048
+UNPACK = 1 << 30
+
+
+def units(pack, unpack, order):
+    """pack / unpack: lists of (len, strided, msg, var) -> (items [(seg, chunk)], unit_first, n_pack_units)"""
+    from rajaperf_b200 import cabi
+    lib = cabi.load()
+
+    def cols(t):
+        n = len(t)
+        return ((ctypes.c_int64 * max(n, 1))(*[x[0] for x in t]), (ctypes.c_int * max(n, 1))(*[x[1] for x in t]),
+                (ctypes.c_int * max(n, 1))(*[x[2] for x in t]), (ctypes.c_int * max(n, 1))(*[x[3] for x in t]), n)
+    p, u = cols(pack), cols(unpack)
+    total = sum(-(-x[0] // CHUNK) for x in pack + unpack)
+    items = (ctypes.c_int * (2 * total + 2))()
+    first = (ctypes.c_int * (total + 2))()
+    ni, nu, npu = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = lib.rpb200_debug_halo_units(p[0], p[1], p[2], p[3], p[4], u[0], u[1], u[2], u[3], u[4], order, items, total + 1, first,
+                                     total + 1, ctypes.byref(ni), ctypes.byref(nu), ctypes.byref(npu))
+    assert rc == 0
+    it = [(items[2 * i], items[2 * i + 1]) for i in range(ni.value)]
+    return it, [first[i] for i in range(nu.value + 1)], npu.value
+
+
+def plan_tuples(dims, hw, nv):
+    """(len, strided, msg, var) of the plan's tuples: strided = the list's first two cells are not adjacent (csrc/halo.cu: classify)"""
+    pack, unpack = sd.halo_lists(dims, hw)
+    def side(lists):
+        return [(int(lists[l].size), int(lists[l].size >= 2 and lists[l][1] - lists[l][0] != 1), l, v) for l in range(26) for v in range(nv)]
+    return side(pack), side(unpack)
+
+
+def check(pack, unpack, order, grids=(1, 7, 592, 4096)):
+    items, first, npu = units(pack, unpack, order)
+    want = sorted([(s, c) for s, t in enumerate(pack) for c in range(-(-t[0] // CHUNK))] +
+                  [(s | UNPACK, c) for s, t in enumerate(unpack) for c in range(-(-t[0] // CHUNK))])
+    assert sorted(items) == want                                      # every (tuple, chunk) exactly once
+    assert first[0] == 0 and first[-1] == len(items) and all(a < b for a, b in zip(first, first[1:]))
+    if order == 0:                                                    # exchange: pack units, then unpack units
+        cut = first[npu]
+        assert all(not (s & UNPACK) for s, _ in items[:cut]) and all(s & UNPACK for s, _ in items[cut:])
+    n_units = len(first) - 1
+    phases = [(0, npu), (npu, n_units)] if order == 0 else [(0, n_units)]
+    for G in grids:                                                   # the kernel's cursor: CTA b walks units b, b + G, ...
+        seen = []
+        for lo, hi in phases:
+            for b in range(min(G, max(hi - lo, 1))):
+                u = lo + b
+                while u < hi:
+                    seen.extend(range(first[u], first[u + 1]))
+                    u += G
+        assert sorted(seen) == list(range(len(items))), G
+    return items, first, npu
+
+
+@pytest.mark.parametrize("order", [1, 3, 5, 0])
+@pytest.mark.parametrize("dims,hw,nv", [((5, 5, 5), 1, 3), ((30, 30, 30), 2, 2), ((100, 100, 100), 1, 3), ((252, 252, 252), 1, 3)])
+def test_plan_unit_lists_cover_every_chunk_once(dims, hw, nv, order):
+    pack, unpack = plan_tuples(dims, hw, nv)
+    items, first, npu = check(pack, unpack, order)
+    xlen = max([t[0] for t in pack if t[1]] + [0])
+    if xlen < CHUNK:
+        return                                                        # no x units at this size: every unit is one item
+    # the x faces: neighbours 0 (-x) and 1 (+x)
+    sizes = [b - a for a, b in zip(first, first[1:])]
+    if order in (1, 3):
+        quads = [items[a:b] for a, b in zip(first, first[1:]) if b - a == 4]
+        assert len(quads) == nv * -(-xlen // CHUNK) and set(sizes) <= {1, 4}
+        for q in quads:                                               # {pack(-x), pack(+x), unpack(-x), unpack(+x)} of one variable, one chunk
+            segs = [s & ~UNPACK for s, _ in q]
+            assert [s & UNPACK for s, _ in q] == [0, 0, UNPACK, UNPACK] and len({c for _, c in q}) == 1
+            assert [s // nv for s in segs] == [0, 1, 0, 1] and len({s % nv for s in segs}) == 1
+        if order == 3:                                                # x units first
+            assert sizes[:len(quads)] == [4] * len(quads)
+    else:
+        pairs = [items[a:b] for a, b in zip(first, first[1:]) if b - a == 2]
+        assert len(pairs) == 2 * nv * -(-xlen // CHUNK) and set(sizes) <= {1, 2}
+        for q in pairs:
+            assert len({s & UNPACK for s, _ in q}) == 1 and len({c for _, c in q}) == 1
+            assert sorted((s & ~UNPACK) // nv for s, _ in q) == [0, 1]
+
+
+def test_512_cubed_counts():
+    """BASELINE config 5: 4608 + 72 chunks... every chunk once; the x units are 256 chunks x 3 variables."""
+    pack, unpack = [], []
+    n = 512
+    for l, off in enumerate([(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)] + [(1, 1, 0)] * 12 + [(1, 1, 1)] * 8):
+        ln = n ** (3 - sum(1 for o in off if o))
+        strided = int(off[0] != 0 and ln >= 2)
+        for v in range(3):
+            pack.append((ln, strided, l, v)); unpack.append((ln, strided, l, v))
+    items, first, _ = check(pack, unpack, 1, grids=(592,))
+    assert sum(1 for a, b in zip(first, first[1:]) if b - a == 4) == 3 * 128
+
+
+@pytest.mark.parametrize("order", [1, 3, 5, 0])
+def test_ragged_generic_tuples(order):
+    rng = np.random.default_rng(order)
+    lens = [0, 1, 3, CHUNK - 1, CHUNK, CHUNK + 1, 3 * CHUNK + 5, 4 * CHUNK, 4 * CHUNK, 4 * CHUNK, 4 * CHUNK]
+    pack = [(int(n), int(i >= 7), i % 5, i % 2) for i, n in enumerate(lens)]
+    unpack = [(int(n), int(rng.integers(0, 2)), i % 3, i % 2) for i, n in enumerate(reversed(lens))]
+    check(pack, unpack, order)
+    check(pack, [], order)
+    check([], unpack, order)

@@ -124,7 +124,7 @@ if "sort" in which:
     k = torch.empty_like(src); v = torch.empty_like(src)
     scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
     for rnd in range(2):
-        for var, label in ((8, "shared-bin histogram"), (4, "lane-private histogram (default)")):
+        for var, label in ((8, "shared-bin histogram"), (7, "no uniform-tile test"), (4, "lane-private histogram + uniform-tile test (default)")):
             ctx.set_tuning("Algorithm_SORT", -1, -1, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, -1, var)
             ms = time_ms(lambda: ctx.sort_keys(k, scratch), 5, 2, setup=lambda: k.copy_(src))
             report(f"sort keys 2^27, {label} round {rnd}", 16 * n, ms, mkeys_s=n / ms / 1e3)
