@@ -178,8 +178,10 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
 #pragma unroll
         for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_hint(var + idx[k], pol_once);
       } else {
+        // .cg: a gather through L1 fetches TWO sectors from L2 per miss (64-byte L1 fill): for a strided face that is 64
+        // bytes of DRAM traffic per 8-byte cell (ncu, profiles/r02_d/: 6.56 M L2 read sectors for 2.98 M L1 miss sectors)
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = var[idx[k]];
+        for (int k = 0; k < EPT; ++k) if (idx[k] >= 0) v[k] = ld_cg(var + idx[k]);
       }
       // MODE 1: the buffer is the peer's receive slot, read back by its unpack right away: default policy
       if (HINT && MODE == 0) {
@@ -270,15 +272,21 @@ halo_kernel(const rpb200_halo_seg* __restrict__ segs_g0, const rpb200_halo_seg* 
 //
 // Dealing is round-robin over units (unit u -> CTA u mod grid), which spreads the slow strided units and the streaming ones
 // evenly over every CTA.  A thread keeps the index loads of its NEXT item in flight while it gathers / scatters the current one.
-struct halo_item { int seg; int chunk; };            // seg: tuple index, bit 30 set = unpack side
+// seg: bits 0-7 first tuple, bits 8-15 number of CONSECUTIVE tuples that share one index list (the variables of a message:
+// the indices of a chunk are loaded once and used for every variable), bit 30 set = unpack side
+struct halo_item { int seg; int chunk; };
 constexpr int ITEM_UNPACK = 1 << 30;
-constexpr int ITEMS_MAX_SEGS = 128;                  // tuples per side kept in shared memory (26 neighbours x <= 4 variables)
+__host__ __device__ inline int item_first(int seg) { return seg & 0xff; }
+__host__ __device__ inline int item_count(int seg) { return (seg >> 8) & 0xff; }
+inline int item_make(int first, int count, int bit) { return first | (count << 8) | bit; }
+constexpr int ITEMS_MAX_SEGS = 128;                  // tuples per side kept in shared memory (26 neighbours x <= 4 variables); < 256
 
 struct halo_items_args {
   const rpb200_halo_seg* psegs[2];                   // pack tuples, generation 0 / 1 (the same array for HALO_PACKING_FUSED)
   const rpb200_halo_seg* usegs[2];
   const halo_item* items;
   const int* unit_first;                             // unit u = items [unit_first[u], unit_first[u + 1])
+  unsigned int* ticket;                              // [0] phase-1 unit ticket, [1] phase-2 unit ticket, [2] CTAs done (re-armed by the last)
   int n_units, n_pack_units, npsegs, nusegs;         // XCHG: units [0, n_pack_units) are the pack phase
   const halo_msg* pmsgs; const halo_msg* umsgs;
   unsigned int* msg_done; unsigned long long* d_epoch; unsigned int* unpack_done; int* error;
@@ -309,13 +317,12 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
   }
   __syncthreads();
 
-  const int G = (int)gridDim.x;
   int idx[EPT], nidx[EPT];
-  // the index loads of item `it` (or nothing past the end of this CTA's share)
-  auto fetch = [&](int it, int end, int (&dst)[EPT], halo_item& h) {
-    if (it < end) {
+  // the index loads of item `it` (nothing when it < 0)
+  auto fetch = [&](int it, int (&dst)[EPT], halo_item& h) {
+    if (it >= 0) {
       h = A.items[it];
-      const rpb200_halo_seg& seg = s_seg[(h.seg & ITEM_UNPACK) ? 1 : 0][h.seg & (ITEM_UNPACK - 1)];
+      const rpb200_halo_seg& seg = s_seg[(h.seg & ITEM_UNPACK) ? 1 : 0][item_first(h.seg)];
       const int64_t i0 = (int64_t)h.chunk * HALO_CHUNK;
       const int cnt = (int)((seg.len - i0) < HALO_CHUNK ? (seg.len - i0) : HALO_CHUNK);
       const int* __restrict__ list = seg.list + i0;
@@ -323,58 +330,93 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
       for (int k = 0; k < EPT; ++k) { const int i = k * HALO_BLOCK + threadIdx.x; dst[k] = (i < cnt) ? __ldg(list + i) : -1; }
     }
   };
+  // one chunk of every variable of the item, with the SAME indices.  Gathers bypass L1 (.cg): through L1 a strided 8-byte
+  // load fetches two sectors from L2.
   auto move = [&](const halo_item h, const int (&ix)[EPT]) {
     const bool unpack = (h.seg & ITEM_UNPACK) != 0;
-    const rpb200_halo_seg& seg = s_seg[unpack ? 1 : 0][h.seg & (ITEM_UNPACK - 1)];
-    double* __restrict__ buf = seg.buffer + (int64_t)h.chunk * HALO_CHUNK;
-    double* __restrict__ var = seg.var;
-    double v[EPT];
-    if (!unpack) {
+    const int first = item_first(h.seg), count = item_count(h.seg);
+    for (int j = 0; j < count; ++j) {
+      const rpb200_halo_seg& seg = s_seg[unpack ? 1 : 0][first + j];
+      double* __restrict__ buf = seg.buffer + (int64_t)h.chunk * HALO_CHUNK;
+      double* __restrict__ var = seg.var;
+      double v[EPT];
+      if (!unpack) {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = var[ix[k]];
+        for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = ld_cg(var + ix[k]);
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
-    } else {
+        for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) buf[k * HALO_BLOCK + threadIdx.x] = v[k];
+      } else {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
+        for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) v[k] = ld_cg(buf + k * HALO_BLOCK + threadIdx.x);
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) var[ix[k]] = v[k];
+        for (int k = 0; k < EPT; ++k) if (ix[k] >= 0) var[ix[k]] = v[k];
+      }
     }
   };
 
-  // this CTA's items in order: the items of unit u, then of unit u + G, ...
-  struct cursor { int u, it, end_it; };
-  auto cursor_begin = [&](int u0, int u_end) {
-    cursor c{u0, 0, 0};
-    if (u0 < u_end) { c.it = __ldg(A.unit_first + u0); c.end_it = __ldg(A.unit_first + u0 + 1); }
-    return c;
-  };
-  auto cursor_next = [&](cursor c, int u_end) {
-    if (++c.it == c.end_it) {
-      c.u += G;
-      if (c.u < u_end) { c.it = __ldg(A.unit_first + c.u); c.end_it = __ldg(A.unit_first + c.u + 1); }
-    }
-    return c;
-  };
-
-  // ---- phase 1: every unit (HALO_PACKING_FUSED) / the pack units (exchange)
-  const int end1 = XCHG ? A.n_pack_units : A.n_units;
-  {
+  // Units are drawn from an atomic ticket, two ahead: while unit u is being moved the next unit is already known (its first
+  // index loads are issued during u's last item) and the ticket after that is in flight.  Heavy units (the x faces) and light
+  // ones therefore balance themselves, whatever the grid.  `tk` is re-armed by the last CTA of the launch (below).
+  __shared__ unsigned int s_tk[2];
+  auto run_phase = [&](unsigned int* tk, int u_lo, int u_end, bool wait_flags, unsigned int& acquired, bool& failed) {
+    if (threadIdx.x == 0) { s_tk[0] = atomicAdd(tk, 1u); s_tk[1] = atomicAdd(tk, 1u); }
+    __syncthreads();
+    int u_cur = u_lo + (int)s_tk[0], u_nxt = u_lo + (int)s_tk[1];
+    __syncthreads();                                         // both slots are read before slot 0 is rewritten
     halo_item h, nh;
-    cursor c = cursor_begin((int)blockIdx.x, end1);
-    fetch(c.u < end1 ? c.it : 1, c.u < end1 ? c.it + 1 : 0, idx, h);
-    while (c.u < end1) {
-      const cursor n = cursor_next(c, end1);
-      fetch(n.u < end1 ? n.it : 1, n.u < end1 ? n.it + 1 : 0, nidx, nh);
-      move(h, idx);
-      if (XCHG && threadIdx.x == 0) s_credit[s_seg[0][h.seg].msg] += 1u;     // only thread 0 touches s_credit between barriers
+    int it = -1, end_it = 0;
+    if (u_cur < u_end) { it = __ldg(A.unit_first + u_cur); end_it = __ldg(A.unit_first + u_cur + 1); }
+    fetch(u_cur < u_end ? it : -1, idx, h);
+    for (int k = 0; u_cur < u_end; ++k) {
+      if (threadIdx.x == 0) s_tk[k & 1] = atomicAdd(tk, 1u);          // the unit after u_nxt
+      int n_it = -1, n_end = 0;
+      if (u_nxt < u_end) { n_it = __ldg(A.unit_first + u_nxt); n_end = __ldg(A.unit_first + u_nxt + 1); }
+      for (; it < end_it; ++it) {
+        fetch(it + 1 < end_it ? it + 1 : n_it, nidx, nh);             // next item of this unit, else the first of the next unit
+        if (wait_flags) {
+          const int m = s_seg[1][item_first(h.seg)].msg;
+          if (!((acquired >> m) & 1u)) {       // first item of message m in this CTA: acquire its flag
+            if (threadIdx.x == 0) {
+              const unsigned long long* f = A.umsgs[m].my_flag;
+              unsigned long long t0 = 0, t1 = 0;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+              int ok = 1;
+              while (ld_acquire_sys(f) < epoch) {
+                __nanosleep(40);
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > A.timeout_ns) { atomicExch(A.error, RPB200_ETIMEDOUT); ok = 0; break; }
+              }
+              s_ok = ok;
+            }
+            __syncthreads();
+            failed = failed || (s_ok == 0);
+            __syncthreads();
+            acquired |= 1u << m;
+          }
+        }
+        if (!failed) move(h, idx);
+        if (XCHG && !wait_flags && threadIdx.x == 0) s_credit[s_seg[0][item_first(h.seg)].msg] += (unsigned int)item_count(h.seg);
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
-      h = nh;
-      c = n;
+        for (int q = 0; q < EPT; ++q) idx[q] = nidx[q];
+        h = nh;
+      }
+      __syncthreads();                                       // s_tk[k & 1] is visible; everybody is done with unit u_cur
+      u_cur = u_nxt; it = n_it; end_it = n_end;
+      u_nxt = u_lo + (int)s_tk[k & 1];
     }
+  };
+
+  unsigned int acquired = 0u;            // bit m: this CTA has already seen message m's flag (thread-uniform)
+  bool failed = false;
+  // ---- phase 1: every unit (HALO_PACKING_FUSED) / the pack units (exchange)
+  run_phase(A.ticket + 0, 0, XCHG ? A.n_pack_units : A.n_units, false, acquired, failed);
+  if (!XCHG) {
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(A.ticket + 2, 1u);
+      if (prev == gridDim.x - 1) { A.ticket[0] = 0u; A.ticket[2] = 0u; }      // every CTA has drawn its last ticket: re-arm
+    }
+    return;
   }
-  if (!XCHG) return;
 
   // all remote stores of this CTA -> barrier -> ONE system fence -> credit every message it touched; whoever completes a
   // message publishes the epoch to the destination's flag (release at system scope)
@@ -394,47 +436,14 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
 
   // ---- phase 2: wait + unpack.  The grid is fully co-resident and phase 1 never waits, so every rank's flags are
   // eventually released.  A message that does not arrive within the time-out is NOT unpacked and the epoch is NOT committed.
-  unsigned int acquired = 0u;            // bit m: this CTA has already seen message m's flag (thread-uniform)
-  bool failed = false;
-  {
-    halo_item h, nh;
-    cursor c = cursor_begin(A.n_pack_units + (int)blockIdx.x, A.n_units);
-    fetch(c.u < A.n_units ? c.it : 1, c.u < A.n_units ? c.it + 1 : 0, idx, h);
-    while (c.u < A.n_units) {
-      const cursor n = cursor_next(c, A.n_units);
-      fetch(n.u < A.n_units ? n.it : 1, n.u < A.n_units ? n.it + 1 : 0, nidx, nh);
-      const int m = s_seg[1][h.seg & (ITEM_UNPACK - 1)].msg;
-      if (!((acquired >> m) & 1u)) {       // first item of message m in this CTA: acquire its flag (units alternate between messages)
-        if (threadIdx.x == 0) {
-          const unsigned long long* f = A.umsgs[m].my_flag;
-          unsigned long long t0 = 0, t1 = 0;
-          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-          int ok = 1;
-          while (ld_acquire_sys(f) < epoch) {
-            __nanosleep(40);
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > A.timeout_ns) { atomicExch(A.error, RPB200_ETIMEDOUT); ok = 0; break; }
-          }
-          s_ok = ok;
-        }
-        __syncthreads();
-        failed = failed || (s_ok == 0);
-        __syncthreads();
-        acquired |= 1u << m;
-      }
-      if (!failed) move(h, idx);
-#pragma unroll
-      for (int k = 0; k < EPT; ++k) idx[k] = nidx[k];
-      h = nh;
-      c = n;
-    }
-  }
+  run_phase(A.ticket + 1, A.n_pack_units, A.n_units, true, acquired, failed);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();                     // this CTA's time-out report (if any) is visible before its retirement is counted
     const unsigned int prev = atomicAdd(A.unpack_done, 1u);
-    if (prev == gridDim.x - 1) {         // every CTA has read the epoch and finished
+    if (prev == gridDim.x - 1) {         // every CTA has read the epoch, drawn its last tickets and finished
       *A.unpack_done = 0u;
+      A.ticket[0] = 0u; A.ticket[1] = 0u;
       __threadfence();
       int err = 0;
       asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(err) : "l"(A.error) : "memory");
@@ -477,7 +486,8 @@ struct worklist_dev {
   std::vector<long long> first;     // host copy: first chunk of every tuple
   std::vector<rpb200_halo_seg> h_segs;   // host copy of the tuples as built (geometry: len, msg, flags, var)
   // item list of the one-launch pack+unpack kernel, cached on the PACK list for the unpack list it was merged with
-  void* d_items = nullptr; const halo_item* d_item_list = nullptr; const int* d_unit_first = nullptr; int n_units = 0;
+  void* d_items = nullptr; const halo_item* d_item_list = nullptr; const int* d_unit_first = nullptr; unsigned int* d_unit_ticket = nullptr;
+  int n_units = 0;
   const void* merged_with = nullptr; int merged_order = -1;
 };
 
@@ -663,6 +673,7 @@ struct rpb200_halo_plan {
   bool connected = false;
   // item lists of the one-launch kernels (halo_items_kernel): HALO_PACKING_FUSED merged, exchange pack-then-unpack
   void* d_xchg_block = nullptr; const halo_item* d_items_xchg = nullptr; const int* d_unit_first_xchg = nullptr;
+  unsigned int* d_ticket_xchg = nullptr;
   int n_units_xchg = 0, n_pack_units_xchg = 0;
 };
 
@@ -839,8 +850,8 @@ struct x_ref { const double* var; int side; int msg; int seg; };
 static std::vector<x_ref> x_tuples(const worklist_dev& pw, const worklist_dev& uw, int64_t xlen, bool want_pack, bool want_unpack)
 {
   std::vector<x_ref> x;
-  if (want_pack) for (int i = 0; i < pw.nsegs; ++i) if (is_x_tuple(pw.h_segs[i], xlen)) x.push_back(x_ref{pw.h_segs[i].var, 0, pw.h_segs[i].msg, i});
-  if (want_unpack) for (int i = 0; i < uw.nsegs; ++i) if (is_x_tuple(uw.h_segs[i], xlen)) x.push_back(x_ref{uw.h_segs[i].var, 1, uw.h_segs[i].msg, i | ITEM_UNPACK});
+  if (want_pack) for (int i = 0; i < pw.nsegs; ++i) if (is_x_tuple(pw.h_segs[i], xlen)) x.push_back(x_ref{pw.h_segs[i].var, 0, pw.h_segs[i].msg, item_make(i, 1, 0)});
+  if (want_unpack) for (int i = 0; i < uw.nsegs; ++i) if (is_x_tuple(uw.h_segs[i], xlen)) x.push_back(x_ref{uw.h_segs[i].var, 1, uw.h_segs[i].msg, item_make(i, 1, ITEM_UNPACK)});
   // variables in order of first appearance (not of address), then side, then message
   std::vector<const double*> order;
   for (const x_ref& r : x) { bool seen = false; for (const double* v : order) seen = seen || v == r.var; if (!seen) order.push_back(r.var); }
@@ -865,7 +876,9 @@ struct unit_list {
   void finish() { first.push_back((int)items.size()); finished = true; }
 };
 
-// streaming groups of one list: for every message (run of consecutive tuples with the same msg), chunk-major
+// streaming groups of one list: for every message (run of consecutive tuples with the same msg), chunk-major.  Consecutive
+// tuples of a message that share one index list and length (the variables of a neighbour: plan_segments, and the reference's
+// own tuples, HALO_PACKING_FUSED-Seq.cpp:43-61) become ONE item: the kernel loads the indices of a chunk once for all of them.
 static void stream_groups(const worklist_dev& w, int64_t xlen, int bit, std::vector<std::vector<halo_item>>& sg)
 {
   int i = 0;
@@ -873,10 +886,20 @@ static void stream_groups(const worklist_dev& w, int64_t xlen, int bit, std::vec
     int j = i;
     int64_t maxc = 0;
     while (j < w.nsegs && w.h_segs[j].msg == w.h_segs[i].msg) { if (!is_x_tuple(w.h_segs[j], xlen)) maxc = std::max(maxc, plan_chunks(w.h_segs[j].len)); ++j; }
+    // runs [t, t + n) of tuples sharing list and length
+    std::vector<std::pair<int, int>> runs;
+    for (int t = i; t < j;) {
+      if (is_x_tuple(w.h_segs[t], xlen)) { ++t; continue; }
+      int n = 1;
+      while (t + n < j && n < 255 && !is_x_tuple(w.h_segs[t + n], xlen) && w.h_segs[t + n].list == w.h_segs[t].list &&
+             w.h_segs[t + n].len == w.h_segs[t].len && w.h_segs[t + n].flags == w.h_segs[t].flags) ++n;
+      runs.push_back(std::make_pair(t, n));
+      t += n;
+    }
     for (int64_t c = 0; c < maxc; ++c) {
       std::vector<halo_item> g;
-      for (int t = i; t < j; ++t)
-        if (!is_x_tuple(w.h_segs[t], xlen) && c < plan_chunks(w.h_segs[t].len)) g.push_back(halo_item{t | bit, (int)c});
+      for (const auto& r : runs)
+        if (c < plan_chunks(w.h_segs[r.first].len)) g.push_back(halo_item{item_make(r.first, r.second, bit), (int)c});
       if (!g.empty()) sg.push_back(g);
     }
     i = j;
@@ -929,7 +952,8 @@ static void build_items_merged(const worklist_dev& pw, const worklist_dev& uw, i
     if (order == 3) take_x = ix < nx;
     else if (ix >= nx) take_x = false;
     else if (is >= ns) take_x = true;
-    else take_x = (ix + 1) * ns <= (is + 1) * nx;      // keep ix / nx and is / ns level
+    else take_x = (ix + 1) * ns * 17 <= (is + 1) * nx * 20;      // X units spread evenly over the first 85 % of the list:
+                                                                  // the launch ends on light units (tickets balance the rest)
     if (take_x) {
       for (const auto& var : xv) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)ix}); L.add_unit(g); }
       ++ix;
@@ -961,16 +985,19 @@ static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, uni
 }
 
 // items and unit_first in ONE device allocation: [items | unit_first]
-static int upload_units(const unit_list& L, void** d_block, const halo_item** d_items, const int** d_unit_first)
+// items, unit_first and the unit tickets in ONE device allocation: [items | unit_first | 4 ticket words (zero: re-armed by the kernel)]
+static int upload_units(const unit_list& L, void** d_block, const halo_item** d_items, const int** d_unit_first, unsigned int** d_ticket)
 {
-  cudaFree(*d_block); *d_block = nullptr; *d_items = nullptr; *d_unit_first = nullptr;
+  cudaFree(*d_block); *d_block = nullptr; *d_items = nullptr; *d_unit_first = nullptr; *d_ticket = nullptr;
   if (L.items.empty()) return 0;
-  const size_t ib = sizeof(halo_item) * L.items.size(), ub = sizeof(int) * L.first.size();
-  RPB_CHECK(cudaMalloc(d_block, ib + ub));
+  const size_t ib = sizeof(halo_item) * L.items.size(), ub = (sizeof(int) * L.first.size() + 15) / 16 * 16;
+  RPB_CHECK(cudaMalloc(d_block, ib + ub + 16));
+  RPB_CHECK(cudaMemset(*d_block, 0, ib + ub + 16));
   RPB_CHECK(cudaMemcpy(*d_block, L.items.data(), ib, cudaMemcpyHostToDevice));
-  RPB_CHECK(cudaMemcpy((char*)*d_block + ib, L.first.data(), ub, cudaMemcpyHostToDevice));
+  RPB_CHECK(cudaMemcpy((char*)*d_block + ib, L.first.data(), sizeof(int) * L.first.size(), cudaMemcpyHostToDevice));
   *d_items = (const halo_item*)*d_block;
   *d_unit_first = (const int*)((char*)*d_block + ib);
+  *d_ticket = (unsigned int*)((char*)*d_block + ib + ub);
   return 0;
 }
 
@@ -1004,7 +1031,7 @@ static int ensure_merged(const rpb200_ctx* ctx, worklist_dev& pw, worklist_dev& 
   if (pw.merged_with == (const void*)&uw && pw.merged_order == order) return 0;
   unit_list L;
   build_items_merged(pw, uw, order, L);
-  const int rc = upload_units(L, &pw.d_items, &pw.d_item_list, &pw.d_unit_first);
+  const int rc = upload_units(L, &pw.d_items, &pw.d_item_list, &pw.d_unit_first, &pw.d_unit_ticket);
   if (rc != 0) { pw.merged_with = nullptr; return rc; }
   pw.n_units = L.units(); pw.merged_with = &uw; pw.merged_order = order;
   return 0;
@@ -1025,7 +1052,7 @@ static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev&
   memset(&A, 0, sizeof(A));
   A.psegs[0] = A.psegs[1] = pw.d_segs;
   A.usegs[0] = A.usegs[1] = uw.d_segs;
-  A.items = pw.d_item_list; A.unit_first = pw.d_unit_first; A.n_units = pw.n_units; A.n_pack_units = 0;
+  A.items = pw.d_item_list; A.unit_first = pw.d_unit_first; A.ticket = pw.d_unit_ticket; A.n_units = pw.n_units; A.n_pack_units = 0;
   A.npsegs = pw.nsegs; A.nusegs = uw.nsegs;
   return launch_items<false>(ctx, RPB_K_HALO_PACKING_FUSED, A, st);
 }
@@ -1212,7 +1239,7 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
     unit_list L;
     int n_pack = 0;
     build_items_xchg(p->xpack_wl[0], p->xunpack_wl[0], L, &n_pack);
-    const int rc = upload_units(L, &p->d_xchg_block, &p->d_items_xchg, &p->d_unit_first_xchg);
+    const int rc = upload_units(L, &p->d_xchg_block, &p->d_items_xchg, &p->d_unit_first_xchg, &p->d_ticket_xchg);
     if (rc != 0) return rc;
     p->n_units_xchg = L.units(); p->n_pack_units_xchg = n_pack;
   }
@@ -1308,7 +1335,8 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
   memset(&A, 0, sizeof(A));
   A.psegs[0] = p->xpack_wl[0].d_segs; A.psegs[1] = p->xpack_wl[1].d_segs;
   A.usegs[0] = p->xunpack_wl[0].d_segs; A.usegs[1] = p->xunpack_wl[1].d_segs;
-  A.items = p->d_items_xchg; A.unit_first = p->d_unit_first_xchg; A.n_units = p->n_units_xchg; A.n_pack_units = p->n_pack_units_xchg;
+  A.items = p->d_items_xchg; A.unit_first = p->d_unit_first_xchg; A.ticket = p->d_ticket_xchg;
+  A.n_units = p->n_units_xchg; A.n_pack_units = p->n_pack_units_xchg;
   A.npsegs = p->xpack_wl[0].nsegs; A.nusegs = p->xunpack_wl[0].nsegs;
   A.pmsgs = p->d_pack_msgs; A.umsgs = p->d_unpack_msgs; A.msg_done = p->d_msg_done; A.d_epoch = p->d_epoch;
   A.unpack_done = p->d_unpack_done; A.error = p->d_error; A.timeout_ns = halo_timeout_ns();

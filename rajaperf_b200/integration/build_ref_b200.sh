@@ -24,13 +24,23 @@ if [ "${MPI:-0}" = "1" ]; then
   MPI_FLAGS=(-DENABLE_MPI=On -DENABLE_FIND_MPI=Off "-DBLT_MPI_INCLUDES=$ROOT/oracle/mpi_stub" "-DBLT_MPI_LIBRARIES=$BUILD/libmpistub.a")
   OUT=raja-perf-with-b200-mpi.exe
 fi
+# TESTS=1: also the reference's own gtest (test/test-raja-perf-suite.cpp: every kernel, every variant that ran, checksum within
+# 1e-7 of the first one) -> oracle/_ref/test-raja-perf-suite-with-b200.exe; turning it on in an existing build tree only adds
+# gtest and the test target (6 build steps)
+TESTS_FLAG=-DENABLE_TESTS=Off
+[ "${TESTS:-0}" = "1" ] && TESTS_FLAG=-DENABLE_TESTS=On
 cd "$BUILD"
 CC=/usr/bin/gcc CXX=/usr/bin/g++ cmake -G Ninja -DCMAKE_BUILD_TYPE=Release -DENABLE_OPENMP=On -DENABLE_CUDA=On \
   -DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc -DCMAKE_CUDA_HOST_COMPILER=/usr/bin/g++ \
-  "-DCMAKE_CUDA_ARCHITECTURES=90-virtual;100-real" -DENABLE_TESTS=Off \
+  "-DCMAKE_CUDA_ARCHITECTURES=90-virtual;100-real" $TESTS_FLAG \
   "-DCMAKE_CXX_FLAGS=-I$ROOT/include" "-DCMAKE_CUDA_FLAGS=-I$ROOT/include" \
   "-DCMAKE_CXX_STANDARD_LIBRARIES=-L$ROOT/rajaperf_b200/lib -lrpb200 -Wl,-rpath,$ROOT/rajaperf_b200/lib" \
   "${MPI_FLAGS[@]}" "$SRC" > cmake.log 2>&1
 ninja raja-perf.exe > ninja.log 2>&1
 cp bin/raja-perf.exe "$ROOT/oracle/_ref/$OUT"
 echo "built $ROOT/oracle/_ref/$OUT"
+if [ "${TESTS:-0}" = "1" ] && [ "${MPI:-0}" != "1" ]; then
+  ninja test-raja-perf-suite.exe >> ninja.log 2>&1
+  cp test/test-raja-perf-suite.exe "$ROOT/oracle/_ref/test-raja-perf-suite-with-b200.exe"
+  echo "built $ROOT/oracle/_ref/test-raja-perf-suite-with-b200.exe"
+fi

@@ -3,8 +3,9 @@ host-only hook rpb200_debug_halo_units -- no GPU is touched.
 
 Checked for HALO_base geometries (the tuples of rpb200_halo_plan_bind: neighbour-major, variable-minor) and for ragged generic
 tuples: every (tuple, chunk) of both lists appears EXACTLY once; units are well-formed; the four x-face chunks of a variable
-form one unit; the exchange order keeps every pack unit before every unpack unit; and a Python model of the kernel's cursor
-(CTA b walks units b, b + G, ...) visits every item exactly once for several grid sizes."""
+form one unit; the variables of a message share one item (their index list is loaded once); the exchange order keeps every
+pack unit before every unpack unit.  (Units are drawn from an atomic ticket by the kernel: any CTA may take any unit, so
+"every unit once" is all the traversal needs.)"""
 import ctypes
 
 import numpy as np
@@ -14,6 +15,14 @@ import suite_data as sd
 
 CHUNK = 2048
 UNPACK = 1 << 30
+
+
+def first_of(seg):
+    return seg & 0xff
+
+
+def count_of(seg):
+    return (seg >> 8) & 0xff
 
 
 def units(pack, unpack, order):
@@ -45,26 +54,22 @@ def plan_tuples(dims, hw, nv):
     return side(pack), side(unpack)
 
 
-def check(pack, unpack, order, grids=(1, 7, 592, 4096)):
+def check(pack, unpack, order):
     items, first, npu = units(pack, unpack, order)
     want = sorted([(s, c) for s, t in enumerate(pack) for c in range(-(-t[0] // CHUNK))] +
                   [(s | UNPACK, c) for s, t in enumerate(unpack) for c in range(-(-t[0] // CHUNK))])
-    assert sorted(items) == want                                      # every (tuple, chunk) exactly once
+    got = []
+    for seg, c in items:                                              # an item moves chunk c of `count` consecutive tuples
+        side = pack if not (seg & UNPACK) else unpack
+        assert count_of(seg) >= 1
+        tuples = side[first_of(seg):first_of(seg) + count_of(seg)]
+        assert len({(t[0], t[2]) for t in tuples}) == 1               # same length and message: they share the index list
+        got += [((first_of(seg) + j) | (seg & UNPACK), c) for j in range(count_of(seg))]
+    assert sorted(got) == want                                        # every (tuple, chunk) exactly once
     assert first[0] == 0 and first[-1] == len(items) and all(a < b for a, b in zip(first, first[1:]))
     if order == 0:                                                    # exchange: pack units, then unpack units
         cut = first[npu]
         assert all(not (s & UNPACK) for s, _ in items[:cut]) and all(s & UNPACK for s, _ in items[cut:])
-    n_units = len(first) - 1
-    phases = [(0, npu), (npu, n_units)] if order == 0 else [(0, n_units)]
-    for G in grids:                                                   # the kernel's cursor: CTA b walks units b, b + G, ...
-        seen = []
-        for lo, hi in phases:
-            for b in range(min(G, max(hi - lo, 1))):
-                u = lo + b
-                while u < hi:
-                    seen.extend(range(first[u], first[u + 1]))
-                    u += G
-        assert sorted(seen) == list(range(len(items))), G
     return items, first, npu
 
 
@@ -82,9 +87,11 @@ def test_plan_unit_lists_cover_every_chunk_once(dims, hw, nv, order):
         quads = [items[a:b] for a, b in zip(first, first[1:]) if b - a == 4]
         assert len(quads) == nv * -(-xlen // CHUNK) and set(sizes) <= {1, 4}
         for q in quads:                                               # {pack(-x), pack(+x), unpack(-x), unpack(+x)} of one variable, one chunk
-            segs = [s & ~UNPACK for s, _ in q]
+            segs = [first_of(s) for s, _ in q]
             assert [s & UNPACK for s, _ in q] == [0, 0, UNPACK, UNPACK] and len({c for _, c in q}) == 1
-            assert [s // nv for s in segs] == [0, 1, 0, 1] and len({s % nv for s in segs}) == 1
+            assert [s // nv for s in segs] == [0, 1, 0, 1] and len({s % nv for s in segs}) == 1 and all(count_of(s) == 1 for s, _ in q)
+        singles = [items[a] for a, b in zip(first, first[1:]) if b - a == 1]
+        assert all(count_of(s) == nv for s, _ in singles)             # every other item carries all the variables of its message
         if order == 3:                                                # x units first
             assert sizes[:len(quads)] == [4] * len(quads)
     else:
@@ -92,11 +99,11 @@ def test_plan_unit_lists_cover_every_chunk_once(dims, hw, nv, order):
         assert len(pairs) == 2 * nv * -(-xlen // CHUNK) and set(sizes) <= {1, 2}
         for q in pairs:
             assert len({s & UNPACK for s, _ in q}) == 1 and len({c for _, c in q}) == 1
-            assert sorted((s & ~UNPACK) // nv for s, _ in q) == [0, 1]
+            assert sorted(first_of(s) // nv for s, _ in q) == [0, 1]
 
 
 def test_512_cubed_counts():
-    """BASELINE config 5: 4608 + 72 chunks... every chunk once; the x units are 256 chunks x 3 variables."""
+    """BASELINE config 5: every chunk once; the x units are 128 chunks x 3 variables."""
     pack, unpack = [], []
     n = 512
     for l, off in enumerate([(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)] + [(1, 1, 0)] * 12 + [(1, 1, 1)] * 8):
@@ -104,8 +111,11 @@ def test_512_cubed_counts():
         strided = int(off[0] != 0 and ln >= 2)
         for v in range(3):
             pack.append((ln, strided, l, v)); unpack.append((ln, strided, l, v))
-    items, first, _ = check(pack, unpack, 1, grids=(592,))
+    items, first, _ = check(pack, unpack, 1)
     assert sum(1 for a, b in zip(first, first[1:]) if b - a == 4) == 3 * 128
+    # the x units lie in the first 85 % of the list: the launch ends on light units
+    last_x = max(u for u, (a, b) in enumerate(zip(first, first[1:])) if b - a == 4)
+    assert last_x < 0.9 * (len(first) - 1)
 
 
 @pytest.mark.parametrize("order", [1, 3, 5, 0])

@@ -96,10 +96,10 @@ def halo(g):
     for rnd in range(2):
         ctx.set_tuning(K, 192, 4, 2)
         report(f"halo{g} pack+unpack TWO launches (r01 default) round {rnd}", 40 * ne, graph_ms(lambda: (plan.pack(), plan.unpack())))
-        for cps in (4, 3):
-            for order, label in ((1, "x units mixed in"), (3, "x units first"), (5, "two phases")):
-                ctx.set_tuning(K, 192, cps, order)
-                report(f"halo{g} pack+unpack ONE launch, {label}, {cps} CTAs/SM round {rnd}", 40 * ne, graph_ms(plan.pack_unpack))
+        for cps, order, label in ((4, 1, "x units mixed in"), (3, 1, "x units mixed in"), (2, 1, "x units mixed in"),
+                                  (4, 3, "x units first"), (4, 5, "two phases")):
+            ctx.set_tuning(K, 192, cps, order)
+            report(f"halo{g} pack+unpack ONE launch, {label}, {cps} CTAs/SM round {rnd}", 40 * ne, graph_ms(plan.pack_unpack))
     ctx.reset_tuning(K)
     X = "Comm_HALO_EXCHANGE_FUSED"
     for rnd in range(2):
