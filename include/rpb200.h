@@ -75,6 +75,7 @@ int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
  *       exchange unroll 1 = ONE launch per rep over the item list, 2 / 4 = pack launch + unpack launch;
  *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 8 = digit histograms in shared bins instead of the lane-private 16-bit
  *       counters (default since round 2: profiles/r02_a_optin.log); 7 = no pass tests its tiles for uniformity;
+ *       ctas_per_sm 1 = the look-back reads one tile descriptor at a time instead of four;
  *   Apps_MASS3DPA / Apps_CONVECTION3DPA: unroll selects a launch shape (csrc/pa.cu; 1 = default);
  *   Apps_LTIMES: ctas_per_sm; unroll 5..8 = psi staged through a bulk-async ring, 10 = row-chunk A fragments, else line-major (default);
  *   Polybench_GEMM: block_size 64 / 96 / 128 / 160 = CTA tiling (else automatic), unroll 8 = 32-deep stages.

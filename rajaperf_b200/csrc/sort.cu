@@ -289,7 +289,7 @@ __device__ __forceinline__ unsigned int key_digit(unsigned long long k, int shif
   return (w >> (shift & 31)) & (RADIX - 1);
 }
 
-template <bool PAIRS, bool FIRST, bool LAST>
+template <bool PAIRS, bool FIRST, bool LAST, int SORT_LB>     // SORT_LB: tile descriptors in flight per look-back step
 __global__ void __launch_bounds__(SORT_BLOCK, 2)
 sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned long long* __restrict__ keys_out,
                      const unsigned long long* __restrict__ vals_in, unsigned long long* __restrict__ vals_out,
@@ -424,13 +424,35 @@ sort_onesweep_kernel(const unsigned long long* __restrict__ keys_in, unsigned lo
     const int b = threadIdx.x;
     unsigned long long excl = 0;
     if (tile > 0) {
+      // look back SORT_LB tiles at a time: the descriptor loads of a batch are independent, so a walk of d tiles costs
+      // ~d / SORT_LB L2 round trips instead of d (the walk is on the tile's critical path: every other thread waits for it)
       int64_t look = (int64_t)tile - 1;
-      for (;;) {
-        unsigned long long w;
-        do { w = ld_desc(desc + (size_t)look * RADIX + b); } while (((w >> 1) & 1ull) != parity);
-        excl += (w >> 2);
-        if (w & 1ull) break;          // inclusive prefix of that tile: done
-        --look;
+      bool done = false;
+      if constexpr (SORT_LB == 1) {
+        for (;;) {
+          unsigned long long w;
+          do { w = ld_desc(desc + (size_t)look * RADIX + b); } while (((w >> 1) & 1ull) != parity);
+          excl += (w >> 2);
+          if (w & 1ull) break;          // inclusive prefix of that tile: done
+          --look;
+        }
+        done = true;
+      }
+      while (!done) {
+        unsigned long long w[SORT_LB];
+#pragma unroll
+        for (int j = 0; j < SORT_LB; ++j)
+          w[j] = (look - j >= 0) ? ld_desc(desc + (size_t)(look - j) * RADIX + b) : (2ull * parity + 1ull);   // before tile 0: inclusive 0
+#pragma unroll
+        for (int j = 0; j < SORT_LB; ++j) {
+          if (!done) {
+            if (look - j >= 0)
+              while (((w[j] >> 1) & 1ull) != parity) w[j] = ld_desc(desc + (size_t)(look - j) * RADIX + b);   // not published yet
+            excl += (w[j] >> 2);
+            if (w[j] & 1ull) done = true;       // inclusive prefix of that tile
+          }
+        }
+        look -= SORT_LB;
       }
       if (tile + 1 < num_tiles)
         st_desc(desc + (size_t)tile * RADIX + b, ((excl + my_total) << 2) | (2ull * parity + 1ull));
@@ -551,25 +573,27 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
 
   const size_t smem = sizeof(unsigned long long) * SORT_TILE + sizeof(unsigned int) * SORT_WARPS * RADIX +
                       sizeof(unsigned int) * RADIX + sizeof(long long) * RADIX + (PAIRS ? SORT_TILE : 0);
-  // per call: the attribute belongs to the current device's context, and a process may hold several contexts
-  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
   // skew[p] != 0: pass p tests its tiles for uniformity; skew[NUM_PASSES] is never set (tuning `unroll` 7: no pass tests)
   const unsigned int* skew = ctrs + 2 * NUM_PASSES;
   const bool no_uniform = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll == 7;
+  const int lb = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].ctas_per_sm == 1 ? 1 : 4;   // tuning `ctas_per_sm` 1: look back one tile at a time
   unsigned long long* kin = (unsigned long long*)keys; unsigned long long* kout = alt_keys;
   unsigned long long* vin = (unsigned long long*)vals; unsigned long long* vout = alt_vals;
   for (int p = 0; p < NUM_PASSES; ++p) {
     const unsigned int parity = (unsigned int)(p & 1);
     const int shift = p * RADIX_BITS;
-    if (p == 0)
-      sort_onesweep_kernel<PAIRS, true, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
-    else if (p == NUM_PASSES - 1)
-      sort_onesweep_kernel<PAIRS, false, true><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
-    else
-      sort_onesweep_kernel<PAIRS, false, false><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, ctrs + 2 * p, tiles, parity, skew + (no_uniform ? NUM_PASSES : p));
+    const unsigned int* sk = skew + (no_uniform ? NUM_PASSES : p);
+    // the attribute is set per call: it belongs to the current device's context, and a process may hold several contexts
+#define RPB_SORT_PASS(F, L, LB)                                                                                                  \
+    do {                                                                                                                         \
+      RPB_CHECK(cudaFuncSetAttribute(sort_onesweep_kernel<PAIRS, F, L, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      sort_onesweep_kernel<PAIRS, F, L, LB><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, \
+                                                                             ctrs + 2 * p, tiles, parity, sk);                  \
+    } while (0)
+    if (p == 0) { if (lb == 1) RPB_SORT_PASS(true, false, 1); else RPB_SORT_PASS(true, false, 4); }
+    else if (p == NUM_PASSES - 1) { if (lb == 1) RPB_SORT_PASS(false, true, 1); else RPB_SORT_PASS(false, true, 4); }
+    else { if (lb == 1) RPB_SORT_PASS(false, false, 1); else RPB_SORT_PASS(false, false, 4); }
+#undef RPB_SORT_PASS
     RPB_LAUNCH_CHECK();
     unsigned long long* t = kin; kin = kout; kout = t;
     t = vin; vin = vout; vout = t;

@@ -159,13 +159,13 @@ def _adversarial_keys(kind, n, rng):
 ADVERSARIAL = ["all_equal", "sorted", "reversed", "suite_like", "one_stranger_per_tile", "two_values_blocks", "mixed_signs_runs"]
 
 
-@pytest.mark.parametrize("hist", ["lanes", "shared_bins", "no_uniform_test"])
+@pytest.mark.parametrize("hist", ["lanes", "shared_bins", "no_uniform_test", "lookback_1"])
 @pytest.mark.parametrize("kind", ADVERSARIAL)
 @pytest.mark.parametrize("n", [8192, 8193, 3 * 8192, 1000003])
 def test_sort_keys_adversarial_sets_bit_exact(ctx, n, kind, hist):
     rng = np.random.default_rng(n + len(kind))
     x = _adversarial_keys(kind, n, rng)
-    ctx.set_tuning("Algorithm_SORT", unroll={"shared_bins": 8, "no_uniform_test": 7}.get(hist, 4))
+    ctx.set_tuning("Algorithm_SORT", ctas_per_sm=1 if hist == "lookback_1" else 4, unroll={"shared_bins": 8, "no_uniform_test": 7}.get(hist, 4))
     try:
         k = dev(x)
         ctx.sort_keys(k, _scratch(ctx, n, False))

@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round 2, call f (1 GPU): SORT look-back batch A/B next to CUB on the same box; halo CTAs-per-SM sweep (fewer is faster?).
+TAG=${TAG:-r02_f}
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_algorithm_gpu.py -m gpu -q -x > gpurun_out/${TAG}_pytest_algo.log 2>&1; echo "pytest algorithm rc=$?"; tail -2 gpurun_out/${TAG}_pytest_algo.log
+timeout 300 python tools/time_r02.py sort halo --out gpurun_out/${TAG}_time.json > gpurun_out/${TAG}_time.log 2>&1; echo "time_r02 rc=$?"
+cat gpurun_out/${TAG}_time.log
+[ -x tools/bin/incumbent ] && (timeout 120 tools/bin/incumbent > gpurun_out/${TAG}_cub.jsonl 2>&1; head -2 gpurun_out/${TAG}_cub.jsonl)
+timeout 200 python tools/time_r02.py halo1024 --out gpurun_out/${TAG}_time1024.json > gpurun_out/${TAG}_time1024.log 2>&1; echo "time_r02 1024 rc=$?"
+cat gpurun_out/${TAG}_time1024.log

@@ -96,14 +96,14 @@ def halo(g):
     for rnd in range(2):
         ctx.set_tuning(K, 192, 4, 2)
         report(f"halo{g} pack+unpack TWO launches (r01 default) round {rnd}", 40 * ne, graph_ms(lambda: (plan.pack(), plan.unpack())))
-        for cps, order, label in ((4, 1, "x units mixed in"), (3, 1, "x units mixed in"), (2, 1, "x units mixed in"),
-                                  (4, 3, "x units first"), (4, 5, "two phases")):
+        for cps, order, label in ((4, 1, "x units mixed in"), (2, 1, "x units mixed in"), (1, 1, "x units mixed in"),
+                                  (2, 3, "x units first"), (2, 5, "two phases")):
             ctx.set_tuning(K, 192, cps, order)
             report(f"halo{g} pack+unpack ONE launch, {label}, {cps} CTAs/SM round {rnd}", 40 * ne, graph_ms(plan.pack_unpack))
     ctx.reset_tuning(K)
     X = "Comm_HALO_EXCHANGE_FUSED"
     for rnd in range(2):
-        for cps in (4, 3):
+        for cps in (4, 2, 1):
             ctx.set_tuning(X, 192, cps, 2)
             report(f"halo{g} exchange 1 rank, TWO launches (r01 default), {cps} CTAs/SM round {rnd}", 56 * ne, graph_ms(plan.exchange))
             ctx.set_tuning(X, 192, cps, 1)
@@ -124,8 +124,9 @@ if "sort" in which:
     k = torch.empty_like(src); v = torch.empty_like(src)
     scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
     for rnd in range(2):
-        for var, label in ((8, "shared-bin histogram"), (7, "no uniform-tile test"), (4, "lane-private histogram + uniform-tile test (default)")):
-            ctx.set_tuning("Algorithm_SORT", -1, -1, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, -1, var)
+        for var, lb, label in ((8, 4, "shared-bin histogram"), (7, 4, "no uniform-tile test"), (4, 1, "look-back one tile at a time"),
+                               (4, 4, "default: lane-private histogram, uniform-tile test, look-back 4 at a time")):
+            ctx.set_tuning("Algorithm_SORT", -1, lb, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, lb, var)
             ms = time_ms(lambda: ctx.sort_keys(k, scratch), 5, 2, setup=lambda: k.copy_(src))
             report(f"sort keys 2^27, {label} round {rnd}", 16 * n, ms, mkeys_s=n / ms / 1e3)
             ms = time_ms(lambda: ctx.sort_pairs(k, v, scratch), 5, 2, setup=lambda: (k.copy_(src), v.copy_(src)))
