@@ -48,15 +48,26 @@ __device__ __forceinline__ unsigned long long key_decode(unsigned long long k)
 }
 
 // Lanes holding the same 8-bit digit.  Built from 8 warp ballots: the hardware MATCH.ANY instruction
-// is an order of magnitude slower on sm_100 (profiles/r01_sort_ncu.md).
+// is an order of magnitude slower on sm_100 (profiles/r01_sort_ncu.md).  Four instructions per bit: test the bit into a
+// predicate (one LOP3), ballot, turn the predicate into an all-ones / all-zeros word (SEL), and fold
+// peers &= ~(vote ^ own) with ONE three-input LOP3 (0x90 = a & ~(b ^ c)).  The round-1 form -- (d >> bit) & 1, then
+// `one ? vote : ~vote` -- compiled to six (SHF, LOP3, ISETP, VOTE, SEL, LOP3): the ranking loop is 45 % of a pass's
+// instructions and the pass is issue-bound, so the two instructions per bit are ~10 % of the sort.
 __device__ __forceinline__ unsigned int match_digit(unsigned int d)
 {
   unsigned int peers = 0xffffffffu;
 #pragma unroll
   for (int bit = 0; bit < RADIX_BITS; ++bit) {
-    const bool one = (d >> bit) & 1u;
-    const unsigned int vote = __ballot_sync(0xffffffffu, one);
-    peers &= one ? vote : ~vote;
+    // written in PTX: nvcc rewrites the C form back into shift / and / compare / negate (6 SASS instructions per bit)
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 ".reg .b32 t, v;\n\t"
+                 "and.b32 t, %1, %2;\n\t"
+                 "setp.ne.u32 p, t, 0;\n\t"
+                 "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+                 "selp.b32 t, 0xffffffff, 0, p;\n\t"
+                 "lop3.b32 %0, %0, v, t, 0x90;\n\t"
+                 "}" : "+r"(peers) : "r"(d), "r"(1u << bit));
   }
   return peers;
 }
@@ -576,7 +587,8 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
   // skew[p] != 0: pass p tests its tiles for uniformity; skew[NUM_PASSES] is never set (tuning `unroll` 7: no pass tests)
   const unsigned int* skew = ctrs + 2 * NUM_PASSES;
   const bool no_uniform = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].unroll == 7;
-  const int lb = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].ctas_per_sm == 1 ? 1 : 4;   // tuning `ctas_per_sm` 1: look back one tile at a time
+  const int lbt = ctx->tune[PAIRS ? RPB_K_SORTPAIRS : RPB_K_SORT].ctas_per_sm;
+  const int lb = (lbt == 1 || lbt == 2) ? lbt : 4;         // tuning `ctas_per_sm` 1 / 2: look back one / two tiles at a time (default 4)
   unsigned long long* kin = (unsigned long long*)keys; unsigned long long* kout = alt_keys;
   unsigned long long* vin = (unsigned long long*)vals; unsigned long long* vout = alt_vals;
   for (int p = 0; p < NUM_PASSES; ++p) {
@@ -590,9 +602,11 @@ int sort_impl(rpb200_ctx* ctx, double* keys, double* vals, int64_t n, void* scra
       sort_onesweep_kernel<PAIRS, F, L, LB><<<tiles, SORT_BLOCK, smem, st>>>(kin, kout, vin, vout, n, shift, hist + p * RADIX, desc, \
                                                                              ctrs + 2 * p, tiles, parity, sk);                  \
     } while (0)
-    if (p == 0) { if (lb == 1) RPB_SORT_PASS(true, false, 1); else RPB_SORT_PASS(true, false, 4); }
-    else if (p == NUM_PASSES - 1) { if (lb == 1) RPB_SORT_PASS(false, true, 1); else RPB_SORT_PASS(false, true, 4); }
-    else { if (lb == 1) RPB_SORT_PASS(false, false, 1); else RPB_SORT_PASS(false, false, 4); }
+#define RPB_SORT_LB(F, L) do { if (lb == 1) RPB_SORT_PASS(F, L, 1); else if (lb == 2) RPB_SORT_PASS(F, L, 2); else RPB_SORT_PASS(F, L, 4); } while (0)
+    if (p == 0) RPB_SORT_LB(true, false);
+    else if (p == NUM_PASSES - 1) RPB_SORT_LB(false, true);
+    else RPB_SORT_LB(false, false);
+#undef RPB_SORT_LB
 #undef RPB_SORT_PASS
     RPB_LAUNCH_CHECK();
     unsigned long long* t = kin; kin = kout; kout = t;

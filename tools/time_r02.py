@@ -124,7 +124,7 @@ if "sort" in which:
     k = torch.empty_like(src); v = torch.empty_like(src)
     scratch = torch.empty(ctx.sort_scratch_bytes(n, True) // 8 + 32, **f64)
     for rnd in range(2):
-        for var, lb, label in ((8, 4, "shared-bin histogram"), (7, 4, "no uniform-tile test"), (4, 1, "look-back one tile at a time"),
+        for var, lb, label in ((4, 1, "look-back one tile at a time"), (4, 2, "look-back two tiles at a time"),
                                (4, 4, "default: lane-private histogram, uniform-tile test, look-back 4 at a time")):
             ctx.set_tuning("Algorithm_SORT", -1, lb, var); ctx.set_tuning("Algorithm_SORTPAIRS", -1, lb, var)
             ms = time_ms(lambda: ctx.sort_keys(k, scratch), 5, 2, setup=lambda: k.copy_(src))
