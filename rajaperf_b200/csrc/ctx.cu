@@ -27,13 +27,15 @@ static void default_tunings(rpb200_ctx* c)
   c->tune[RPB_K_DIFFUSION3DPA]  = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_CONVECTION3DPA] = rpb_tuning{128, 0, 1};
   c->tune[RPB_K_INDEXLIST]      = rpb_tuning{512, 4, 4};
-  // halo kernels: block_size 256 = contiguous chunk ranges, 192 = the same with the PACK launches walking the work
-  // list backwards (the strided x faces are packed last, so the unpack -- which walks forward and starts with the ghost
-  // cells sharing their L2 lines -- finds them resident: 108 -> 98 us pack+unpack, 120 -> 103 us exchange on every box
-  // tried), 128 = round-robin; unroll 4 = L2 eviction hints; exchange: unroll 1 = ONE fused launch per rep, 2 / 4 = pack
-  // launch + unpack launch.  Round-robin, hints and the single launch win on some B200s and lose on others
-  // (profiles/r01_halo_variants.md); these settings never lost.
-  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{192, 4, 1};
+  // halo kernels.  HALO_PACKING_FUSED: ONE launch over the unit list (unroll 1: x-face units mixed in with the streaming
+  // units; 3: first; 5: two phases; 2 / 4: the two-launch form without / with L2 hints), 2 CTAs per SM -- fewer resident CTAs
+  // are FASTER here: 86 us at 2 per SM against 100 us at 4 per SM at 512^3, 309 against 407 us at 1024^3; the two-launch
+  // form takes 96 / 491 us (profiles/r02_f/).  Two-launch forms: block_size 256 = contiguous chunk ranges, 192 = the same
+  // with the PACK launches walking the work list backwards (the strided x faces are packed last, so the unpack -- which
+  // walks forward and starts with the ghost cells sharing their L2 lines -- finds them resident), 128 = round-robin.
+  // HALO_EXCHANGE_FUSED: unroll 2 = pack launch + unpack launch (default: 100-106 us at 512^3 on one rank against 104-122 us
+  // for the one-launch form; at 1024^3 both forms take ~435 us at 2 CTAs per SM), 1 = one launch over the unit list.
+  c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{192, 2, 1};
   c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{192, 4, 2};
 }
 

@@ -19,8 +19,8 @@ void HALO_PACKING_FUSED::setB200TuningDefinitions(VariantID vid)
 {
   addB200Tuning(vid, getDefaultTuningName());               // one launch, x-face items mixed in with the streaming items
   if (getKernelID() != rajaperf::Comm_HALO_PACKING_FUSED) return;
-  addB200Tuning(vid, "x_first", 192, 4, 3);                 // one launch, x-face units first
-  addB200Tuning(vid, "two_phases", 192, 4, 5);              // one launch: every pack unit, then every unpack unit
+  addB200Tuning(vid, "x_first", 192, 2, 3);                 // one launch, x-face units first
+  addB200Tuning(vid, "two_phases", 192, 2, 5);              // one launch: every pack unit, then every unpack unit
   addB200Tuning(vid, "two_launches", 192, 4, 2);            // pack launch + unpack launch, contiguous chunk ranges, packs walk backwards
   addB200Tuning(vid, "two_launches_forward", 256, 4, 2);    // packs walk forward too
   addB200Tuning(vid, "two_launches_round_robin", 128, 4, 2);   // chunks dealt round-robin to the CTAs
