@@ -72,7 +72,10 @@ int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
  *   Comm_HALO_PACKING_FUSED / Comm_HALO_EXCHANGE_FUSED, two-launch forms: block_size 256 = contiguous chunk ranges per CTA,
  *       192 = the same with pack launches walking the list backwards (default), 128 = round-robin; ctas_per_sm; unroll 4 = L2
  *       eviction-priority hints on.  One-launch forms (rpb200_halo_plan_pack_unpack, rpb200_halo_exchange): ctas_per_sm;
- *       exchange unroll 1 = ONE launch per rep over the item list, 2 / 4 = pack launch + unpack launch;
+ *       exchange unroll 1 = ONE launch per rep over the unit list (every pack unit, signal, wait + every unpack unit),
+ *       3 = ONE launch with pack and unpack units on one ticket and messages signalled unit by unit (the unpack of early
+ *       messages overlaps the packing of late ones), 2 / 4 = pack launch + unpack launch (default 2);
+ *       the one-launch forms need every CTA of a rank resident while its peers pack: one rank per GPU;
  *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 8 = digit histograms in shared bins instead of the lane-private 16-bit
  *       counters (default since round 2: profiles/r02_a_optin.log); 7 = no pass tests its tiles for uniformity;
  *       ctas_per_sm 1 = the look-back reads one tile descriptor at a time instead of four;
@@ -198,7 +201,7 @@ int rpb200_halo_unpack(rpb200_ctx*, const rpb200_halo_worklist*, rpb200_stream_t
 int rpb200_halo_pack_unpack(rpb200_ctx*, rpb200_halo_worklist* pack, rpb200_halo_worklist* unpack, rpb200_stream_t);
 /* Test hook, host-only (no device is touched): the unit list the one-launch kernels walk for tuples of the given geometry
  * (lengths, strided flags, message ordinals, variable ids).  order 1 / 3 / 5 = the HALO_PACKING_FUSED orders (x units mixed
- * in / first / two phases), 0 = the exchange order.  items_out: (tuple index | 1 << 30 for the unpack side, chunk) pairs;
+ * in / first / two phases), 0 = the exchange order, 6 = the progressive exchange order.  items_out: (tuple index | 1 << 30 for the unpack side, chunk) pairs;
  * unit_first_out: n_units + 1 entries.  Lets the CPU test-suite check that every (tuple, chunk) is moved exactly once.   */
 int rpb200_debug_halo_units(const int64_t* pack_len, const int* pack_strided, const int* pack_msg, const int* pack_var, int npack,
                             const int64_t* unpack_len, const int* unpack_strided, const int* unpack_msg, const int* unpack_var,

@@ -288,6 +288,7 @@ struct halo_items_args {
   const int* unit_first;                             // unit u = items [unit_first[u], unit_first[u + 1])
   unsigned int* ticket;                              // [0] phase-1 unit ticket, [1] phase-2 unit ticket, [2] CTAs done (re-armed by the last)
   int n_units, n_pack_units, npsegs, nusegs;         // XCHG: units [0, n_pack_units) are the pack phase
+  int progressive;                                   // XCHG: ONE ticket over pack and unpack units, messages signalled unit by unit
   const halo_msg* pmsgs; const halo_msg* umsgs;
   unsigned int* msg_done; unsigned long long* d_epoch; unsigned int* unpack_done; int* error;
   unsigned long long timeout_ns;
@@ -358,7 +359,28 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
   // index loads are issued during u's last item) and the ticket after that is in flight.  Heavy units (the x faces) and light
   // ones therefore balance themselves, whatever the grid.  `tk` is re-armed by the last CTA of the launch (below).
   __shared__ unsigned int s_tk[2];
-  auto run_phase = [&](unsigned int* tk, int u_lo, int u_end, bool wait_flags, unsigned int& acquired, bool& failed) {
+  // credit the messages this CTA packed since the last call (thread 0, after a CTA barrier that follows the stores): ONE
+  // system fence, then whoever completes a message publishes the epoch to the destination's flag (release at system scope)
+  auto flush_credits = [&]() {
+    __threadfence_system();
+    for (int m = 0; m < NNB; ++m) {
+      const unsigned int mine = s_credit[m];
+      if (mine == 0u) continue;
+      s_credit[m] = 0u;
+      const halo_msg hm = A.pmsgs[m];
+      const unsigned int prev = atomicAdd(A.msg_done + m, mine);
+      if (prev + mine == hm.chunks) {
+        A.msg_done[m] = 0u;              // re-armed for the next rep (stream-ordered launches)
+        st_release_sys(hm.remote_flag, epoch);
+      }
+    }
+  };
+  // mode 0: pack units (never waits); 1: unpack units (acquire each message's flag once per CTA); 2: both kinds from ONE
+  // ticket, pack units first -- a pack unit's messages are credited as soon as the unit is stored (thread 0, while the other
+  // warps go on), so flags are released message by message and the unpack of early messages overlaps the packing (and the
+  // NVLink transfer) of late ones.  No deadlock: tickets increase, so every pack unit is held by a CTA that has not drawn an
+  // unpack unit yet, pack units never wait, and the grid is co-resident.
+  auto run_phase = [&](unsigned int* tk, int u_lo, int u_end, int mode, unsigned int& acquired, bool& failed) {
     if (threadIdx.x == 0) { s_tk[0] = atomicAdd(tk, 1u); s_tk[1] = atomicAdd(tk, 1u); }
     __syncthreads();
     int u_cur = u_lo + (int)s_tk[0], u_nxt = u_lo + (int)s_tk[1];
@@ -371,6 +393,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
       if (threadIdx.x == 0) s_tk[k & 1] = atomicAdd(tk, 1u);          // the unit after u_nxt
       int n_it = -1, n_end = 0;
       if (u_nxt < u_end) { n_it = __ldg(A.unit_first + u_nxt); n_end = __ldg(A.unit_first + u_nxt + 1); }
+      const bool wait_flags = mode == 1 || (mode == 2 && u_cur >= A.n_pack_units);
       for (; it < end_it; ++it) {
         fetch(it + 1 < end_it ? it + 1 : n_it, nidx, nh);             // next item of this unit, else the first of the next unit
         if (wait_flags) {
@@ -401,6 +424,7 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
         h = nh;
       }
       __syncthreads();                                       // s_tk[k & 1] is visible; everybody is done with unit u_cur
+      if (XCHG && mode == 2 && !wait_flags && threadIdx.x == 0) flush_credits();
       u_cur = u_nxt; it = n_it; end_it = n_end;
       u_nxt = u_lo + (int)s_tk[k & 1];
     }
@@ -409,7 +433,10 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
   unsigned int acquired = 0u;            // bit m: this CTA has already seen message m's flag (thread-uniform)
   bool failed = false;
   // ---- phase 1: every unit (HALO_PACKING_FUSED) / the pack units (exchange)
-  run_phase(A.ticket + 0, 0, XCHG ? A.n_pack_units : A.n_units, false, acquired, failed);
+  if (XCHG && A.progressive) {
+    run_phase(A.ticket + 0, 0, A.n_units, 2, acquired, failed);
+  } else {
+  run_phase(A.ticket + 0, 0, XCHG ? A.n_pack_units : A.n_units, 0, acquired, failed);
   if (!XCHG) {
     if (threadIdx.x == 0) {
       const unsigned int prev = atomicAdd(A.ticket + 2, 1u);
@@ -418,25 +445,14 @@ halo_items_kernel(const __grid_constant__ halo_items_args A)
     return;
   }
 
-  // all remote stores of this CTA -> barrier -> ONE system fence -> credit every message it touched; whoever completes a
-  // message publishes the epoch to the destination's flag (release at system scope)
+  // all remote stores of this CTA -> barrier -> ONE system fence -> credit every message it touched
   __syncthreads();
-  if (threadIdx.x == 0) __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < NNB && s_credit[threadIdx.x] != 0u) {
-    const int m = threadIdx.x;
-    const halo_msg hm = A.pmsgs[m];
-    const unsigned int mine = s_credit[m];
-    const unsigned int prev = atomicAdd(A.msg_done + m, mine);
-    if (prev + mine == hm.chunks) {
-      A.msg_done[m] = 0u;                // re-armed for the next rep (stream-ordered launches)
-      st_release_sys(hm.remote_flag, epoch);
-    }
-  }
+  if (threadIdx.x == 0) flush_credits();
 
   // ---- phase 2: wait + unpack.  The grid is fully co-resident and phase 1 never waits, so every rank's flags are
   // eventually released.  A message that does not arrive within the time-out is NOT unpacked and the epoch is NOT committed.
-  run_phase(A.ticket + 1, A.n_pack_units, A.n_units, true, acquired, failed);
+  run_phase(A.ticket + 1, A.n_pack_units, A.n_units, 1, acquired, failed);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();                     // this CTA's time-out report (if any) is visible before its retirement is counted
@@ -674,6 +690,9 @@ struct rpb200_halo_plan {
   // item lists of the one-launch kernels (halo_items_kernel): HALO_PACKING_FUSED merged, exchange pack-then-unpack
   void* d_xchg_block = nullptr; const halo_item* d_items_xchg = nullptr; const int* d_unit_first_xchg = nullptr;
   unsigned int* d_ticket_xchg = nullptr;
+  // the progressive (one-ticket) exchange order
+  void* d_prog_block = nullptr; const halo_item* d_items_prog = nullptr; const int* d_unit_first_prog = nullptr;
+  unsigned int* d_ticket_prog = nullptr; int n_units_prog = 0, n_pack_units_prog = 0;
   int n_units_xchg = 0, n_pack_units_xchg = 0;
 };
 
@@ -745,7 +764,7 @@ extern "C" void rpb200_halo_plan_destroy(rpb200_halo_plan* p)
   cudaFree(p->d_window);
   cudaFree(p->d_pack_msgs); cudaFree(p->d_unpack_msgs); cudaFree(p->d_send_msgs); cudaFree(p->d_msg_done); cudaFree(p->d_error);
   cudaFree(p->d_epoch); cudaFree(p->d_unpack_done);
-  cudaFree(p->d_xchg_block);
+  cudaFree(p->d_xchg_block); cudaFree(p->d_prog_block);
   delete p;
 }
 
@@ -967,13 +986,26 @@ static void build_items_merged(const worklist_dev& pw, const worklist_dev& uw, i
 // HALO_EXCHANGE_FUSED: all pack units, then all unpack units.  The X tuples are packed LAST (ascending chunks) and unpacked
 // FIRST (descending chunks): the ghost cells share their L2 lines with the owned cells read a moment earlier (LIFO reuse
 // across the signal); the -x / +x chunks of one variable form one unit (one CTA: shared sectors, shared DRAM bursts).
-static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, unit_list& L, int* n_pack_units)
+// progressive (the one-ticket form): X pair units FIRST on both sides, ascending -- the strided faces are the slowest messages to
+// pack and to unpack, so they start first, and their flags are out after a third of the packing.
+static void build_items_xchg(const worklist_dev& pw, const worklist_dev& uw, unit_list& L, int* n_pack_units, bool progressive = false)
 {
   const int64_t xlen = x_tuple_len(pw, uw);
   std::vector<std::vector<halo_item>> sp, su;
   stream_groups(pw, xlen, 0, sp);
   stream_groups(uw, xlen, ITEM_UNPACK, su);
   const auto xp = by_variable(x_tuples(pw, uw, xlen, true, false)), xu = by_variable(x_tuples(pw, uw, xlen, false, true));
+  if (progressive) {
+    for (int64_t c = 0; c < plan_chunks(xlen); ++c)
+      for (const auto& var : xp) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+    for (const auto& g : sp) L.add_singles(g);
+    *n_pack_units = L.units();
+    for (int64_t c = 0; c < plan_chunks(xlen); ++c)
+      for (const auto& var : xu) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
+    for (const auto& g : su) L.add_singles(g);
+    L.finish();
+    return;
+  }
   for (const auto& g : sp) L.add_singles(g);
   for (int64_t c = 0; c < plan_chunks(xlen); ++c)
     for (const auto& var : xp) { std::vector<halo_item> g; for (const x_ref& r : var) g.push_back(halo_item{r.seg, (int)c}); L.add_unit(g); }
@@ -1059,7 +1091,7 @@ static int worklist_pack_unpack(rpb200_ctx* ctx, worklist_dev& pw, worklist_dev&
 
 // Host-only: the unit list the one-launch kernels would walk for tuples of the given geometry (no device memory is touched, so
 // the CPU test-suite checks the builders: every (tuple, chunk) exactly once, units well-formed, pack units before unpack units
-// for the exchange).  order: 1 / 3 / 5 = the HALO_PACKING_FUSED orders, 0 = the exchange order.
+// for the exchange).  order: 1 / 3 / 5 = the HALO_PACKING_FUSED orders, 0 = the exchange order, 6 = the progressive exchange order.
 extern "C" int rpb200_debug_halo_units(const int64_t* pack_len, const int* pack_strided, const int* pack_msg, const int* pack_var, int npack,
                                        const int64_t* unpack_len, const int* unpack_strided, const int* unpack_msg, const int* unpack_var,
                                        int nunpack, int order, int* items_out, int max_items, int* unit_first_out, int max_units,
@@ -1081,7 +1113,7 @@ extern "C" int rpb200_debug_halo_units(const int64_t* pack_len, const int* pack_
   fill(uw, unpack_len, unpack_strided, unpack_msg, unpack_var, nunpack);
   unit_list L;
   int npu = 0;
-  if (order == 0) build_items_xchg(pw, uw, L, &npu);
+  if (order == 0 || order == 6) build_items_xchg(pw, uw, L, &npu, order == 6);
   else build_items_merged(pw, uw, order, L);
   *n_items = (int)L.items.size(); *n_units = L.units();
   if (n_pack_units) *n_pack_units = npu;
@@ -1234,7 +1266,7 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
   }
   RPB_CHECK(cudaMemcpy(p->d_pack_msgs, pm.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
   RPB_CHECK(cudaMemcpy(p->d_unpack_msgs, um.data(), sizeof(halo_msg) * NNB, cudaMemcpyHostToDevice));
-  p->n_units_xchg = 0;
+  p->n_units_xchg = 0; p->n_units_prog = 0;
   if (!p->vars.empty() && NNB * p->nvars <= ITEMS_MAX_SEGS) {
     unit_list L;
     int n_pack = 0;
@@ -1242,6 +1274,11 @@ static int exchange_finish_connect(rpb200_halo_plan* p)
     const int rc = upload_units(L, &p->d_xchg_block, &p->d_items_xchg, &p->d_unit_first_xchg, &p->d_ticket_xchg);
     if (rc != 0) return rc;
     p->n_units_xchg = L.units(); p->n_pack_units_xchg = n_pack;
+    unit_list P;
+    build_items_xchg(p->xpack_wl[0], p->xunpack_wl[0], P, &n_pack, true);
+    const int rc2 = upload_units(P, &p->d_prog_block, &p->d_items_prog, &p->d_unit_first_prog, &p->d_ticket_prog);
+    if (rc2 != 0) return rc2;
+    p->n_units_prog = P.units(); p->n_pack_units_prog = n_pack;
   }
   p->connected = true;
   return 0;
@@ -1335,8 +1372,13 @@ extern "C" int rpb200_halo_exchange(rpb200_halo_plan* p, rpb200_stream_t s)
   memset(&A, 0, sizeof(A));
   A.psegs[0] = p->xpack_wl[0].d_segs; A.psegs[1] = p->xpack_wl[1].d_segs;
   A.usegs[0] = p->xunpack_wl[0].d_segs; A.usegs[1] = p->xunpack_wl[1].d_segs;
-  A.items = p->d_items_xchg; A.unit_first = p->d_unit_first_xchg; A.ticket = p->d_ticket_xchg;
-  A.n_units = p->n_units_xchg; A.n_pack_units = p->n_pack_units_xchg;
+  if (t.unroll == 3 && p->n_units_prog > 0) {       // tuning `unroll` 3: the progressive one-ticket form
+    A.items = p->d_items_prog; A.unit_first = p->d_unit_first_prog; A.ticket = p->d_ticket_prog;
+    A.n_units = p->n_units_prog; A.n_pack_units = p->n_pack_units_prog; A.progressive = 1;
+  } else {
+    A.items = p->d_items_xchg; A.unit_first = p->d_unit_first_xchg; A.ticket = p->d_ticket_xchg;
+    A.n_units = p->n_units_xchg; A.n_pack_units = p->n_pack_units_xchg;
+  }
   A.npsegs = p->xpack_wl[0].nsegs; A.nusegs = p->xunpack_wl[0].nsegs;
   A.pmsgs = p->d_pack_msgs; A.umsgs = p->d_unpack_msgs; A.msg_done = p->d_msg_done; A.d_epoch = p->d_epoch;
   A.unpack_done = p->d_unpack_done; A.error = p->d_error; A.timeout_ns = halo_timeout_ns();

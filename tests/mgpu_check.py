@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity check, launched by torchrun (one rank per GPU):
   * HALO_EXCHANGE_FUSED on the default rank grid vs the CPU simulation of the same grid (bit-exact), in both launch forms
-    (pack launch + unpack launch; ONE launch over the item list)
+    (pack launch + unpack launch; ONE launch in two phases; ONE launch with progressive signalling)
   * global DOT / REDUCE_SUM: shards + one all-reduced scalar vs the oracle on the whole array.
 Rank 0 prints `MGPU_CHECK PASS|FAIL ...` and one JSON line with what was compared (tools/gpu_r02_mgpu.sh keeps both)."""
 import json
@@ -27,7 +27,7 @@ ctx = Context(local)
 pd = rdist.rank_grid(world)
 ok = True
 cases = []
-for unroll, dims, hw, nv, reps in [(u,) + c for u in (2, 1) for c in (((6, 6, 6), 1, 3, 3), ((40, 40, 40), 2, 2, 4), ((128, 128, 128), 1, 3, 5),
+for unroll, dims, hw, nv, reps in [(u,) + c for u in (2, 1, 3) for c in (((6, 6, 6), 1, 3, 3), ((40, 40, 40), 2, 2, 4), ((128, 128, 128), 1, 3, 5),
                                                                         ((252, 252, 252), 1, 3, 2))]:
     ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=unroll)
     plan = ctx.halo_plan(dims, hw, nv, rank, pd)
@@ -46,7 +46,7 @@ for unroll, dims, hw, nv, reps in [(u,) + c for u in (2, 1) for c in (((6, 6, 6)
             print(f"rank {rank}: halo mismatch dims={dims} var={v}", flush=True)
     dist.barrier()
     plan.close()
-    cases.append({"launches_per_rep": 1 if unroll == 1 else 2, "cells": list(dims), "halo_width": hw, "vars": nv, "reps": reps})
+    cases.append({"form": {2: "pack launch + unpack launch", 1: "one launch, two phases", 3: "one launch, progressive"}[unroll], "cells": list(dims), "halo_width": hw, "vars": nv, "reps": reps})
 ctx.reset_tuning("Comm_HALO_EXCHANGE_FUSED")
 
 n = 3000001

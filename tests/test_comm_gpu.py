@@ -395,7 +395,7 @@ def test_halo_exchange_fused_suite_checksum_single_rank(ctx, size, reps, hw, nv)
     plan.close()
 
 
-@pytest.mark.parametrize("unroll", [2, 1], ids=["two_launches", "one_launch"])
+@pytest.mark.parametrize("unroll", [2, 1, 3], ids=["two_launches", "one_launch", "one_launch_progressive"])
 def test_halo_full_size_properties(ctx, unroll):
     """512^3 per GPU (BASELINE config 5): after one exchange every ghost cell equals the periodic
     image of an owned cell; a second exchange is idempotent; owned cells are never modified."""
@@ -430,17 +430,18 @@ def _halo_full_size_properties(ctx, n, hw, nv):
     plan.close()
 
 
+@pytest.mark.parametrize("unroll", [1, 3], ids=["two_phases", "progressive"])
 @pytest.mark.parametrize("dims,hw,nv", [((6, 6, 6), 1, 3), ((20, 20, 20), 2, 2), ((64, 64, 64), 1, 3), ((252, 252, 252), 1, 3)])
-def test_halo_exchange_one_launch_form_bit_exact(ctx, dims, hw, nv):
-    """Tuning `unroll` 1 of Comm_HALO_EXCHANGE_FUSED: the whole rep is ONE launch over the item list (all pack items, signal,
-    wait + unpack items).  One rank per GPU only (every CTA of a rank must be resident while its peers pack), so on one GPU
+def test_halo_exchange_one_launch_form_bit_exact(ctx, dims, hw, nv, unroll):
+    """Tunings `unroll` 1 / 3 of Comm_HALO_EXCHANGE_FUSED: the whole rep is ONE launch over the unit list (1: all pack units,
+    signal, wait + unpack units; 3: one ticket over both kinds, messages signalled unit by unit).  One rank per GPU only (every CTA of a rank must be resident while its peers pack), so on one GPU
     this is the 1 x 1 x 1 rank grid: 26 self-messages, i.e. the periodic self-exchange of the oracle."""
     reps = 3
     plan = ctx.halo_plan(dims, hw, nv)
     vs = [torch.arange(plan.var_size, dtype=torch.float64, device="cuda") + v for v in range(nv)]
     plan.window(vs, want_handle=False)
     plan.connect_ptrs([0])
-    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=1)
+    ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", unroll=unroll)
     try:
         for _ in range(reps):
             plan.exchange()

@@ -56,22 +56,79 @@ def verified():
         t = torch.tensor([0.0 if ok else 1.0], **f64); dist.all_reduce(t, op=dist.ReduceOp.MAX); ok = t.item() == 0.0
     return bool(ok)
 
+def nvlink_kib(idx):
+    """cumulative NVLink data counters of GPU idx, summed over its links (nvidia-smi nvlink -gt d): (tx KiB, rx KiB) or None"""
+    import re, subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(idx)], capture_output=True, text=True, timeout=20).stdout
+        tx = sum(int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+        rx = sum(int(x) for x in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+        return (tx, rx) if (tx or rx) else None
+    except Exception:
+        return None
+
+
+def split_us(reps=200):
+    """pack launch and unpack launch timed separately (CUDA events inside a plain rep loop; each kernel is several times
+    longer than the host's launch cost, so the loop is GPU-bound): (pack us, unpack us), max over ranks"""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps + 1)]
+    for _ in range(5):
+        plan.exchange_pack(); plan.exchange_unpack()
+    torch.cuda.synchronize()
+    if world > 1: dist.barrier()
+    ev[0].record()
+    for r in range(reps):
+        plan.exchange_pack(); ev[2 * r + 1].record()
+        plan.exchange_unpack(); ev[2 * r + 2].record()
+    torch.cuda.synchronize()
+    pk = sum(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps)) / reps * 1e3
+    up = sum(ev[2 * r + 1].elapsed_time(ev[2 * r + 2]) for r in range(reps)) / reps * 1e3
+    if world > 1:
+        t = torch.tensor([pk, up], **f64); dist.all_reduce(t, op=dist.ReduceOp.MAX); pk, up = float(t[0]), float(t[1])
+    return round(pk, 1), round(up, 1)
+
+
 res, ver = {}, {}
 reps = 100 if g <= 512 else 40
+forms = ((192, 4, 2), (192, 2, 2), (192, 4, 3), (192, 2, 3)) if os.environ.get("FORMS", "") == "two" else ((192, 4, 2), (192, 4, 1), (192, 4, 3), (192, 2, 3))
 for rnd in range(2):
-    for blk, cps, xu in ((192, 4, 2), (192, 4, 1), (192, 3, 1)):
+    for blk, cps, xu in forms:
         ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
         for v in range(nv):                                     # fresh ghost cells: the check must see THIS form's work
             vars_[v].copy_(torch.arange(plan.var_size, **f64) + v)
             e = g + 2
             a = vars_[v].view(e, e, e)
             a[0].fill_(-1.0); a[-1].fill_(-1.0); a[:, 0].fill_(-1.0); a[:, -1].fill_(-1.0); a[:, :, 0].fill_(-1.0); a[:, :, -1].fill_(-1.0)
+        plan.exchange(); torch.cuda.synchronize()
+        try:
+            plan.status()
+        except Exception as e:                               # a flag wait timed out: do not replay 100 such reps
+            res[f"{xu}/{cps} FAILED"] = str(e)[:80]
+            break
         ms = graph_ms(plan.exchange, reps)
         plan.status()
-        key = f"{'1 launch' if xu == 1 else '2 launches'}, {cps} CTAs/SM"
+        key = f"{ {1: '1 launch two phases', 2: '2 launches', 3: '1 launch progressive'}[xu] }, {cps} CTAs/SM"
         res[key] = min(res.get(key, 1e9), round(ms * 1e3, 1))
         ver[key] = ver.get(key, True) and verified()
+# the default form once more, pack and unpack launches timed separately, with the NVLink byte counters of GPU `local` around it
+ctx.reset_tuning("Comm_HALO_EXCHANGE_FUSED")
+n_split = 200
+before = nvlink_kib(local) if rank == 0 else None
+pack_us, unpack_us = split_us(n_split)
+plan.status()
+after = nvlink_kib(local) if rank == 0 else None
+halo_bytes = 8 * nv * sum(nb["pack_len"] for nb in plan.neighbors)
+remote_bytes = 8 * nv * sum(nb["pack_len"] for nb in plan.neighbors if nb["rank"] != rank)
 if rank == 0:
-    print(json.dumps({"n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": g, "us_per_rep": res, "verified": ver}), flush=True)
+    out = {"n_gpus": world, "rank_grid": rank_grid(world), "cells_per_gpu": g, "us_per_rep": res, "verified": ver,
+           "default_form_split": {"pack_launch_us": pack_us, "unpack_launch_us": unpack_us, "reps": n_split},
+           "bytes_packed_per_rep": halo_bytes, "bytes_to_other_gpus_per_rep": remote_bytes}
+    if remote_bytes and pack_us:
+        out["remote_store_gbs_if_pack_bound"] = round(remote_bytes / pack_us / 1e3, 1)
+    if before and after:
+        out["nvlink_counters_rank0"] = {"tx_bytes_per_rep": round((after[0] - before[0]) * 1024 / (n_split + 5)),
+                                        "rx_bytes_per_rep": round((after[1] - before[1]) * 1024 / (n_split + 5)),
+                                        "how": "nvidia-smi nvlink -gt d, summed over links, around the split-timing loop"}
+    print(json.dumps(out), flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

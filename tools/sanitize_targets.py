@@ -91,12 +91,12 @@ if "halo" in which:
     e = g + 2
     idx = torch.arange(e, device="cuda"); src = ((idx - 1) % g) + 1
     want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64)
-    for unroll in (1, 2):                                            # one-launch item list / pack launch + unpack launch
+    for unroll in (1, 2, 3):                                         # one launch (two phases) / pack launch + unpack launch / one launch (progressive)
         vars_ = mk()
         pb = [torch.zeros(nv * nb["pack_len"], **f64) for nb in plan.neighbors]
         ub = [torch.full((nv * nb["unpack_len"],), 7.0, **f64) for nb in plan.neighbors]
         plan.bind(vars_, pb, ub)
-        ctx.set_tuning("Comm_HALO_PACKING_FUSED", -1, -1, unroll)
+        ctx.set_tuning("Comm_HALO_PACKING_FUSED", -1, -1, 1 if unroll == 3 else unroll)
         for _ in range(2):
             plan.pack_unpack()
         torch.cuda.synchronize()
