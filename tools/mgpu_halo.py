@@ -90,7 +90,7 @@ def split_us(reps=200):
 
 res, ver = {}, {}
 reps = 100 if g <= 512 else 40
-forms = ((192, 4, 2), (192, 2, 2), (192, 4, 3), (192, 2, 3)) if os.environ.get("FORMS", "") == "two" else ((192, 4, 2), (192, 4, 1), (192, 4, 3), (192, 2, 3))
+forms = ((192, 4, 2), (192, 2, 2), (192, 2, 3)) if os.environ.get("FORMS", "") == "two" else ((192, 4, 2), (192, 4, 1), (192, 4, 3), (192, 2, 3))
 for rnd in range(2):
     for blk, cps, xu in forms:
         ctx.set_tuning("Comm_HALO_EXCHANGE_FUSED", blk, cps, xu)
