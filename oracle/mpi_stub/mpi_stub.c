@@ -81,8 +81,12 @@ typedef struct {
   pthread_mutex_t mu;
   pthread_cond_t cv;
   int bar_count, bar_gen;
-  int nmsgs, first_untaken;
-  size_t heap_top, heap_end;     /* bump allocator for payloads; rewound when every message has been taken */
+  /* the message log and the payload heap are RINGS: first_untaken .. nmsgs are monotonically increasing message numbers
+   * (slot = number % SHM_MAX_MSGS); payloads are allocated at heap_top, wrapping to heap_base, and freed in log order as
+   * the oldest messages are taken.  A sender that finds no room waits (ranks that run ahead of their peers -- GPU variants
+   * on 8 ranks -- once exhausted a bump allocator that was only rewound when NOTHING was in flight: round 2).            */
+  size_t nmsgs, first_untaken;
+  size_t heap_top, heap_end, heap_base;
   char coll[SHM_MAX_RANKS][SHM_SLOT_BYTES];
   shm_msg_t msgs[SHM_MAX_MSGS];
 } shm_t;
@@ -110,27 +114,49 @@ static void shm_barrier(void)
   shm_unlock();
 }
 
-/* mutex held: the oldest untaken message src -> me with this tag, or -1 */
-static int shm_find(int src, int tag)
+#define SHM_MSG(n) (&g_shm->msgs[(n) % SHM_MAX_MSGS])
+
+/* mutex held: the oldest untaken message src -> me with this tag (its message number), or -1 */
+static long shm_find(int src, int tag)
 {
-  for (int i = g_shm->first_untaken; i < g_shm->nmsgs; ++i) {
-    const shm_msg_t* m = &g_shm->msgs[i];
-    if (!m->taken && m->dst == g_rank && m->src == src && m->tag == tag) return i;
+  for (size_t i = g_shm->first_untaken; i < g_shm->nmsgs; ++i) {
+    const shm_msg_t* m = SHM_MSG(i);
+    if (!m->taken && m->dst == g_rank && m->src == src && m->tag == tag) return (long)i;
   }
   return -1;
 }
 
-/* mutex held: copy message i out and retire it */
-static void shm_take(int i, void* buf, size_t bytes)
+/* mutex held: copy message i out and retire it; the log and the heap are freed from their old end */
+static void shm_take(long i, void* buf, size_t bytes)
 {
-  shm_msg_t* m = &g_shm->msgs[i];
+  shm_msg_t* m = SHM_MSG((size_t)i);
   if (m->bytes > bytes) die("message longer than the posted receive");
   memcpy(buf, g_arena + m->offset, m->bytes);
   m->taken = 1;
-  while (g_shm->first_untaken < g_shm->nmsgs && g_shm->msgs[g_shm->first_untaken].taken) ++g_shm->first_untaken;
-  if (g_shm->first_untaken == g_shm->nmsgs) {              /* nothing in flight: rewind the log and the heap */
-    g_shm->nmsgs = 0; g_shm->first_untaken = 0; g_shm->heap_top = sizeof(shm_t);
+  const size_t before = g_shm->first_untaken;
+  while (g_shm->first_untaken < g_shm->nmsgs && SHM_MSG(g_shm->first_untaken)->taken) ++g_shm->first_untaken;
+  if (g_shm->first_untaken == g_shm->nmsgs) g_shm->heap_top = g_shm->heap_base;       /* nothing in flight */
+  if (g_shm->first_untaken != before) pthread_cond_broadcast(&g_shm->cv);             /* room for a waiting sender */
+}
+
+/* mutex held: room for `need` payload bytes in the ring (the live region runs from the oldest untaken message's payload to
+ * heap_top, possibly wrapped); returns the offset or 0 */
+static size_t shm_alloc(size_t need)
+{
+  if (g_shm->first_untaken == g_shm->nmsgs) {                 /* empty */
+    if (g_shm->heap_base + need > g_shm->heap_end) die("one message is larger than the arena (--arena-mb)");
+    g_shm->heap_top = g_shm->heap_base + need;
+    return g_shm->heap_base;
   }
+  const size_t head = SHM_MSG(g_shm->first_untaken)->offset;
+  size_t top = g_shm->heap_top;
+  if (top >= head) {                                          /* not wrapped: [head, top) is live */
+    if (top + need <= g_shm->heap_end) { g_shm->heap_top = top + need; return top; }
+    if (g_shm->heap_base + need <= head && head > g_shm->heap_base) { g_shm->heap_top = g_shm->heap_base + need; return g_shm->heap_base; }
+    return 0;
+  }
+  if (top + need <= head) { g_shm->heap_top = top + need; return top; }              /* wrapped: [head, end) and [base, top) are live */
+  return 0;
 }
 
 int MPI_Init(int* argc, char*** argv)
@@ -156,7 +182,9 @@ int MPI_Init(int* argc, char*** argv)
     pthread_mutexattr_init(&ma); pthread_mutexattr_setpshared(&ma, PTHREAD_PROCESS_SHARED);
     pthread_condattr_init(&ca); pthread_condattr_setpshared(&ca, PTHREAD_PROCESS_SHARED);
     pthread_mutex_init(&g_shm->mu, &ma); pthread_cond_init(&g_shm->cv, &ca);
-    g_shm->heap_top = sizeof(shm_t); g_shm->heap_end = (size_t)st.st_size;
+    g_shm->heap_base = (sizeof(shm_t) + 63) & ~(size_t)63;
+    g_shm->heap_top = g_shm->heap_base; g_shm->heap_end = (size_t)st.st_size;
+    g_shm->nmsgs = 0; g_shm->first_untaken = 0;
     __atomic_store_n(&g_shm->ready, 1, __ATOMIC_RELEASE);
   } else {
     while (!__atomic_load_n(&g_shm->ready, __ATOMIC_ACQUIRE)) usleep(100);
@@ -288,11 +316,15 @@ int MPI_Isend(const void* buf, int count, MPI_Datatype type, int dest, int tag, 
   if (g_size > 1) {                                        /* P ranks: append to the shared log, buffered */
     shm_lock();
     const size_t need = (bytes + 63) & ~(size_t)63;
-    if (g_shm->nmsgs >= SHM_MAX_MSGS || g_shm->heap_top + need > g_shm->heap_end) die("message arena exhausted");
-    shm_msg_t* m = &g_shm->msgs[g_shm->nmsgs++];
-    m->src = g_rank; m->dst = dest; m->tag = tag; m->taken = 0; m->bytes = bytes; m->offset = g_shm->heap_top;
+    size_t off = 0;
+    for (;;) {                                             /* a full ring: wait for receivers (60 s without progress: die) */
+      if (g_shm->nmsgs - g_shm->first_untaken < SHM_MAX_MSGS && (need == 0 || (off = shm_alloc(need)) != 0)) break;
+      shm_wait();
+    }
+    shm_msg_t* m = SHM_MSG(g_shm->nmsgs);
+    g_shm->nmsgs++;
+    m->src = g_rank; m->dst = dest; m->tag = tag; m->taken = 0; m->bytes = bytes; m->offset = need ? off : g_shm->heap_base;
     memcpy(g_arena + m->offset, buf, bytes);
-    g_shm->heap_top += need;
     pthread_cond_broadcast(&g_shm->cv);
     shm_unlock();
     g_slots[r].delivered = 1;                              /* the payload left this process: the request is complete */
@@ -335,7 +367,7 @@ int MPI_Wait(MPI_Request* req, MPI_Status* status)
   if (g_size > 1 && *req != MPI_REQUEST_NULL && g_slots[*req].kind == 1 && !g_slots[*req].done) {
     slot_t* s = &g_slots[*req];
     shm_lock();
-    int i;
+    long i;
     while ((i = shm_find(s->peer, s->tag)) < 0) shm_wait();
     shm_take(i, s->buf, s->bytes);
     shm_unlock();
@@ -374,7 +406,7 @@ int MPI_Waitany(int count, MPI_Request* reqs, int* index, MPI_Status* status)
       for (int i = 0; i < count; ++i) {
         if (reqs[i] == MPI_REQUEST_NULL) continue;
         slot_t* s = &g_slots[reqs[i]];
-        const int m = shm_find(s->peer, s->tag);
+        const long m = shm_find(s->peer, s->tag);
         if (m >= 0) {
           shm_take(m, s->buf, s->bytes);
           shm_unlock();

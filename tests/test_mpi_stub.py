@@ -161,3 +161,52 @@ def test_shared_memory_transport_ring_and_collectives(mpi, nranks, tmp_path):
     finally:
         os.unlink(arena)
     assert rcs == [0] * nranks
+
+
+_RING_PROGRAM = r"""
+import ctypes, sys
+import numpy as np
+L = ctypes.CDLL(sys.argv[1])
+p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+L.MPI_Init(None, None)
+r, s = ctypes.c_int(), ctypes.c_int()
+L.MPI_Comm_rank(0, ctypes.byref(r)); L.MPI_Comm_size(0, ctypes.byref(s))
+r, s = r.value, s.value
+right, left = (r + 1) % s, (r - 1) % s
+n = 1 << 19                                   # 4 MiB messages
+ok = True
+for rep in range(40):                         # 40 reps x s ranks x 2 messages x 4 MiB >> the 48 MiB of payload room
+    out1, out2 = np.full(n, 1000.0 * rep + r), np.full(n, -1000.0 * rep - r)
+    in1, in2 = np.zeros(n), np.zeros(n)
+    req = (ctypes.c_int * 4)()
+    L.MPI_Irecv(p(in1), n, 8, left, 1, 0, ctypes.byref(req, 0))
+    L.MPI_Irecv(p(in2), n, 8, right, 2, 0, ctypes.byref(req, 4))
+    L.MPI_Isend(p(out1), n, 8, right, 1, 0, ctypes.byref(req, 8))
+    L.MPI_Isend(p(out2), n, 8, left, 2, 0, ctypes.byref(req, 12))
+    L.MPI_Waitall(4, req, None)               # no barrier between reps: ranks drift apart, messages of several reps are in flight
+    ok = ok and np.all(in1 == 1000.0 * rep + left) and np.all(in2 == -1000.0 * rep - right)
+L.MPI_Finalize()
+sys.exit(0 if ok else 3)
+"""
+
+
+def test_shared_memory_arena_is_a_ring(mpi, tmp_path):
+    """More bytes than the arena holds pass through it when ranks are not in lock step: the message log and the payload heap
+    are rings, and a sender that finds no room waits for a receiver (round 2: a bump allocator that was only rewound when
+    nothing was in flight ran out under 8 GPU ranks and hung the reference driver)."""
+    import subprocess
+    import sys
+    nranks = 4
+    prog = tmp_path / "ring.py"
+    prog.write_text(_RING_PROGRAM)
+    arena = f"/dev/shm/rpb_mpi_test_ring_{os.getpid()}"
+    with open(arena, "wb") as f:
+        f.truncate(96 << 20)                   # ~45 MiB of bookkeeping + ~50 MiB of payload room: 12 messages
+    try:
+        procs = [subprocess.Popen([sys.executable, str(prog), SO],
+                                  env=dict(os.environ, RPB_MPI_SIZE=str(nranks), RPB_MPI_RANK=str(r), RPB_MPI_SHM=arena))
+                 for r in range(nranks)]
+        rcs = [p.wait(timeout=180) for p in procs]
+    finally:
+        os.unlink(arena)
+    assert rcs == [0] * nranks

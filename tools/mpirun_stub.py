@@ -19,7 +19,7 @@ def main():
     ap.add_argument("-n", type=int, required=True)
     ap.add_argument("--gpu-per-rank", action="store_true")
     ap.add_argument("--all-output", action="store_true")
-    ap.add_argument("--arena-mb", type=int, default=1024)
+    ap.add_argument("--arena-mb", type=int, default=0, help="shared-memory arena (default: 512 MB per rank, at least 1024)")
     ap.add_argument("--timeout", type=int, default=900)
     ap.add_argument("cmd", nargs=argparse.REMAINDER)
     a = ap.parse_args()
@@ -34,9 +34,13 @@ def main():
             ngpu = 0
         if ngpu == 0:
             sys.exit("--gpu-per-rank: no GPU visible")
+    import tempfile
+    import time
+    arena_mb = a.arena_mb or max(1024, 512 * a.n)
     path = f"/dev/shm/rpb_mpi_{os.getpid()}"
     with open(path, "wb") as f:
-        f.truncate(a.arena_mb << 20)
+        f.truncate(arena_mb << 20)
+    logs = []
     try:
         procs = []
         for r in range(a.n):
@@ -45,9 +49,32 @@ def main():
             if ngpu:      # rotated list: device 0 is this rank's GPU, the others stay visible (CUDA IPC needs the peer's device)
                 env["CUDA_VISIBLE_DEVICES"] = ",".join(str((r + i) % ngpu) for i in range(ngpu))
             quiet = r != 0 and not a.all_output
-            procs.append(subprocess.Popen(cmd, env=env, stdout=subprocess.DEVNULL if quiet else None,
-                                          stderr=subprocess.DEVNULL if quiet else None))
-        rcs = [p.wait(timeout=a.timeout) for p in procs]
+            log = tempfile.TemporaryFile(mode="w+") if quiet else None       # kept: shown if the rank fails
+            logs.append(log)
+            procs.append(subprocess.Popen(cmd, env=env, stdout=log if quiet else None, stderr=subprocess.STDOUT if quiet else None))
+        # poll: the first rank that exits non-zero takes the others down (they would wait for it until their own time-out)
+        t0 = time.time()
+        rcs = [None] * a.n
+        while any(rc is None for rc in rcs):
+            for r, p in enumerate(procs):
+                if rcs[r] is None:
+                    rcs[r] = p.poll()
+            failed = [r for r, rc in enumerate(rcs) if rc not in (None, 0)]
+            if failed or time.time() - t0 > a.timeout:
+                for r, p in enumerate(procs):
+                    if rcs[r] is None:
+                        p.kill()
+                        rcs[r] = p.wait()
+                if not failed:
+                    print(f"[mpirun_stub] time-out after {a.timeout} s", file=sys.stderr)
+                    rcs = [rc if rc else 124 for rc in rcs]
+                break
+            time.sleep(0.05)
+        for r, rc in enumerate(rcs):
+            if rc and logs[r] is not None:
+                logs[r].seek(0)
+                tail = logs[r].read()[-2000:]
+                print(f"[mpirun_stub] rank {r} exited with {rc}; its output ended with:\n{tail}", file=sys.stderr)
     finally:
         os.unlink(path)
     bad = [rc for rc in rcs if rc]
