@@ -3,7 +3,7 @@
   * HALO_EXCHANGE_FUSED on the default rank grid vs the CPU simulation of the same grid (bit-exact), in both launch forms
     (pack launch + unpack launch; ONE launch in two phases; ONE launch with progressive signalling)
   * global DOT / REDUCE_SUM: shards + one all-reduced scalar vs the oracle on the whole array.
-Rank 0 prints `MGPU_CHECK PASS|FAIL ...` and one JSON line with what was compared (tools/gpu_r02_mgpu.sh keeps both)."""
+Rank 0 prints `MGPU_CHECK PASS|FAIL ...` and one JSON line with what was compared (tools/gpu_call.sh mgpu_check:P keeps both)."""
 import json
 import os
 import sys
