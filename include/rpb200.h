@@ -74,7 +74,8 @@ int rpb200_stream_detach(rpb200_ctx* ctx, rpb200_stream_t stream);
  *       eviction-priority hints on.  One-launch forms (rpb200_halo_plan_pack_unpack, rpb200_halo_exchange): ctas_per_sm;
  *       exchange unroll 1 = ONE launch per rep over the unit list (every pack unit, signal, wait + every unpack unit),
  *       3 = ONE launch with pack and unpack units on one ticket and messages signalled unit by unit (the unpack of early
- *       messages overlaps the packing of late ones), 2 / 4 = pack launch + unpack launch (default 2);
+ *       messages overlaps the packing of late ones), 2 / 4 = pack launch + unpack launch (default 2); exchange ctas_per_sm
+ *       0 (default) = automatic: 4, or 2 for the two launches of a rep of more than 5000 chunks (1024^3 cells per rank);
  *       the one-launch forms need every CTA of a rank resident while its peers pack: one rank per GPU;
  *   Algorithm_SORT / Algorithm_SORTPAIRS: unroll 8 = digit histograms in shared bins instead of the lane-private 16-bit
  *       counters (default since round 2: profiles/r02_a_optin.log); 7 = no pass tests its tiles for uniformity;

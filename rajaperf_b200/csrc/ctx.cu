@@ -34,9 +34,10 @@ static void default_tunings(rpb200_ctx* c)
   // with the PACK launches walking the work list backwards (the strided x faces are packed last, so the unpack -- which
   // walks forward and starts with the ghost cells sharing their L2 lines -- finds them resident), 128 = round-robin.
   // HALO_EXCHANGE_FUSED: unroll 2 = pack launch + unpack launch (default: 100-106 us at 512^3 on one rank against 104-122 us
-  // for the one-launch form; at 1024^3 both forms take ~435 us at 2 CTAs per SM), 1 = one launch over the unit list.
+  // for the one-launch form; at 1024^3 both forms take ~435 us at 2 CTAs per SM), 1 = one launch over the unit list;
+  // ctas_per_sm 0 = automatic (csrc/halo.cu: 4 per SM, 2 for the two launches of a rep of more than 5000 chunks -- 1024^3).
   c->tune[RPB_K_HALO_PACKING_FUSED]  = rpb_tuning{192, 2, 1};
-  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{192, 4, 2};
+  c->tune[RPB_K_HALO_EXCHANGE_FUSED] = rpb_tuning{192, 0, 2};
 }
 
 extern "C" const char* rpb200_version(void) { return "rajaperf-b200 0.1 (sm_100a)"; }

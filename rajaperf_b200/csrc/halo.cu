@@ -587,6 +587,9 @@ struct exchange_args {
   int* error = nullptr;
 };
 
+// two-launch exchange, ctas_per_sm left automatic: launches over more chunks than this run 2 CTAs per SM instead of 4
+constexpr int64_t HALO_AUTO_CPS_CHUNKS = 5000;
+
 // seg_lo < 0: the whole work list; else only the tuples [seg_lo, seg_hi)
 template <bool PACK, int MODE>
 int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const exchange_args& x, cudaStream_t st,
@@ -600,7 +603,12 @@ int worklist_launch(const rpb200_ctx* ctx, int kid, const worklist_dev& w, const
     chunk_hi = seg_hi < w.nsegs ? w.first[seg_hi] : w.total_chunks;
     if (chunk_hi == chunk_lo && !(MODE == 2 && commit)) return 0;        // empty tuples: nothing to launch
   }
-  const int cps = ctx->tune[kid].ctas_per_sm > 0 ? ctx->tune[kid].ctas_per_sm : 4;
+  // ctas_per_sm 0 = automatic: 4 CTAs per SM, except for exchange launches over more than HALO_AUTO_CPS_CHUNKS chunks, which
+  // take 2 -- measured with both settings on the same boxes (profiles/r02_f/, profiles/r02_mgpu/): 512^3 cells per rank
+  // (2313 chunks) 100-106 us at 4 per SM against 110-118 us at 2; 1024^3 (9234 chunks) 504 against 437 us on one rank and
+  // 547 against 549 us on 2 x 2 x 2 ranks.
+  int cps = ctx->tune[kid].ctas_per_sm;
+  if (cps <= 0) cps = (kid == RPB_K_HALO_EXCHANGE_FUSED && chunk_hi - chunk_lo > HALO_AUTO_CPS_CHUNKS) ? 2 : 4;
   int64_t grid = (int64_t)ctx->sm_count * cps;
   if (grid > chunk_hi - chunk_lo) grid = chunk_hi - chunk_lo;
   if (grid < 1) grid = 1;
