@@ -569,6 +569,20 @@ def run_e2e(torch, dist, ctx, dev, world, n, x0, x1, y, alpha, steps, dot_reside
                    "of the output; DOT + D2H of the partial) -> host; wall clock around stream syncs, max over ranks"}
 
 
+def ghosts_are_periodic_images(torch, vars_, g, hw, dev):
+    """Every rank holds var[i] = i + v, so after an exchange on ANY rank grid each ghost cell must hold the value of
+    its periodic image inside the owned box, and owned cells must be untouched (tests/test_comm_gpu.py: the full-size
+    property test; tests/test_bench_cpu.py checks this function against the CPU simulation of the exchange).  All variables,
+    compared on the device the variables live on."""
+    e = g + 2 * hw
+    idx = torch.arange(e, device=dev)
+    src = ((idx - hw) % g) + hw
+    want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64)
+    ok = all(bool(torch.equal(vars_[v].view(e, e, e), want + v)) for v in range(len(vars_)))
+    del want
+    return ok
+
+
 def run_extras(torch, dist, ctx, dev, rank, world, peak):
     """Per-kernel GB/s at BASELINE sizes (configs[2..4]) and the halo exchange on the N-rank grid."""
     out = {}
@@ -684,18 +698,6 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
 
-    def ghosts_are_periodic_images(vars_, g, hw):
-        """Every rank holds var[i] = i + v, so after an exchange on ANY rank grid each ghost cell must hold the value of
-        its periodic image inside the owned box, and owned cells must be untouched (tests/test_comm_gpu.py: the full-size
-        property test).  Checked on the device, all variables."""
-        e = g + 2 * hw
-        idx = torch.arange(e, device=dev)
-        src = ((idx - hw) % g) + hw
-        want = (src.view(e, 1, 1) * e * e + src.view(1, e, 1) * e + src.view(1, 1, e)).to(torch.float64)
-        ok = all(bool(torch.equal(vars_[v].view(e, e, e), want + v)) for v in range(len(vars_)))
-        del want
-        return ok
-
     halo = None
     for g in (512, 1024):
         hw, nv, reps = 1, 3, (100 if g == 512 else 40)
@@ -721,7 +723,7 @@ def run_extras(torch, dist, ctx, dev, rank, world, peak):
             plan.connect_ptrs([0])
         ms = graph_ms(plan.exchange, reps)
         plan.status()                                          # raises if any rank's unpack timed out on a message
-        verified = ghosts_are_periodic_images(vars_, g, hw)
+        verified = ghosts_are_periodic_images(torch, vars_, g, hw, dev)
         if world > 1:
             t = torch.tensor([ms, 0.0 if verified else 1.0], **f64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

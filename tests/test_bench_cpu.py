@@ -98,3 +98,54 @@ def test_ncu_traffic_is_refused_unless_it_is_of_the_launch_this_run_makes(bench,
     assert got is None and "n =" in why
     got, why = bench.ncu_traffic(Ctx((512, 0, 2)), "Stream_COPY", 1 << 28)
     assert got is None and "no ncu capture" in why
+
+
+def test_device_side_suite_data_is_bit_identical_to_the_oracle(bench):
+    """bench.py generates the suite's input arrays on the device with torch arithmetic; the same expressions on CPU tensors must
+    reproduce initData (common/DataUtils.cpp:504-513: (factor*(i+1.1))/(i+1.12345)) bit for bit, shards included."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    n = 300001
+    for factor, count in ((0.2, 0), (0.1, 1)):
+        want = oracle.init_real(n, count)
+        got = bench.init_real_dev(torch, n, factor, "cpu").numpy()
+        assert np.array_equal(got.view(np.int64), want.view(np.int64))
+    # a shard of a larger array (the sharded REDUCE_SUM of the N > 1 path): elements [first, first + m) of the same sequence
+    whole = oracle.init_real(n, 0)
+    for first, m in ((0, 7), (12345, 100000), (n - 5, 5)):
+        got = bench.init_real_dev_range(torch, first, m, 0.2, "cpu").numpy()
+        assert np.array_equal(got.view(np.int64), whole[first:first + m].view(np.int64))
+    # far into an 8-GPU array (rank 7 of 8 x 2^27): still the closed form, evaluated in double
+    first = 7 * (1 << 27) + 3
+    got = bench.init_real_dev_range(torch, first, 4, 0.2, "cpu").numpy()
+    i = np.arange(first, first + 4, dtype=np.float64)
+    assert np.array_equal(got, (0.2 * (i + 1.1)) / (i + 1.12345))
+    assert bench.init_scalar(0.2) == (0.2 * 1.1) / 1.12345
+
+
+@pytest.mark.parametrize("pdims", [(1, 1, 1), (2, 2, 2), (3, 1, 2)])
+@pytest.mark.parametrize("g,hw,nv", [(6, 1, 3), (10, 2, 2)])
+def test_halo_verification_accepts_the_simulated_exchange_and_rejects_a_wrong_cell(bench, pdims, g, hw, nv):
+    """`halo_exchange.verified` rests on ghosts_are_periodic_images(): it must hold for every rank of the CPU simulation of the
+    reference's exchange (HALO_EXCHANGE_FUSED-Seq.cpp:35-116) on any rank grid, fail before the exchange, and fail when a
+    single ghost or owned cell is off."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_comm_gpu import simulate_exchange
+    e = g + 2 * hw
+    fresh = [torch.arange(e ** 3, dtype=torch.float64) + v for v in range(nv)]
+    assert not bench.ghosts_are_periodic_images(torch, fresh, g, hw, "cpu")          # ghost cells not exchanged yet
+    ranks = simulate_exchange((g, g, g), hw, nv, pdims, 2)
+    for vs in ranks:
+        tv = [torch.from_numpy(v.copy()) for v in vs]
+        assert bench.ghosts_are_periodic_images(torch, tv, g, hw, "cpu")
+    tv = [torch.from_numpy(v.copy()) for v in ranks[-1]]
+    tv[nv - 1][0] += 1.0                                                           # a corner ghost cell
+    assert not bench.ghosts_are_periodic_images(torch, tv, g, hw, "cpu")
+    tv[nv - 1][0] -= 1.0
+    assert bench.ghosts_are_periodic_images(torch, tv, g, hw, "cpu")
+    centre = ((e // 2) * e + e // 2) * e + e // 2
+    tv[0][centre] = -7.0                                                           # an owned cell
+    assert not bench.ghosts_are_periodic_images(torch, tv, g, hw, "cpu")
