@@ -315,6 +315,16 @@ def cpu_kernels_reference(budget_s=75.0):
     return out
 
 
+def workload_config(n, n_gpus):
+    """`config` of the JSON line -- the SAME dict for both arms (the driver compares them): it names the workload, not the
+    implementation; what ran it is in `arm`."""
+    return {"workload": f"Stream group COPY/MUL/ADD/TRIAD/DOT, --size {n} doubles per GPU (BASELINE.json configs[1]); "
+                        "one step = one rep of each kernel",
+            "bytes_per_step_per_gpu": STEP_BYTES_PER_ELEM * n,
+            "l2": "each array is 2 GiB >> 126 MB L2 (and >> the host's last-level cache): no flush needed between iterations",
+            "parallelism": f"weak scaling over {n_gpus} GPU(s): one --size problem per GPU (suite SPMD model), DOT all-reduced across ranks"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -325,8 +335,9 @@ def run_reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic (suite initData formula)",
-        "config": {"workload": f"Stream group COPY/MUL/ADD/TRIAD/DOT, --size {n} doubles, Base_OpenMP on host cores",
-                   "threads": threads},
+        "config": workload_config(n, args.gpus),
+        "arm": f"the reference's Base_OpenMP kernels on this box's host cores ({threads} threads; kind = {kind}); one --size problem "
+               "whatever N is: GB/s does not depend on how many problems are queued",
         "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -461,11 +472,8 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (suite initData formula, generated on the device)",
-            "config": {"workload": f"Stream group COPY/MUL/ADD/TRIAD/DOT, Base_B200, --size {n} doubles per GPU "
-                                   "(BASELINE.json configs[1]); one step = one rep of each kernel",
-                       "bytes_per_step_per_gpu": STEP_BYTES_PER_ELEM * n,
-                       "l2": "each array is 2 GiB >> 126 MB L2: no flush needed between iterations",
-                       "parallelism": f"{world} independent --size problems (suite SPMD model), DOT all-reduced"},
+            "config": workload_config(n, world),
+            "arm": f"Base_B200 (librpb200.so through the C ABI) on {world} B200(s), one rank per GPU",
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 5 * K, "clocks": clocks,
             "kernels": kernels, "halo_exchange": halo, "dot_value": dot_value,
         }

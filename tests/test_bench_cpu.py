@@ -46,6 +46,9 @@ def test_reference_arm_prints_the_contract_line(bench, monkeypatch):
     assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    # both arms print the SAME config (it names the workload; the implementation is in `arm`)
+    assert line["config"] == bench.workload_config(1 << 20, 1) and "Base_OpenMP" in line["arm"]
+    assert "Base_B200" not in json.dumps(line["config"]) and "OpenMP" not in json.dumps(line["config"])
     # ranks other than 0 print nothing
     buf = io.StringIO()
     with redirect_stdout(buf):
