@@ -65,6 +65,50 @@ MPI_CASES += [("Comm_HALO_PACKING_FUSED", 0, 1, [], 1), ("Comm_HALO_PACKING_FUSE
               ("Comm_HALO_PACKING", 0, 1, [], 1)]
 
 
+def fuzz_cases(n_per_kernel, seed):
+    """Seeded random (size, reps, flags) draws per kernel: ragged sizes around the kernels' tile boundaries (8192-element
+    tiles, 2048-element halo chunks, 8-element PA batches), odd LTIMES shapes, halo widths 1-3 with 1-6 variables, and for the
+    MPI-only kernels random rank grids of 1-8 ranks.  (kernel, size, reps, flags, ranks); ranks = 0 marks a case of the
+    non-MPI binary."""
+    import random
+    rng = random.Random(seed)
+
+    def near(*anchors):
+        a = rng.choice(anchors)
+        return max(1, a + rng.choice([-3, -1, 0, 1, 2, 7]) + (rng.randrange(0, a) if rng.random() < 0.3 else 0))
+
+    out = []
+    for k in ["Stream_COPY", "Stream_MUL", "Stream_ADD", "Stream_TRIAD", "Stream_DOT", "Algorithm_REDUCE_SUM", "Algorithm_SCAN",
+              "Algorithm_SORT", "Algorithm_SORTPAIRS", "Basic_INDEXLIST", "Basic_INDEXLIST_3LOOP", "Algorithm_MEMCPY", "Algorithm_MEMSET"]:
+        for _ in range(n_per_kernel):
+            out.append((k, near(5, 33, 257, 2048, 8192, 16384, 3 * 8192, 65536, 200000), rng.randint(1, 4), [], 0))
+    for k in ["Apps_MASS3DPA", "Apps_DIFFUSION3DPA", "Apps_CONVECTION3DPA"]:
+        for _ in range(n_per_kernel):
+            out.append((k, near(70, 125 * 7, 125 * 8 + 60, 64 * 9, 64 * 33, 20000), rng.randint(1, 3), [], 0))
+    for _ in range(n_per_kernel):
+        d, g, m = rng.choice([1, 3, 8, 17, 32, 64, 70]), rng.choice([1, 2, 8, 13, 32]), rng.choice([1, 5, 17, 25, 31])
+        flags = ["--ltimes_num_d", str(d), "--ltimes_num_g", str(g), "--ltimes_num_m", str(m)] if rng.random() < 0.7 else []
+        out.append(("Apps_LTIMES", near(2048, 2048 * 9, 50000, 150000), rng.randint(1, 3), flags, 0))
+    for _ in range(n_per_kernel):
+        out.append(("Polybench_GEMM", near(1, 50, 900, 4096, 30000), rng.randint(1, 2), [], 0))
+
+    def halo_flags():
+        w, nv = rng.randint(1, 3), rng.randint(1, 6)
+        side = rng.randint(2 * w, 34)                       # a box at least as wide as two halos in every direction
+        return side ** 3 + rng.choice([0, 0, 1, 5]), ["--halo_width", str(w), "--halo_num_vars", str(nv)]
+    for k in ["Comm_HALO_PACKING_FUSED", "Comm_HALO_PACKING"]:
+        for _ in range(n_per_kernel):
+            size, fl = halo_flags()
+            out.append((k, size, rng.randint(1, 3), fl, 0))
+    grids = [(1, 1, 1), (2, 1, 1), (1, 2, 1), (1, 1, 2), (3, 1, 1), (2, 2, 1), (2, 1, 2), (5, 1, 1), (3, 2, 1), (1, 2, 3), (7, 1, 1), (2, 2, 2), (4, 2, 1)]
+    for k in ["Comm_HALO_EXCHANGE_FUSED", "Comm_HALO_EXCHANGE", "Comm_HALO_SENDRECV"]:
+        for _ in range(n_per_kernel):
+            size, fl = halo_flags()
+            gx, gy, gz = rng.choice(grids)
+            out.append((k, size, rng.randint(1, 3), fl + ["--mpi_3d_division", str(gx), str(gy), str(gz)], gx * gy * gz))
+    return out
+
+
 def mpirun(nranks, cmd, timeout=600):
     """P processes of `cmd` over the stub's shared-memory transport (oracle/mpi_stub/mpi_stub.c): one zero-filled arena
     under /dev/shm, RPB_MPI_SIZE / RPB_MPI_RANK / RPB_MPI_SHM in the environment; rank 0 writes the reports."""
@@ -123,13 +167,41 @@ def run_case(exe, kernel, size, reps, extra, workdir, ranks=1):
     return m.group(1)
 
 
+def fuzz_main(a):
+    plain = os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe")
+    mpi = os.path.join(ROOT, "oracle", "_ref", "raja-perf-mpi1.exe")
+    work = os.path.join(ROOT, "build", "golden_work")
+    os.makedirs(work, exist_ok=True)
+    rows = []
+    for kernel, size, reps, extra, ranks in fuzz_cases(a.fuzz, a.seed):
+        try:
+            ck = run_case(mpi if ranks else plain, kernel, size, reps, extra, work, max(ranks, 1))
+        except Exception as e:                    # the reference itself refuses or crashes on this input: not a golden
+            print("SKIPPED", kernel, size, reps, extra, ranks, str(e)[:120], file=sys.stderr)
+            continue
+        rows.append({"kernel": kernel, "size": size, "reps": reps, "flags": extra, "variant": "Base_Seq", "checksum": ck, "ranks": ranks})
+        print(kernel, size, reps, extra, ranks, ck, file=sys.stderr)
+    out = a.out or os.path.join(ROOT, "tests", "golden", "ref_checksums_fuzz.json")
+    json.dump({"source": "reference raja-perf.exe / raja-perf-mpi1.exe (suite v2024.07.0, commit 9af20b3; the CPU-only builds of "
+                         "oracle/build_ref.sh and oracle/build_ref_mpi.sh), g++ 13.3 -O3, glibc rand(), x87 long double",
+               "command": f"python tests/golden/make_golden.py --fuzz {a.fuzz} --seed {a.seed}   (ranks = 0: the non-MPI binary; "
+                          "ranks >= 1: P processes of the MPI-stub binary, the checksum is the report's average over the ranks)",
+               "cases": rows}, open(out, "w"), indent=1)
+    print(f"wrote {len(rows)} cases to {out}", file=sys.stderr)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--exe", default=os.path.join(ROOT, "oracle", "_ref", "raja-perf.exe"))
     ap.add_argument("--out", default=None)
     ap.add_argument("--mpi", action="store_true", help="the MPI-only Comm kernels from the one-rank MPI-stub build")
     ap.add_argument("--dryrun", action="store_true", help="the --dryrun tables of the MPI-stub build (all 23 kernels) -> ref_dryrun.json")
+    ap.add_argument("--fuzz", type=int, default=0, help="N seeded random cases per kernel from both binaries -> ref_checksums_fuzz.json")
+    ap.add_argument("--seed", type=int, default=20261018)
     a = ap.parse_args()
+    if a.fuzz:
+        fuzz_main(a)
+        return
     if a.dryrun:
         exe = os.path.join(ROOT, "oracle", "_ref", "raja-perf-mpi1.exe")
         out = a.out or os.path.join(ROOT, "tests", "golden", "ref_dryrun.json")

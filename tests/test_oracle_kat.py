@@ -13,6 +13,9 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_che
 # the kernels the reference compiles only WITH MPI, from the unmodified sources linked against the one-rank MPI
 # stand-in of oracle/mpi_stub (oracle/build_ref_mpi.sh; generator: tests/golden/make_golden.py --mpi)
 GOLD_MPI1 = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums_mpi1.json")))
+# seeded random draws from both reference binaries (make_golden.py --fuzz): ragged sizes around the tile boundaries, odd
+# LTIMES shapes, halo widths 1-3 with 1-6 variables, random rank grids of 1-8 ranks for the MPI-only kernels
+GOLD_FUZZ = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_checksums_fuzz.json")))
 
 
 def _iparams(kernel, flags, ranks=1):
@@ -51,6 +54,17 @@ def test_oracle_reproduces_reference_exchange_checksums(case):
     got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"], case["ranks"]))
     ref = np.longdouble(case["checksum"])
     tol = np.longdouble(2e-19) if case["ranks"] == 1 else np.longdouble(1e-18)      # + the rounding of the rank average
+    assert abs(got - ref) <= abs(ref) * tol, (got, ref)
+
+
+@pytest.mark.parametrize("case", GOLD_FUZZ["cases"],
+                         ids=lambda c: f"{c['kernel']}-s{c['size']}-r{c['reps']}-p{c['ranks']}-{'_'.join(x for x in c['flags'] if not x.startswith('--'))}")
+def test_oracle_reproduces_reference_checksums_on_random_inputs(case):
+    """184 more pins: the oracle against the unmodified reference on inputs nobody picked by hand."""
+    ranks = max(case["ranks"], 1)
+    got = oracle.kat(case["kernel"], case["size"], case["reps"], _iparams(case["kernel"], case["flags"], ranks))
+    ref = np.longdouble(case["checksum"])
+    tol = np.longdouble(2e-19) if ranks == 1 else np.longdouble(1e-18)               # + the rounding of the rank average
     assert abs(got - ref) <= abs(ref) * tol, (got, ref)
 
 
