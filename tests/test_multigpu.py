@@ -14,6 +14,11 @@ def test_rank_grid_follows_the_reference_factorisation():
     from rajaperf_b200.dist import rank_grid
     assert [rank_grid(p) for p in (1, 2, 3, 4, 6, 8, 12, 16)] == \
         [[1, 1, 1], [2, 1, 1], [3, 1, 1], [2, 2, 1], [2, 3, 1], [2, 2, 2], [2, 2, 3], [4, 2, 2]]
+    # what the unmodified reference prints ("3D division = a x b x c") when P processes of its MPI build start over the MPI
+    # stand-in:  python tools/mpirun_stub.py -n P -- oracle/_ref/raja-perf-mpi1.exe --dryrun -k Comm_HALO_EXCHANGE_FUSED
+    printed = {1: [1, 1, 1], 2: [2, 1, 1], 3: [3, 1, 1], 5: [5, 1, 1], 6: [2, 3, 1], 7: [7, 1, 1], 8: [2, 2, 2], 9: [3, 3, 1],
+               10: [2, 5, 1], 12: [2, 2, 3], 16: [4, 2, 2], 18: [2, 3, 3], 24: [6, 2, 2], 27: [3, 3, 3], 30: [2, 3, 5], 32: [4, 4, 2]}
+    assert {p: rank_grid(p) for p in printed} == printed
 
 
 def test_shard_ranges_cover_and_align():
