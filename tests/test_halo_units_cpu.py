@@ -127,3 +127,20 @@ def test_ragged_generic_tuples(order):
     check(pack, unpack, order)
     check(pack, [], order)
     check([], unpack, order)
+
+
+def test_random_plan_geometries_every_chunk_once_in_every_order():
+    """Seeded random boxes (non-cubic, thin, wider halos, 1-4 variables -- 4 x 26 tuples is the most the one-launch kernels keep in
+    shared memory; beyond that the library falls back to two launches): the property the kernels' traversal needs."""
+    rng = np.random.default_rng(20261018)
+    seen_x_units = 0
+    for _ in range(30):
+        hw = int(rng.choice([1, 1, 1, 2, 3]))
+        dims = tuple(int(x) for x in rng.choice([hw, 2 * hw, 7, 33, 64, 129, 200], size=3))
+        nv = int(rng.integers(1, 5))
+        pack, unpack = plan_tuples(dims, hw, nv)
+        for order in (1, 3, 5, 0, 6):
+            items, first, _ = check(pack, unpack, order)
+            if order == 1:
+                seen_x_units += sum(1 for a, b in zip(first, first[1:]) if b - a == 4)
+    assert seen_x_units > 0                                           # some of the boxes were big enough to have x units
